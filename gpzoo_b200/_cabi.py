@@ -1,0 +1,89 @@
+"""ctypes binding of include/gpzoo_b200.h.
+
+The CUDA shared library is the product: if it is missing or a call fails, this module raises — there is
+no PyTorch / CPU fallback anywhere in the package.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libgpzoo_b200.so")
+_lib = None
+_lock = threading.Lock()
+launch_count = 0          # number of C-ABI compute calls issued (bench.py reports kernel launches from this)
+
+c_i, c_i64, c_f, c_d, c_p = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_double, ctypes.c_void_p
+
+
+class GpzError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise GpzError(
+                        f"{LIB_PATH} not found: build it with `python -m gpzoo_b200.build` "
+                        "(gpzoo_b200 has no CPU or PyTorch fallback)")
+                l = ctypes.CDLL(LIB_PATH)
+                l.gpz_error_string.restype = ctypes.c_char_p
+                l.gpz_error_string.argtypes = [c_i]
+                l.gpz_abi_version.restype = c_i
+                for suf in ("f32", "f64"):
+                    getattr(l, f"gpz_poisson_workspace_bytes_{suf}").restype = c_i64
+                _lib = l
+    return _lib
+
+
+def _suffix(dtype):
+    if dtype == torch.float32:
+        return "f32", c_f
+    if dtype == torch.float64:
+        return "f64", c_d
+    raise GpzError(f"gpzoo_b200 computes in float32 or float64, got {dtype}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL).  Tensors must be contiguous CUDA tensors."""
+    if t is None:
+        return c_p(0)
+    if not t.is_cuda:
+        raise GpzError("gpzoo_b200 kernels need CUDA tensors (no CPU path exists)")
+    if not t.is_contiguous():
+        raise GpzError("internal error: non-contiguous tensor passed to the C ABI")
+    return c_p(t.data_ptr())
+
+
+def stream():
+    return c_p(torch.cuda.current_stream().cuda_stream)
+
+
+def call(name, dtype, *args):
+    """Invoke gpz_<name>_<f32|f64>(*args, stream) and raise on a non-zero return code."""
+    global launch_count
+    suf, _ = _suffix(dtype)
+    fn = getattr(lib(), f"gpz_{name}_{suf}")
+    rc = fn(*args, stream())
+    launch_count += 1
+    if rc != 0:
+        raise GpzError(f"gpz_{name}_{suf} failed: {lib().gpz_error_string(rc).decode()} (rc={rc})")
+
+
+def scalar(dtype, v):
+    return _suffix(dtype)[1](float(v))
+
+
+def exported_symbols():
+    """Every symbol include/gpzoo_b200.h declares (used by the CPU test that the library exports them)."""
+    import re
+    hdr = os.path.join(os.path.dirname(_HERE), "include", "gpzoo_b200.h")
+    txt = open(hdr).read()
+    return sorted(set(re.findall(r"\b(gpz_[a-z0-9_]+)\s*\(", txt)))

@@ -1,0 +1,13 @@
+// ABI version and error strings.
+#include "common.cuh"
+#include "gpzoo_b200.h"
+
+extern "C" int gpz_abi_version(void) { return 1; }
+
+extern "C" const char* gpz_error_string(int rc) {
+  if (rc == 0) return "success";
+  if (rc == GPZ_ERR_BADARG) return "gpzoo_b200: bad argument";
+  if (rc == GPZ_ERR_UNSUPPORTED) return "gpzoo_b200: unsupported size (see limits in csrc/*.cu)";
+  if (rc < 0 && rc > -1000) return cudaGetErrorString((cudaError_t)(-rc));
+  return "gpzoo_b200: unknown error";
+}

@@ -1,0 +1,341 @@
+// K1: fused pairwise-distance + exp kernel-matrix build and its backward.
+//
+// Replaces  torch.cdist(X,Z)**2 -> expand(L) -> /l^2 -> exp -> *sigma^2   (kernels.py:114-130, 141-155)
+// and the multi-group form with group-distance scaling                   (kernels.py:172-191, 204-228):
+//
+//   K[l,i,j] = sigma_l^2 * exp(-0.5 * |x1_i - x2_j|^2 / (ls_l^2 * den)) / den^(p/2),   den = a_l * r2[g1_i, g2_j] + 1
+//
+// (den = 1 without groups).  d^2 is a direct sum of squared differences (never |x|^2+|z|^2-2xz), which is
+// what makes fp32 results track the fp64 reference.  Output layout L x n1 x n2, n2 contiguous.
+// HBM-bound: one pass writes 4*L*n1*n2 bytes; each thread owns 4 consecutive j and streams float4 stores.
+#include "common.cuh"
+#include "gpzoo_b200.h"
+
+namespace gpz {
+
+constexpr int KB_DMAX = 4;      // spatial dimension supported by the kernels (reference uses D = 1 or 2)
+constexpr int KB_LMAX = 32;     // factors handled per launch by the backward (host loops over chunks)
+constexpr int KB_ROWS = 16;     // rows (i) per CTA
+constexpr int KB_THREADS = 256;
+constexpr int KB_VEC = 4;       // consecutive j per thread
+constexpr int KB_GMAX = 64;     // max number of groups (r2 table kept in shared memory)
+
+template <typename T> struct KBArgs {
+  const T* x1; const T* x2;         // n1 x D, n2 x D
+  const T* sigma; const T* ls;      // L
+  const T* a;                       // L  group-difference coefficient (already squared / abs'd by the host); MG only
+  const T* r2;                      // ng x ng squared embedding distances; MG only
+  const int64_t* g1; const int64_t* g2;
+  int n1, n2, D, L, ng;
+  T p_half;                         // input_dim / 2
+  T jitter;                         // added to K[l,i,i] (add_jitter, utilities.py:407-418); 0 for cross matrices
+};
+
+template <typename T> struct Vec4 { T v[4]; };
+
+template <typename T, bool MG, bool ALIGNED>
+__global__ void __launch_bounds__(KB_THREADS) kbuild_fwd_kernel(const KBArgs<T> a, T* __restrict__ out) {
+  __shared__ T s_c[KB_LMAX * 8], s_s2[KB_LMAX * 8], s_a[KB_LMAX * 8];
+  __shared__ T s_r2[MG ? KB_GMAX * KB_GMAX : 1];
+  const int tid = threadIdx.x;
+  for (int l = tid; l < a.L; l += KB_THREADS) {
+    const T ls = a.ls[l], sg = a.sigma[l];
+    s_c[l] = T(-0.5) / (ls * ls);
+    s_s2[l] = sg * sg;
+    if (MG) s_a[l] = a.a[l];
+  }
+  if (MG) for (int e = tid; e < a.ng * a.ng; e += KB_THREADS) s_r2[e] = a.r2[e];
+  __syncthreads();
+
+  const int64_t j0 = ((int64_t)blockIdx.x * KB_THREADS + tid) * KB_VEC;
+  if (j0 >= a.n2) return;
+  const int nv = (int)min((int64_t)KB_VEC, a.n2 - j0);
+  T xj[KB_DMAX][KB_VEC];
+  int gj[KB_VEC];
+#pragma unroll
+  for (int v = 0; v < KB_VEC; ++v) {
+#pragma unroll
+    for (int d = 0; d < KB_DMAX; ++d) xj[d][v] = (v < nv && d < a.D) ? a.x2[(j0 + v) * a.D + d] : T(0);
+    gj[v] = (MG && v < nv) ? (int)a.g2[j0 + v] : 0;
+  }
+  const int i0 = blockIdx.y * KB_ROWS, i1 = min(i0 + KB_ROWS, a.n1);
+  for (int i = i0; i < i1; ++i) {
+    T d2[KB_VEC], r2[KB_VEC];
+#pragma unroll
+    for (int v = 0; v < KB_VEC; ++v) d2[v] = T(0);
+#pragma unroll
+    for (int d = 0; d < KB_DMAX; ++d) {
+      if (d < a.D) {
+        const T xi = a.x1[(int64_t)i * a.D + d];
+#pragma unroll
+        for (int v = 0; v < KB_VEC; ++v) { const T df = xi - xj[d][v]; d2[v] = fma(df, df, d2[v]); }
+      }
+    }
+    if (MG) {
+      const int gi = (int)a.g1[i];
+#pragma unroll
+      for (int v = 0; v < KB_VEC; ++v) r2[v] = s_r2[gi * a.ng + gj[v]];
+    }
+    for (int l = 0; l < a.L; ++l) {
+      const T c = s_c[l], s2 = s_s2[l];
+      Vec4<T> k;
+#pragma unroll
+      for (int v = 0; v < KB_VEC; ++v) {
+        T val;
+        if (MG) {
+          const T den = fma(s_a[l], r2[v], T(1));
+          const T sc = a.p_half == T(1) ? T(1) / den : Num<T>::pow(den, -a.p_half);
+          val = s2 * Num<T>::exp(c * d2[v] / den) * sc;
+        } else {
+          val = s2 * Num<T>::exp(c * d2[v]);
+        }
+        if (a.jitter != T(0) && (int64_t)i == j0 + v) val += a.jitter;
+        k.v[v] = val;
+      }
+      T* o = out + ((int64_t)l * a.n1 + i) * a.n2 + j0;
+      if (ALIGNED && nv == KB_VEC) {
+        if (sizeof(T) == 4) {
+          __stcs(reinterpret_cast<float4*>(o), make_float4((float)k.v[0], (float)k.v[1], (float)k.v[2], (float)k.v[3]));
+        } else {
+          __stcs(reinterpret_cast<double2*>(o), make_double2((double)k.v[0], (double)k.v[1]));
+          __stcs(reinterpret_cast<double2*>(o) + 1, make_double2((double)k.v[2], (double)k.v[3]));
+        }
+      } else {
+        for (int v = 0; v < nv; ++v) o[v] = k.v[v];
+      }
+    }
+  }
+}
+
+// Backward: given G = dLoss/dK (L x n1 x n2) recompute K and reduce
+//   g_sigma[l] += (2/sigma_l) sum G K0                       (K0 without jitter)
+//   g_ls[l]    += sum G K0 d2 / (ls^3 den)
+//   g_a[l]     += sum G K0 (0.5 d2/(ls^2 den^2) - p_half/den) r2             (MG)
+//   g_x1[i,:]  -= sum_{l,j} G K0 (x1_i - x2_j)/(ls^2 den) ;  g_x2[j,:] += same
+// One CTA covers KB_ROWS rows x (KB_THREADS*4) columns; the L accumulators live in registers.
+template <typename T, bool MG, bool ALIGNED>
+__global__ void __launch_bounds__(KB_THREADS) kbuild_bwd_kernel(const KBArgs<T> a, const T* __restrict__ G, int l0, int Lc,
+                                                                 T* __restrict__ g_x1, T* __restrict__ g_x2,
+                                                                 T* __restrict__ g_sigma, T* __restrict__ g_ls,
+                                                                 T* __restrict__ g_a) {
+  __shared__ T s_c[KB_LMAX], s_s2[KB_LMAX], s_a[KB_LMAX];
+  __shared__ T s_r2[MG ? KB_GMAX * KB_GMAX : 1];
+  __shared__ T s_red[32];
+  __shared__ T s_row[KB_ROWS][KB_DMAX][KB_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int l = tid; l < Lc; l += KB_THREADS) {
+    const T ls = a.ls[l0 + l], sg = a.sigma[l0 + l];
+    s_c[l] = T(-0.5) / (ls * ls);
+    s_s2[l] = sg * sg;
+    if (MG) s_a[l] = a.a[l0 + l];
+  }
+  if (MG) for (int e = tid; e < a.ng * a.ng; e += KB_THREADS) s_r2[e] = a.r2[e];
+  __syncthreads();
+
+  const int64_t j0 = ((int64_t)blockIdx.x * KB_THREADS + tid) * KB_VEC;
+  const int nv = j0 < a.n2 ? (int)min((int64_t)KB_VEC, a.n2 - j0) : 0;
+  T xj[KB_DMAX][KB_VEC];
+  int gj[KB_VEC];
+#pragma unroll
+  for (int v = 0; v < KB_VEC; ++v) {
+#pragma unroll
+    for (int d = 0; d < KB_DMAX; ++d) xj[d][v] = (v < nv && d < a.D) ? a.x2[(j0 + v) * a.D + d] : T(0);
+    gj[v] = (MG && v < nv) ? (int)a.g2[j0 + v] : 0;
+  }
+  T acc_s[KB_LMAX], acc_l[KB_LMAX], acc_a[MG ? KB_LMAX : 1];
+#pragma unroll
+  for (int l = 0; l < KB_LMAX; ++l) { acc_s[l] = T(0); acc_l[l] = T(0); if (MG) acc_a[l] = T(0); }
+  T gx2[KB_DMAX][KB_VEC];
+#pragma unroll
+  for (int d = 0; d < KB_DMAX; ++d)
+#pragma unroll
+    for (int v = 0; v < KB_VEC; ++v) gx2[d][v] = T(0);
+
+  const int i0 = blockIdx.y * KB_ROWS, i1 = min(i0 + KB_ROWS, a.n1);
+  for (int i = i0; i < i1; ++i) {
+    T df[KB_DMAX][KB_VEC], d2[KB_VEC], r2[KB_VEC], w[KB_VEC];   // w = sum_l G K0 /(ls^2 den)
+#pragma unroll
+    for (int v = 0; v < KB_VEC; ++v) { d2[v] = T(0); w[v] = T(0); r2[v] = T(0); }
+#pragma unroll
+    for (int d = 0; d < KB_DMAX; ++d) {
+      const T xi = d < a.D ? a.x1[(int64_t)i * a.D + d] : T(0);
+#pragma unroll
+      for (int v = 0; v < KB_VEC; ++v) { df[d][v] = xi - xj[d][v]; d2[v] = fma(df[d][v], df[d][v], d2[v]); }
+    }
+    if (MG) {
+      const int gi = (int)a.g1[i];
+#pragma unroll
+      for (int v = 0; v < KB_VEC; ++v) r2[v] = s_r2[gi * a.ng + gj[v]];
+    }
+    if (nv > 0) {
+#pragma unroll
+      for (int l = 0; l < KB_LMAX; ++l) {
+        if (l < Lc) {
+          const T c = s_c[l], s2 = s_s2[l];
+          const T* gp = G + ((int64_t)(l0 + l) * a.n1 + i) * a.n2 + j0;
+          T g[KB_VEC];
+          if (ALIGNED && nv == KB_VEC) {
+            if (sizeof(T) == 4) {
+              const float4 t = __ldcs(reinterpret_cast<const float4*>(gp));
+              g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
+            } else {
+              const double2 t0 = __ldcs(reinterpret_cast<const double2*>(gp));
+              const double2 t1 = __ldcs(reinterpret_cast<const double2*>(gp) + 1);
+              g[0] = t0.x; g[1] = t0.y; g[2] = t1.x; g[3] = t1.y;
+            }
+          } else {
+#pragma unroll
+            for (int v = 0; v < KB_VEC; ++v) g[v] = v < nv ? gp[v] : T(0);
+          }
+#pragma unroll
+          for (int v = 0; v < KB_VEC; ++v) {
+            T k0, idn;
+            if (MG) {
+              const T den = fma(s_a[l], r2[v], T(1));
+              idn = T(1) / den;
+              const T sc = a.p_half == T(1) ? idn : Num<T>::pow(den, -a.p_half);
+              k0 = s2 * Num<T>::exp(c * d2[v] * idn) * sc;
+            } else {
+              idn = T(1);
+              k0 = s2 * Num<T>::exp(c * d2[v]);
+            }
+            const T gk = g[v] * k0;
+            const T u = gk * (T(-2) * c) * idn;          // G K0 / (ls^2 den)
+            acc_s[l] += gk;
+            acc_l[l] = fma(u, d2[v], acc_l[l]);          // later divided by ls
+            if (MG) acc_a[l] = fma(gk * r2[v], (T(-1) * c * d2[v] * idn - a.p_half) * idn, acc_a[l]);
+            w[v] += u;
+          }
+        }
+      }
+    }
+    // row reduction for g_x1[i,:]
+#pragma unroll
+    for (int d = 0; d < KB_DMAX; ++d) {
+      if (d < a.D) {
+        T r = T(0);
+#pragma unroll
+        for (int v = 0; v < KB_VEC; ++v) { r = fma(w[v], df[d][v], r); gx2[d][v] = fma(w[v], df[d][v], gx2[d][v]); }
+        r = warp_sum(r);
+        if (lane == 0) s_row[i - i0][d][warp] = r;
+      }
+    }
+  }
+  __syncthreads();
+  if (g_x1 != nullptr) {
+    for (int e = tid; e < (i1 - i0) * a.D; e += KB_THREADS) {
+      const int ii = e / a.D, d = e % a.D;
+      T r = T(0);
+#pragma unroll
+      for (int wv = 0; wv < KB_THREADS / 32; ++wv) r += s_row[ii][d][wv];
+      atomicAdd(g_x1 + (int64_t)(i0 + ii) * a.D + d, -r);
+    }
+  }
+  if (g_x2 != nullptr) {
+    for (int v = 0; v < nv; ++v)
+#pragma unroll
+      for (int d = 0; d < KB_DMAX; ++d)
+        if (d < a.D) atomicAdd(g_x2 + (j0 + v) * a.D + d, gx2[d][v]);
+  }
+#pragma unroll
+  for (int l = 0; l < KB_LMAX; ++l) {
+    if (l < Lc) {                                   // uniform across the block
+      T v = block_sum<T>(acc_s[l], s_red);
+      if (tid == 0) atomicAdd(g_sigma + l0 + l, v * T(2) / a.sigma[l0 + l]);
+      v = block_sum<T>(acc_l[l], s_red);
+      if (tid == 0) atomicAdd(g_ls + l0 + l, v / a.ls[l0 + l]);
+      if (MG) {
+        v = block_sum<T>(acc_a[l], s_red);
+        if (tid == 0 && g_a != nullptr) atomicAdd(g_a + l0 + l, v);
+      }
+    }
+  }
+}
+
+// plain Euclidean distance matrix (n1 x n2) by direct differences: kernel(X, Z, return_distance=True)
+// (kernels.py:118-124) without cdist's matmul path.
+template <typename T>
+__global__ void cdist_kernel(const T* __restrict__ x1, const T* __restrict__ x2, T* __restrict__ out, int n1, int n2, int D) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)n1 * n2) return;
+  const int i = (int)(e / n2), j = (int)(e % n2);
+  T d2 = T(0);
+  for (int d = 0; d < D; ++d) { const T df = x1[(int64_t)i * D + d] - x2[(int64_t)j * D + d]; d2 = fma(df, df, d2); }
+  out[e] = Num<T>::sqrt(d2);
+}
+
+template <typename T>
+int kbuild_fwd(const KBArgs<T>& a, T* out, cudaStream_t st) {
+  if (a.D < 1 || a.D > KB_DMAX || a.L < 1 || a.L > KB_LMAX * 8) return GPZ_ERR_UNSUPPORTED;
+  const bool mg = a.g1 != nullptr;
+  if (mg && (a.ng < 1 || a.ng > KB_GMAX)) return GPZ_ERR_UNSUPPORTED;
+  if (a.n1 == 0 || a.n2 == 0) return GPZ_OK;
+  const bool al = (a.n2 % KB_VEC == 0) && ((reinterpret_cast<uintptr_t>(out) & 31) == 0);
+  dim3 grid((unsigned)cdiv(a.n2, (int64_t)KB_THREADS * KB_VEC), (unsigned)cdiv(a.n1, KB_ROWS));
+  if (mg) {
+    if (al) kbuild_fwd_kernel<T, true, true><<<grid, KB_THREADS, 0, st>>>(a, out);
+    else kbuild_fwd_kernel<T, true, false><<<grid, KB_THREADS, 0, st>>>(a, out);
+  } else {
+    if (al) kbuild_fwd_kernel<T, false, true><<<grid, KB_THREADS, 0, st>>>(a, out);
+    else kbuild_fwd_kernel<T, false, false><<<grid, KB_THREADS, 0, st>>>(a, out);
+  }
+  GPZ_CHECK_LAUNCH();
+  return GPZ_OK;
+}
+
+template <typename T>
+int kbuild_bwd(const KBArgs<T>& a, const T* G, T* g_x1, T* g_x2, T* g_sigma, T* g_ls, T* g_a, cudaStream_t st) {
+  if (a.D < 1 || a.D > KB_DMAX || a.L < 1) return GPZ_ERR_UNSUPPORTED;
+  const bool mg = a.g1 != nullptr;
+  if (mg && (a.ng < 1 || a.ng > KB_GMAX)) return GPZ_ERR_UNSUPPORTED;
+  if (g_x1) GPZ_CUDA(cudaMemsetAsync(g_x1, 0, sizeof(T) * a.n1 * a.D, st));
+  if (g_x2) GPZ_CUDA(cudaMemsetAsync(g_x2, 0, sizeof(T) * a.n2 * a.D, st));
+  GPZ_CUDA(cudaMemsetAsync(g_sigma, 0, sizeof(T) * a.L, st));
+  GPZ_CUDA(cudaMemsetAsync(g_ls, 0, sizeof(T) * a.L, st));
+  if (g_a) GPZ_CUDA(cudaMemsetAsync(g_a, 0, sizeof(T) * a.L, st));
+  if (a.n1 == 0 || a.n2 == 0) return GPZ_OK;
+  const bool al = (a.n2 % KB_VEC == 0) && ((reinterpret_cast<uintptr_t>(G) & 31) == 0);
+  dim3 grid((unsigned)cdiv(a.n2, (int64_t)KB_THREADS * KB_VEC), (unsigned)cdiv(a.n1, KB_ROWS));
+  for (int l0 = 0; l0 < a.L; l0 += KB_LMAX) {
+    const int Lc = min(KB_LMAX, a.L - l0);
+    // g_x1/g_x2 accumulate over all l-chunks (atomics), so every chunk launch adds its share
+    if (mg) {
+      if (al) kbuild_bwd_kernel<T, true, true><<<grid, KB_THREADS, 0, st>>>(a, G, l0, Lc, g_x1, g_x2, g_sigma, g_ls, g_a);
+      else kbuild_bwd_kernel<T, true, false><<<grid, KB_THREADS, 0, st>>>(a, G, l0, Lc, g_x1, g_x2, g_sigma, g_ls, g_a);
+    } else {
+      if (al) kbuild_bwd_kernel<T, false, true><<<grid, KB_THREADS, 0, st>>>(a, G, l0, Lc, g_x1, g_x2, g_sigma, g_ls, g_a);
+      else kbuild_bwd_kernel<T, false, false><<<grid, KB_THREADS, 0, st>>>(a, G, l0, Lc, g_x1, g_x2, g_sigma, g_ls, g_a);
+    }
+    GPZ_CHECK_LAUNCH();
+  }
+  return GPZ_OK;
+}
+
+}  // namespace gpz
+
+using namespace gpz;
+
+#define GPZ_KB_IMPL(SUF, T)                                                                                        \
+  extern "C" int gpz_kernel_build_fwd_##SUF(const T* x1, const T* x2, const T* sigma, const T* ls, const T* a,     \
+                                            const T* r2, const int64_t* g1, const int64_t* g2, int n1, int n2,     \
+                                            int D, int L, int ng, T p_half, T jitter, T* out, void* stream) {      \
+    KBArgs<T> k{x1, x2, sigma, ls, a, r2, g1, g2, n1, n2, D, L, ng, p_half, jitter};                               \
+    return kbuild_fwd<T>(k, out, (cudaStream_t)stream);                                                            \
+  }                                                                                                                \
+  extern "C" int gpz_kernel_build_bwd_##SUF(const T* x1, const T* x2, const T* sigma, const T* ls, const T* a,     \
+                                            const T* r2, const int64_t* g1, const int64_t* g2, int n1, int n2,     \
+                                            int D, int L, int ng, T p_half, const T* G, T* g_x1, T* g_x2,          \
+                                            T* g_sigma, T* g_ls, T* g_a, void* stream) {                           \
+    KBArgs<T> k{x1, x2, sigma, ls, a, r2, g1, g2, n1, n2, D, L, ng, p_half, T(0)};                                 \
+    return kbuild_bwd<T>(k, G, g_x1, g_x2, g_sigma, g_ls, g_a, (cudaStream_t)stream);                              \
+  }                                                                                                                \
+  extern "C" int gpz_cdist_##SUF(const T* x1, const T* x2, T* out, int n1, int n2, int D, void* stream) {          \
+    const int64_t total = (int64_t)n1 * n2;                                                                        \
+    if (total == 0) return GPZ_OK;                                                                                 \
+    cdist_kernel<T><<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(x1, x2, out, n1, n2, D);         \
+    GPZ_CHECK_LAUNCH();                                                                                            \
+    return GPZ_OK;                                                                                                 \
+  }
+
+GPZ_KB_IMPL(f32, float)
+GPZ_KB_IMPL(f64, double)

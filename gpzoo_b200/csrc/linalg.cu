@@ -1,0 +1,290 @@
+// K2: batched blocked right-looking Cholesky (gp.py:213,360,55 -> torch.linalg.cholesky) and the
+// blocked triangular inverse used to turn the two triangular solves of torch.cholesky_solve
+// (gp.py:218,365) into triangular matrix products, plus the small O(M^2) element-wise helpers of the
+// variational parameters (lower-Cholesky transform gp.py:220, KL reductions torch kl.py MVN||MVN).
+//
+// Blocked right-looking factorisation, panel width NB: for each panel k
+//   (1) potf2: factor the NB x NB diagonal block in shared memory (one CTA per factor l)
+//   (2) trsm : L21 = A21 L11^-T, one thread per row, panel staged through shared memory
+//   (3) syrk : A22 -= L21 L21^T  -- the only O(M^3) part; a GEMM (gemm_simt.cuh / tcgen05 path)
+#include "gemm_simt.cuh"
+#include "gpzoo_b200.h"
+
+namespace gpz {
+
+constexpr int NB = 64;
+
+// ---- (1) diagonal block ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) potf2_kernel(T* __restrict__ Aall, int M, int k0, int nb, int* __restrict__ info) {
+  __shared__ T s[NB][NB + 1];
+  T* A = Aall + (int64_t)blockIdx.x * M * M;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  for (int e = tid; e < nb * nb; e += 256) {
+    const int i = e / nb, j = e % nb;
+    s[i][j] = j <= i ? A[(int64_t)(k0 + i) * M + k0 + j] : T(0);
+  }
+  for (int j = 0; j < nb; ++j) {
+    __syncthreads();
+    const T d = s[j][j];
+    if (!(d > T(0))) {                       // not positive definite (also catches NaN), LAPACK-style info
+      if (tid == 0 && info[blockIdx.x] == 0) info[blockIdx.x] = k0 + j + 1;
+    }
+    const T inv = T(1) / d;
+    for (int i = j + 1 + ty; i < nb; i += 16)
+      for (int k = j + 1 + tx; k <= i; k += 16) s[i][k] -= s[i][j] * s[k][j] * inv;
+    __syncthreads();
+    const T rs = Num<T>::rsqrt(d);
+    if (tid > j && tid < nb) s[tid][j] *= rs;
+    if (tid == j) s[j][j] = Num<T>::sqrt(d);
+  }
+  __syncthreads();
+  for (int e = tid; e < nb * nb; e += 256) {
+    const int i = e / nb, j = e % nb;
+    A[(int64_t)(k0 + i) * M + k0 + j] = s[i][j];     // upper part of the block written as 0
+  }
+}
+
+// ---- (2) panel solve:  X L11^T = A21  ------------------------------------------------------------
+template <typename T> struct PanelRows { static constexpr int R = sizeof(T) == 8 ? 16 : 64; };
+template <typename T>
+__global__ void __launch_bounds__(NB) trsm_panel_kernel(T* __restrict__ Aall, int M, int k0, int nb) {
+  constexpr int RB = PanelRows<T>::R;
+  __shared__ T l11[NB][NB + 1];
+  __shared__ T rows[RB][NB + 1];
+  T* A = Aall + (int64_t)blockIdx.y * M * M;
+  const int tid = threadIdx.x;
+  const int r0 = k0 + nb + blockIdx.x * RB;
+  const int nr = min(RB, M - r0);
+  for (int e = tid; e < nb * nb; e += NB) {
+    const int i = e / nb, j = e % nb;
+    l11[i][j] = A[(int64_t)(k0 + i) * M + k0 + j];
+  }
+  for (int e = tid; e < nr * nb; e += NB) {
+    const int i = e / nb, j = e % nb;
+    rows[i][j] = A[(int64_t)(r0 + i) * M + k0 + j];
+  }
+  __syncthreads();
+  if (tid < nr) {
+    for (int c = 0; c < nb; ++c) {
+      T v = rows[tid][c];
+      for (int t = 0; t < c; ++t) v -= rows[tid][t] * l11[c][t];
+      rows[tid][c] = v / l11[c][c];
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < nr * nb; e += NB) {
+    const int i = e / nb, j = e % nb;
+    A[(int64_t)(r0 + i) * M + k0 + j] = rows[i][j];
+  }
+}
+
+template <typename T> __global__ void zero_upper_kernel(T* __restrict__ A, int M, int64_t total) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int64_t r = e % ((int64_t)M * M);
+  const int i = (int)(r / M), j = (int)(r % M);
+  if (j > i) A[e] = T(0);
+}
+
+template <typename T> int potrf(T* A, int M, int L, int* info, cudaStream_t st) {
+  GPZ_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * L, st));
+  const int64_t sL = (int64_t)M * M;
+  for (int k0 = 0; k0 < M; k0 += NB) {
+    const int nb = min(NB, M - k0);
+    potf2_kernel<T><<<L, 256, 0, st>>>(A, M, k0, nb, info);
+    GPZ_CHECK_LAUNCH();
+    const int rem = M - k0 - nb;
+    if (rem > 0) {
+      trsm_panel_kernel<T><<<dim3((unsigned)cdiv(rem, PanelRows<T>::R), L), NB, 0, st>>>(A, M, k0, nb);
+      GPZ_CHECK_LAUNCH();
+      T* L21 = A + (int64_t)(k0 + nb) * M + k0;
+      T* A22 = A + (int64_t)(k0 + nb) * M + (k0 + nb);
+      int rc = gemm<T>(st, false, true, rem, rem, nb, T(-1), L21, M, sL, L21, M, sL, T(1), A22, M, sL, L, 0, 0, 1);
+      if (rc) return rc;
+    }
+  }
+  const int64_t total = sL * L;
+  zero_upper_kernel<T><<<(unsigned)cdiv(total, 256), 256, 0, st>>>(A, M, total);
+  GPZ_CHECK_LAUNCH();
+  return GPZ_OK;
+}
+
+// ---- triangular inverse ---------------------------------------------------------------------------
+// diagonal blocks: X_ii = L_ii^-1 by forward substitution, one thread per column
+template <typename T>
+__global__ void __launch_bounds__(NB) trtri_diag_kernel(const T* __restrict__ Lall, T* __restrict__ Xall, int M) {
+  // s holds L_ii in its lower triangle (incl. diagonal) and the strictly-lower part of X transposed in its
+  // strictly-upper triangle (x[r][c], r > c, lives at s[c][r]); the diagonal of X lives in xd.
+  __shared__ T s[NB][NB + 1];
+  __shared__ T xd[NB];
+  const T* Lm = Lall + (int64_t)blockIdx.y * M * M;
+  T* X = Xall + (int64_t)blockIdx.y * M * M;
+  const int k0 = blockIdx.x * NB, nb = min(NB, M - k0), tid = threadIdx.x;
+  for (int e = tid; e < nb * nb; e += NB) {
+    const int i = e / nb, j = e % nb;
+    if (j <= i) s[i][j] = Lm[(int64_t)(k0 + i) * M + k0 + j];
+  }
+  __syncthreads();
+  if (tid < nb) {
+    const int c = tid;
+    const T xc = T(1) / s[c][c];
+    xd[c] = xc;
+    for (int r = c + 1; r < nb; ++r) {
+      T v = -s[r][c] * xc;
+      for (int t = c + 1; t < r; ++t) v -= s[r][t] * s[c][t];
+      s[c][r] = v / s[r][r];
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < nb * nb; e += NB) {
+    const int i = e / nb, j = e % nb;
+    X[(int64_t)(k0 + i) * M + k0 + j] = j < i ? s[j][i] : (j == i ? xd[i] : T(0));
+  }
+}
+
+// X = L^-1 for lower-triangular L (L x M x M).  `tmp` is an L x NB x M scratch panel.
+// Block row i:  X[i, 0:i] = -X_ii * (L[i, 0:i] * X[0:i, 0:i]),  X_ii from trtri_diag_kernel.
+template <typename T> int trtri(const T* Lc, T* X, T* tmp, int M, int L, cudaStream_t st) {
+  const int64_t sL = (int64_t)M * M;
+  GPZ_CUDA(cudaMemsetAsync(X, 0, sizeof(T) * sL * L, st));
+  const int nblk = (int)cdiv(M, NB);
+  trtri_diag_kernel<T><<<dim3(nblk, L), NB, 0, st>>>(Lc, X, M);
+  GPZ_CHECK_LAUNCH();
+  for (int i = 1; i < nblk; ++i) {
+    const int r0 = i * NB, nb = min(NB, M - r0);
+    int rc = gemm<T>(st, false, false, nb, r0, r0, T(-1), Lc + (int64_t)r0 * M, M, sL, X, M, sL, T(0), tmp, M,
+                     (int64_t)NB * M, L, 0, 1, 0);
+    if (rc) return rc;
+    rc = gemm<T>(st, false, false, nb, r0, nb, T(1), X + (int64_t)r0 * M + r0, M, sL, tmp, M, (int64_t)NB * M, T(0),
+                 X + (int64_t)r0 * M, M, sL, L, 1, 0, 0);
+    if (rc) return rc;
+  }
+  return GPZ_OK;
+}
+
+// ---- element-wise O(M^2) helpers -------------------------------------------------------------------
+// lower-Cholesky transform (torch transforms.py LowerCholeskyTransform._call; gp.py:220):
+//   out = tril(raw,-1) + diag(exp(diag raw))
+template <typename T> __global__ void lct_fwd_kernel(const T* __restrict__ raw, T* __restrict__ out, int M, int64_t total) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int64_t r = e % ((int64_t)M * M);
+  const int i = (int)(r / M), j = (int)(r % M);
+  out[e] = j < i ? raw[e] : (j == i ? Num<T>::exp(raw[e]) : T(0));
+}
+// graw = tril(g,-1) + diag(g_ii * Lu_ii)
+template <typename T>
+__global__ void lct_bwd_kernel(const T* __restrict__ g, const T* __restrict__ out, T* __restrict__ graw, int M, int64_t total) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int64_t r = e % ((int64_t)M * M);
+  const int i = (int)(r / M), j = (int)(r % M);
+  graw[e] = j < i ? g[e] : (j == i ? g[e] * out[e] : T(0));
+}
+// mode 0: out = tril(in) with halved diagonal (the Phi operator of the Cholesky backward)
+// mode 1: out = (in + in^T)/2
+// mode 2: out = tril(in)
+template <typename T>
+__global__ void tri_op_kernel(const T* __restrict__ in, T* __restrict__ out, int M, int64_t total, int mode) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int64_t b = e / ((int64_t)M * M), r = e % ((int64_t)M * M);
+  const int i = (int)(r / M), j = (int)(r % M);
+  if (mode == 1) out[e] = T(0.5) * (in[e] + in[b * M * M + (int64_t)j * M + i]);
+  else if (mode == 0) out[e] = j < i ? in[e] : (j == i ? T(0.5) * in[e] : T(0));
+  else out[e] = j <= i ? in[e] : T(0);
+}
+
+// KL(N(mu, Lu Lu^T) || N(0, Lc Lc^T)) per factor from the whitened quantities T = Lc^-1 Lu, q = Lc^-1 mu:
+//   kl = sum log diag Lc - sum log diag Lu + 0.5 (|T|_F^2 + |q|^2 - M)         (torch kl.py MVN||MVN)
+template <typename T>
+__global__ void __launch_bounds__(256) mvn_kl_fwd_kernel(const T* __restrict__ Tm, const T* __restrict__ q, const T* __restrict__ Lc,
+                                                          const T* __restrict__ Lu, T* __restrict__ kl, int M) {
+  __shared__ double red[32];
+  const int l = blockIdx.x;
+  const int64_t sL = (int64_t)M * M;
+  double acc = 0.0;
+  for (int64_t e = threadIdx.x; e < sL; e += blockDim.x) {
+    const double t = (double)Tm[l * sL + e];
+    acc += 0.5 * t * t;
+  }
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    const double qq = (double)q[(int64_t)l * M + i];
+    acc += 0.5 * qq * qq + ::log((double)Lc[l * sL + (int64_t)i * M + i]) - ::log((double)Lu[l * sL + (int64_t)i * M + i]);
+  }
+  acc = block_sum<double>(acc, red);
+  if (threadIdx.x == 0) kl[l] = (T)(acc - 0.5 * M);
+}
+// gT = g*T ; gq = g*q ; gLc = diag(g / Lc_ii) ; gLu = diag(-g / Lu_ii)
+template <typename T>
+__global__ void mvn_kl_bwd_kernel(const T* __restrict__ g, const T* __restrict__ Tm, const T* __restrict__ q, const T* __restrict__ Lc,
+                                  const T* __restrict__ Lu, T* __restrict__ gT, T* __restrict__ gq, T* __restrict__ gLc,
+                                  T* __restrict__ gLu, int M, int64_t total) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int64_t sL = (int64_t)M * M, l = e / sL, r = e % sL;
+  const int i = (int)(r / M), j = (int)(r % M);
+  const T gl = g[l];
+  gT[e] = gl * Tm[e];
+  gLc[e] = i == j ? gl / Lc[e] : T(0);
+  gLu[e] = i == j ? -gl / Lu[e] : T(0);
+  if (j == 0) gq[l * M + i] = gl * q[l * M + i];
+}
+
+}  // namespace gpz
+
+using namespace gpz;
+#define ST(s) ((cudaStream_t)(s))
+
+#define GPZ_LINALG_IMPL(SUF, T)                                                                                   \
+  extern "C" int gpz_potrf_##SUF(T* A, int M, int L, int* info, void* stream) {                                  \
+    if (M <= 0 || L <= 0) return GPZ_ERR_BADARG;                                                                  \
+    return potrf<T>(A, M, L, info, ST(stream));                                                                  \
+  }                                                                                                               \
+  extern "C" int gpz_trtri_##SUF(const T* Lc, T* X, T* tmp, int M, int L, void* stream) {                        \
+    if (M <= 0 || L <= 0) return GPZ_ERR_BADARG;                                                                  \
+    return trtri<T>(Lc, X, tmp, M, L, ST(stream));                                                               \
+  }                                                                                                               \
+  extern "C" int gpz_gemm_##SUF(int ta, int tb, int m, int n, int k, T alpha, const T* A, int64_t lda, int64_t sA, \
+                                const T* B, int64_t ldb, int64_t sB, T beta, T* D, int64_t ldd, int64_t sD,      \
+                                int batch, int a_tri, int b_tri, int d_tri, int splitk, void* stream) {           \
+    return gemm<T>(ST(stream), ta != 0, tb != 0, m, n, k, alpha, A, lda, sA, B, ldb, sB, beta, D, ldd, sD, batch, \
+                   a_tri, b_tri, d_tri, splitk);                                                                  \
+  }                                                                                                               \
+  extern "C" int gpz_lower_cholesky_fwd_##SUF(const T* raw, T* out, int M, int L, void* stream) {                \
+    const int64_t total = (int64_t)M * M * L;                                                                     \
+    lct_fwd_kernel<T><<<(unsigned)cdiv(total, 256), 256, 0, ST(stream)>>>(raw, out, M, total);                   \
+    GPZ_CHECK_LAUNCH();                                                                                           \
+    return GPZ_OK;                                                                                                \
+  }                                                                                                               \
+  extern "C" int gpz_lower_cholesky_bwd_##SUF(const T* g, const T* out, T* graw, int M, int L, void* stream) {   \
+    const int64_t total = (int64_t)M * M * L;                                                                     \
+    lct_bwd_kernel<T><<<(unsigned)cdiv(total, 256), 256, 0, ST(stream)>>>(g, out, graw, M, total);               \
+    GPZ_CHECK_LAUNCH();                                                                                           \
+    return GPZ_OK;                                                                                                \
+  }                                                                                                               \
+  extern "C" int gpz_tri_op_##SUF(const T* in, T* out, int M, int L, int mode, void* stream) {                   \
+    const int64_t total = (int64_t)M * M * L;                                                                     \
+    if (in == out && mode == 1) return GPZ_ERR_BADARG;                                                            \
+    tri_op_kernel<T><<<(unsigned)cdiv(total, 256), 256, 0, ST(stream)>>>(in, out, M, total, mode);               \
+    GPZ_CHECK_LAUNCH();                                                                                           \
+    return GPZ_OK;                                                                                                \
+  }                                                                                                               \
+  extern "C" int gpz_mvn_kl_fwd_##SUF(const T* Tm, const T* q, const T* Lc, const T* Lu, T* kl, int M, int L,    \
+                                      void* stream) {                                                             \
+    mvn_kl_fwd_kernel<T><<<L, 256, 0, ST(stream)>>>(Tm, q, Lc, Lu, kl, M);                                       \
+    GPZ_CHECK_LAUNCH();                                                                                           \
+    return GPZ_OK;                                                                                                \
+  }                                                                                                               \
+  extern "C" int gpz_mvn_kl_bwd_##SUF(const T* g, const T* Tm, const T* q, const T* Lc, const T* Lu, T* gT,      \
+                                      T* gq, T* gLc, T* gLu, int M, int L, void* stream) {                        \
+    const int64_t total = (int64_t)M * M * L;                                                                     \
+    mvn_kl_bwd_kernel<T><<<(unsigned)cdiv(total, 256), 256, 0, ST(stream)>>>(g, Tm, q, Lc, Lu, gT, gq, gLc, gLu, \
+                                                                             M, total);                           \
+    GPZ_CHECK_LAUNCH();                                                                                           \
+    return GPZ_OK;                                                                                                \
+  }
+
+GPZ_LINALG_IMPL(f32, float)
+GPZ_LINALG_IMPL(f64, double)

@@ -1,0 +1,298 @@
+// K7: fused Poisson log-likelihood with the factor-loading contraction, forward + backward in one pass.
+//
+// Reference chain (likelihoods.py:49-53, 80-97, 110-145; utilities.py:611-614; torch poisson.py log_prob):
+//   F = mean + eps*sd            (Normal.rsample, E samples)          E x F x B
+//   rate = softplus(V) * (softplus(W) @ exp(F))                       E x G x B   (materialised by the reference)
+//   ll = mean_e sum_{g,n} [ y log rate - rate (- lgamma(y+1)) ]
+// and autograd's backward through all of it.  Here nothing of size G x B is ever written: one pass over
+// y (G x B floats, the algorithmic HBM traffic) produces ll and the gradients w.r.t. mean, spread, W, V.
+//
+// Mapping: a CTA owns 128 spots (thread = spot, so y rows are read coalesced) and walks the genes in
+// chunks of 32.  Phase A (thread = spot): zr, log-lik, t = d ll/d zr, accumulates d/dF in registers and
+// parks t in shared memory.  Phase B (lane = gene, warp = quarter of the spots): the gW[g,f] partial
+// sum_n t[g,n] exp(F)[f,n] from shared memory.  Per-CTA gW partials go to a workspace slice and are
+// summed by a second tiny kernel (deterministic, no atomics on the G x F output).
+#include "common.cuh"
+#include "gpzoo_b200.h"
+
+namespace gpz {
+
+constexpr int PZ_SPOTS = 128;
+constexpr int PZ_GCH = 32;
+
+template <typename T> struct PoissonArgs {
+  const T* y; int64_t y_ld;           // G x Ntot, row stride
+  const int64_t* idx;                  // B or null (minibatch gather y[:, idx], V[idx])
+  const T* W; int w_softplus;          // G x F raw loadings; softplus (NSF2/PNMF) or raw (Hybrid_NSF)
+  const T* V;                          // Ntot raw
+  const T* mean; const T* spread;      // F x B ; spread = variance for f < n_var (clamped at clamp_min), sd otherwise
+  const T* eps;                        // E x F x B
+  int G, F, B, E, n_var;
+  T clamp_min;
+  int with_lgamma;
+  // outputs
+  double* ll_part;                     // gridDim.x * gridDim.y
+  T* gW_part;                          // gridDim.x x G x F
+  T* gV;                               // B   (d ll / d V[idx[n]])
+  T* gmean; T* gspread;                // F x B
+  int genes_per_cta;                   // multiple of PZ_GCH
+  int atomic_out;                      // gridDim.y > 1
+};
+
+template <typename T, int FMAX>
+__global__ void __launch_bounds__(PZ_SPOTS) poisson_kernel(const PoissonArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char pz_smem[];
+  typedef T RowT[PZ_SPOTS + 1];
+  typedef T RowE[PZ_SPOTS];
+  typedef T RowW[FMAX];
+  typedef T AccW[PZ_GCH][FMAX];
+  RowT* tS = reinterpret_cast<RowT*>(pz_smem);                         // [PZ_GCH][PZ_SPOTS+1]
+  RowE* efS = reinterpret_cast<RowE*>(tS + PZ_GCH);                    // [FMAX][PZ_SPOTS]
+  RowW* sW = reinterpret_cast<RowW*>(efS + FMAX);                      // [PZ_GCH][FMAX]
+  AccW* sAcc = reinterpret_cast<AccW*>(sW + PZ_GCH);                   // [4][PZ_GCH][FMAX]
+  __shared__ double red[32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = blockIdx.x * PZ_SPOTS + tid;
+  const bool active = n < a.B;
+  const int64_t col = active ? (a.idx ? a.idx[n] : (int64_t)n) : 0;
+  const T invE = T(1) / T(a.E);
+
+  T mu[FMAX], sd[FMAX], gm[FMAX], gs[FMAX];
+#pragma unroll
+  for (int f = 0; f < FMAX; ++f) {
+    gm[f] = T(0); gs[f] = T(0); mu[f] = T(0); sd[f] = T(0);
+    if (f < a.F && active) {
+      mu[f] = a.mean[(int64_t)f * a.B + n];
+      const T s = a.spread[(int64_t)f * a.B + n];
+      sd[f] = f < a.n_var ? Num<T>::sqrt(s > a.clamp_min ? s : a.clamp_min) : s;
+    }
+  }
+  const T vraw = active ? a.V[col] : T(0);
+  const T spV = active ? softplus(vraw) : T(0);
+  T gVacc = T(0);
+  double ll = 0.0;
+
+  const int g_begin = blockIdx.y * a.genes_per_cta;
+  const int g_end = min(a.G, g_begin + a.genes_per_cta);
+  for (int g0 = g_begin; g0 < g_end; g0 += PZ_GCH) {
+    T acc[FMAX];
+#pragma unroll
+    for (int f = 0; f < FMAX; ++f) acc[f] = T(0);
+    __syncthreads();
+    for (int e = tid; e < PZ_GCH * FMAX; e += PZ_SPOTS) {
+      const int gi = e / FMAX, f = e % FMAX;
+      T w = T(0);
+      if (g0 + gi < g_end && f < a.F) {
+        w = a.W[(int64_t)(g0 + gi) * a.F + f];
+        if (a.w_softplus) w = softplus(w);
+      }
+      sW[gi][f] = w;
+    }
+    for (int e = 0; e < a.E; ++e) {
+      T ef[FMAX], pg[FMAX];
+#pragma unroll
+      for (int f = 0; f < FMAX; ++f) {
+        pg[f] = T(0);
+        T v = T(0);
+        if (f < a.F && active) v = Num<T>::exp(fma(a.eps[((int64_t)e * a.F + f) * a.B + n], sd[f], mu[f]));
+        ef[f] = v;
+      }
+      __syncthreads();               // previous phase B finished with tS / efS; sW visible
+#pragma unroll
+      for (int f = 0; f < FMAX; ++f) efS[f][tid] = ef[f];
+      // ---- phase A: thread = spot ----
+      T llc = T(0);
+      for (int gi = 0; gi < PZ_GCH; ++gi) {
+        T t = T(0);
+        if (active && g0 + gi < g_end) {
+          const T y = a.y[(int64_t)(g0 + gi) * a.y_ld + col];
+          T zr = T(0);
+#pragma unroll
+          for (int f = 0; f < FMAX; ++f) zr = fma(sW[gi][f], ef[f], zr);
+          const T r = spV * zr;
+          T lp = (y == T(0) ? T(0) : y * Num<T>::log(r)) - r;
+          if (a.with_lgamma && y > T(1.5)) lp -= Num<T>::lgamma(y + T(1));   // lgamma(1) = lgamma(2) = 0
+          llc += lp;
+          t = (y / zr - spV) * invE;
+          gVacc += (y - r) * invE;
+#pragma unroll
+          for (int f = 0; f < FMAX; ++f) pg[f] = fma(sW[gi][f], t, pg[f]);
+        }
+        tS[gi][tid] = t;
+      }
+      ll += (double)llc;
+#pragma unroll
+      for (int f = 0; f < FMAX; ++f) {
+        if (f < a.F && active) {
+          const T gF = ef[f] * pg[f];
+          gm[f] += gF;
+          gs[f] = fma(gF, a.eps[((int64_t)e * a.F + f) * a.B + n], gs[f]);
+        }
+      }
+      __syncthreads();
+      // ---- phase B: lane = gene, warp = quarter of the spots ----
+      const int nb = warp * 32;
+#pragma unroll 4
+      for (int k = 0; k < 32; ++k) {
+        const T t = tS[lane][nb + k];
+#pragma unroll
+        for (int f = 0; f < FMAX; ++f) acc[f] = fma(t, efS[f][nb + k], acc[f]);
+      }
+    }
+#pragma unroll
+    for (int f = 0; f < FMAX; ++f) sAcc[warp][lane][f] = acc[f];
+    __syncthreads();
+    for (int e = tid; e < PZ_GCH * a.F; e += PZ_SPOTS) {
+      const int gi = e / a.F, f = e % a.F;
+      if (g0 + gi < g_end)
+        a.gW_part[((int64_t)blockIdx.x * a.G + g0 + gi) * a.F + f] =
+            sAcc[0][gi][f] + sAcc[1][gi][f] + sAcc[2][gi][f] + sAcc[3][gi][f];
+    }
+  }
+
+  if (active) {
+    const T gv = softplus_grad(vraw) * gVacc / spV;
+    if (a.atomic_out) atomicAdd(a.gV + n, gv); else a.gV[n] = gv;
+#pragma unroll
+    for (int f = 0; f < FMAX; ++f) {
+      if (f < a.F) {
+        T gsp = gs[f];
+        if (f < a.n_var) {                        // spread is a variance: d sd/d var = 1/(2 sd) where not clamped
+          const T s = a.spread[(int64_t)f * a.B + n];
+          gsp = s >= a.clamp_min ? gsp / (T(2) * sd[f]) : T(0);
+        }
+        const int64_t o = (int64_t)f * a.B + n;
+        if (a.atomic_out) { atomicAdd(a.gmean + o, gm[f]); atomicAdd(a.gspread + o, gsp); }
+        else { a.gmean[o] = gm[f]; a.gspread[o] = gsp; }
+      }
+    }
+  }
+  const double tot = block_sum<double>(ll, red);
+  if (tid == 0) a.ll_part[blockIdx.y * gridDim.x + blockIdx.x] = tot;
+}
+
+// gW[g,f] = (softplus'(W[g,f]) or 1) * sum_b gW_part[b,g,f]
+template <typename T>
+__global__ void poisson_gw_reduce_kernel(const T* __restrict__ part, const T* __restrict__ W, T* __restrict__ gW, int64_t GF, int nb,
+                                         int w_softplus) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= GF) return;
+  T s = T(0);
+  for (int b = 0; b < nb; ++b) s += part[(int64_t)b * GF + e];
+  gW[e] = w_softplus ? s * softplus_grad(W[e]) : s;
+}
+
+__global__ void sum_double_kernel(const double* __restrict__ part, int n, double* __restrict__ out) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += part[i];
+  s = block_sum<double>(s, red);
+  if (threadIdx.x == 0) out[0] = s;
+}
+
+template <typename T, int FMAX> constexpr size_t poisson_smem() {
+  return sizeof(T) * (PZ_GCH * (PZ_SPOTS + 1) + FMAX * PZ_SPOTS + PZ_GCH * FMAX + 4 * PZ_GCH * FMAX);
+}
+template <typename T, int FMAX> int poisson_launch(const PoissonArgs<T>& a, dim3 grid, cudaStream_t st) {
+  constexpr size_t smem = poisson_smem<T, FMAX>();
+  GPZ_CUDA(cudaFuncSetAttribute(poisson_kernel<T, FMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  poisson_kernel<T, FMAX><<<grid, PZ_SPOTS, smem, st>>>(a);
+  GPZ_CHECK_LAUNCH();
+  return GPZ_OK;
+}
+
+static void poisson_grid(int G, int B, int* nbx, int* nby, int* gpc) {
+  *nbx = (int)cdiv(B, PZ_SPOTS);
+  const int chunks = (int)cdiv(G, PZ_GCH);
+  int by = 1;
+  if (*nbx < 296) by = (int)min((int64_t)chunks, cdiv(296, *nbx > 0 ? *nbx : 1));
+  const int cpc = (int)cdiv(chunks, by);
+  *gpc = cpc * PZ_GCH;
+  *nby = (int)cdiv(G, *gpc);
+}
+
+template <typename T>
+int poisson_fwdbwd(PoissonArgs<T> a, T* gW, double* ll_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (a.F < 1 || a.F > 32 || a.E < 1 || a.G < 1) return GPZ_ERR_UNSUPPORTED;
+  if (a.B == 0) return GPZ_OK;
+  int nbx, nby, gpc;
+  poisson_grid(a.G, a.B, &nbx, &nby, &gpc);
+  const size_t need = sizeof(double) * ((size_t)nbx * nby + 2) + sizeof(T) * (size_t)nbx * a.G * a.F;
+  if (ws_bytes < need) return GPZ_ERR_BADARG;
+  a.ll_part = reinterpret_cast<double*>(ws);
+  a.gW_part = reinterpret_cast<T*>(a.ll_part + (size_t)nbx * nby + 2);
+  a.genes_per_cta = gpc;
+  a.atomic_out = nby > 1;
+  if (a.atomic_out) {
+    GPZ_CUDA(cudaMemsetAsync(a.gV, 0, sizeof(T) * a.B, st));
+    GPZ_CUDA(cudaMemsetAsync(a.gmean, 0, sizeof(T) * a.B * a.F, st));
+    GPZ_CUDA(cudaMemsetAsync(a.gspread, 0, sizeof(T) * a.B * a.F, st));
+  }
+  dim3 grid(nbx, nby);
+  int rc;
+  if (a.F <= 4) rc = poisson_launch<T, 4>(a, grid, st);
+  else if (a.F <= 12) rc = poisson_launch<T, 12>(a, grid, st);
+  else if (a.F <= 20) rc = poisson_launch<T, 20>(a, grid, st);
+  else rc = poisson_launch<T, 32>(a, grid, st);
+  if (rc) return rc;
+  const int64_t GF = (int64_t)a.G * a.F;
+  poisson_gw_reduce_kernel<T><<<(unsigned)cdiv(GF, 256), 256, 0, st>>>(a.gW_part, a.W, gW, GF, nbx, a.w_softplus);
+  GPZ_CHECK_LAUNCH();
+  sum_double_kernel<<<1, 256, 0, st>>>(a.ll_part, nbx * nby, ll_out);
+  GPZ_CHECK_LAUNCH();
+  return GPZ_OK;
+}
+
+// rate[e,g,n] = softplus(V[col]) * sum_f w(W[g,f]) exp(F[e,f,n]) -- the compatibility path that materialises
+// pY.rate for callers of model.forward() (likelihoods.py:83-85); not used by the fused ELBO.
+template <typename T>
+__global__ void poisson_rate_kernel(const T* __restrict__ W, int w_softplus, const T* __restrict__ V, const int64_t* __restrict__ idx,
+                                    const T* __restrict__ Fs, T* __restrict__ rate, int G, int F, int B, int E) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = blockIdx.z;
+  if (n >= B) return;
+  const T spV = softplus(V[idx ? idx[n] : (int64_t)n]);
+  const int g0 = blockIdx.y * 32, g1 = min(G, g0 + 32);
+  for (int g = g0; g < g1; ++g) {
+    T zr = T(0);
+    for (int f = 0; f < F; ++f) {
+      T w = W[(int64_t)g * F + f];
+      if (w_softplus) w = softplus(w);
+      zr = fma(w, Num<T>::exp(Fs[((int64_t)e * F + f) * B + n]), zr);
+    }
+    rate[((int64_t)e * G + g) * B + n] = spV * zr;
+  }
+}
+
+}  // namespace gpz
+
+using namespace gpz;
+
+#define GPZ_POISSON_IMPL(SUF, T)                                                                                       \
+  extern "C" int64_t gpz_poisson_workspace_bytes_##SUF(int G, int F, int B) {                                          \
+    int nbx, nby, gpc;                                                                                                 \
+    poisson_grid(G, B, &nbx, &nby, &gpc);                                                                              \
+    return (int64_t)(sizeof(double) * ((size_t)nbx * nby + 2) + sizeof(T) * (size_t)nbx * G * F);                      \
+  }                                                                                                                    \
+  extern "C" int gpz_poisson_fwdbwd_##SUF(const T* y, int64_t y_ld, const int64_t* idx, const T* W, int w_softplus,    \
+                                          const T* V, const T* mean, const T* spread, const T* eps, int G, int F,      \
+                                          int B, int E, int n_var, T clamp_min, int with_lgamma, double* ll, T* gW,    \
+                                          T* gV, T* gmean, T* gspread, void* ws, int64_t ws_bytes, void* stream) {     \
+    PoissonArgs<T> a;                                                                                                  \
+    a.y = y; a.y_ld = y_ld; a.idx = idx; a.W = W; a.w_softplus = w_softplus; a.V = V; a.mean = mean;                   \
+    a.spread = spread; a.eps = eps; a.G = G; a.F = F; a.B = B; a.E = E; a.n_var = n_var; a.clamp_min = clamp_min;      \
+    a.with_lgamma = with_lgamma; a.gV = gV; a.gmean = gmean; a.gspread = gspread;                                      \
+    return poisson_fwdbwd<T>(a, gW, ll, ws, (size_t)ws_bytes, (cudaStream_t)stream);                                   \
+  }                                                                                                                    \
+  extern "C" int gpz_poisson_rate_##SUF(const T* W, int w_softplus, const T* V, const int64_t* idx, const T* Fs,       \
+                                        T* rate, int G, int F, int B, int E, void* stream) {                           \
+    if (B == 0 || G == 0 || E == 0) return GPZ_OK;                                                                     \
+    poisson_rate_kernel<T><<<dim3((unsigned)cdiv(B, 128), (unsigned)cdiv(G, 32), E), 128, 0, (cudaStream_t)stream>>>(  \
+        W, w_softplus, V, idx, Fs, rate, G, F, B, E);                                                                  \
+    GPZ_CHECK_LAUNCH();                                                                                                \
+    return GPZ_OK;                                                                                                     \
+  }
+
+GPZ_POISSON_IMPL(f32, float)
+GPZ_POISSON_IMPL(f64, double)

@@ -1,0 +1,374 @@
+"""torch.autograd.Functions over the C ABI (include/gpzoo_b200.h).
+
+The reference gets every gradient from autograd over stock ATen ops (utilities.py:485,620
+`loss.backward()`); here each fused CUDA kernel has a hand-written backward kernel and these Functions
+only allocate tensors and pass pointers.  Maths: SURVEY.md Appendix A (validated against the reference).
+All Functions work on L-batched, contiguous CUDA tensors in float32 or float64.
+"""
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _cabi
+from ._cabi import c_i, c_i64, c_p, call, ptr, scalar
+
+# When True (default) a non-positive-definite Kzz raises torch.linalg.LinAlgError right away like the
+# reference's torch.linalg.cholesky (one device sync).  Throughput runs may turn it off and call
+# `check_cholesky_info()` when they read the loss.
+SYNC_CHECKS = True
+_pending_info = []
+
+
+def set_sync_checks(flag: bool):
+    global SYNC_CHECKS
+    SYNC_CHECKS = bool(flag)
+
+
+def check_cholesky_info():
+    global _pending_info
+    pend, _pending_info = _pending_info, []
+    for info in pend:
+        bad = info.nonzero()
+        if bad.numel():
+            l = int(bad[0, 0])
+            raise torch.linalg.LinAlgError(
+                f"gpzoo_b200.cholesky: (Batch element {l}): the input is not positive-definite "
+                f"(leading minor of order {int(info[l])} is not positive-definite)")
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def gemm(A, B, ta=False, tb=False, alpha=1.0, beta=0.0, out=None, a_tri=0, b_tri=0, d_tri=0, splitk=1):
+    """out[b] = alpha op(A[b]) op(B[b]) + beta out[b]; A, B, out are (batch, rows, cols) contiguous."""
+    bsz = A.shape[0]
+    m, k = (A.shape[2], A.shape[1]) if ta else (A.shape[1], A.shape[2])
+    n = B.shape[1] if tb else B.shape[2]
+    kb = B.shape[2] if tb else B.shape[1]
+    assert kb == k and B.shape[0] == bsz, (A.shape, B.shape, ta, tb)
+    if out is None:
+        out = (torch.zeros if (d_tri or splitk > 1) else torch.empty)((bsz, m, n), dtype=A.dtype, device=A.device)
+    dt = A.dtype
+    call("gemm", dt, c_i(int(ta)), c_i(int(tb)), c_i(m), c_i(n), c_i(k), scalar(dt, alpha),
+         ptr(A), c_i64(A.shape[2]), c_i64(A.shape[1] * A.shape[2]),
+         ptr(B), c_i64(B.shape[2]), c_i64(B.shape[1] * B.shape[2]),
+         scalar(dt, beta), ptr(out), c_i64(out.shape[2]), c_i64(out.shape[1] * out.shape[2]),
+         c_i(bsz), c_i(a_tri), c_i(b_tri), c_i(d_tri), c_i(splitk))
+    return out
+
+
+def tri_op(X, mode, out=None):
+    if out is None:
+        out = torch.empty_like(X)
+    call("tri_op", X.dtype, ptr(X), ptr(out), c_i(X.shape[-1]), c_i(X.shape[0]), c_i(mode))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# K1
+# ------------------------------------------------------------------------------------------------
+class KernelBuild(Function):
+    """K[l,i,j] = sigma_l^2 exp(-0.5 |x1_i-x2_j|^2/(ls_l^2 den)) / den^p_half (+ jitter on i==j).
+
+    Replaces kernels.py:114-130 / 141-155 / 172-191 / 204-228 (+ utilities.py:407-418 add_jitter)."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, sigma, ls, a, r2, g1, g2, p_half, jitter):
+        x1, x2, sigma, ls = _c(x1), _c(x2), _c(sigma), _c(ls)
+        dt = x1.dtype
+        n1, D = x1.shape
+        n2 = x2.shape[0]
+        L = sigma.numel()
+        mg = g1 is not None
+        if mg:
+            a, r2, g1, g2 = _c(a), _c(r2), _c(g1), _c(g2)
+        out = torch.empty((L, n1, n2), dtype=dt, device=x1.device)
+        call("kernel_build_fwd", dt, ptr(x1), ptr(x2), ptr(sigma), ptr(ls), ptr(a if mg else None),
+             ptr(r2 if mg else None), ptr(g1 if mg else None), ptr(g2 if mg else None), c_i(n1), c_i(n2), c_i(D), c_i(L),
+             c_i(r2.shape[0] if mg else 0), scalar(dt, p_half), scalar(dt, jitter), ptr(out))
+        ctx.save_for_backward(x1, x2, sigma, ls, a if mg else None, r2 if mg else None, g1 if mg else None,
+                              g2 if mg else None)
+        ctx.p_half = p_half
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, G):
+        x1, x2, sigma, ls, a, r2, g1, g2 = ctx.saved_tensors
+        dt = x1.dtype
+        G = _c(G)
+        n1, D = x1.shape
+        n2 = x2.shape[0]
+        L = sigma.numel()
+        mg = g1 is not None
+        need = ctx.needs_input_grad
+        g_x1 = torch.empty_like(x1) if need[0] else None
+        g_x2 = torch.empty_like(x2) if need[1] else None
+        g_sigma = torch.empty_like(sigma)
+        g_ls = torch.empty_like(ls)
+        g_a = torch.empty_like(a) if mg else None
+        call("kernel_build_bwd", dt, ptr(x1), ptr(x2), ptr(sigma), ptr(ls), ptr(a), ptr(r2), ptr(g1), ptr(g2),
+             c_i(n1), c_i(n2), c_i(D), c_i(L), c_i(r2.shape[0] if mg else 0), scalar(dt, ctx.p_half), ptr(G),
+             ptr(g_x1), ptr(g_x2), ptr(g_sigma), ptr(g_ls), ptr(g_a))
+        return g_x1, g_x2, g_sigma, g_ls, g_a, None, None, None, None, None
+
+
+def cdist(x1, x2):
+    """Euclidean distance matrix by direct differences (kernels.py:118 torch.cdist; no gradient)."""
+    x1, x2 = _c(x1.detach()), _c(x2.detach())
+    out = torch.empty((x1.shape[0], x2.shape[0]), dtype=x1.dtype, device=x1.device)
+    call("cdist", x1.dtype, ptr(x1), ptr(x2), ptr(out), c_i(x1.shape[0]), c_i(x2.shape[0]), c_i(x1.shape[1]))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# K2
+# ------------------------------------------------------------------------------------------------
+class CholeskyInverse(Function):
+    """(Lc, Linv) = (chol(Kzz), chol(Kzz)^-1) for Kzz (L x M x M).  gp.py:213 torch.linalg.cholesky; the
+    inverse factor turns cholesky_solve (gp.py:218) and kl_divergence's solves into triangular products."""
+
+    @staticmethod
+    def forward(ctx, Kzz):
+        dt = Kzz.dtype
+        L, M, _ = Kzz.shape
+        Lc = Kzz.detach().clone(memory_format=torch.contiguous_format)
+        info = torch.empty(L, dtype=torch.int32, device=Kzz.device)
+        call("potrf", dt, ptr(Lc), c_i(M), c_i(L), ptr(info))
+        if SYNC_CHECKS:
+            _pending_info.append(info)
+            check_cholesky_info()
+        else:
+            _pending_info.append(info)
+        Linv = torch.empty_like(Lc)
+        tmp = torch.empty((L, 64, M), dtype=dt, device=Kzz.device)
+        call("trtri", dt, ptr(Lc), ptr(Linv), ptr(tmp), c_i(M), c_i(L))
+        ctx.save_for_backward(Lc, Linv)
+        return Lc, Linv
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gLc, gLinv):
+        Lc, Linv = ctx.saved_tensors
+        if gLc is None and gLinv is None:
+            return None
+        g = tri_op(_c(gLc), 2) if gLc is not None else torch.zeros_like(Lc)
+        if gLinv is not None:
+            t1 = gemm(Linv, _c(gLinv), ta=True, a_tri=2)                       # Linv^T gLinv
+            gemm(t1, Linv, tb=True, alpha=-1.0, beta=1.0, out=g, b_tri=2, d_tri=1)   # g -= tril(t1 Linv^T)
+        P = gemm(Lc, g, ta=True, a_tri=2, b_tri=1, d_tri=1)                    # tril(Lc^T g)
+        tri_op(P, 0, out=P)                                                    # halve the diagonal
+        t1 = gemm(Linv, P, ta=True, a_tri=2, b_tri=1)                          # Linv^T Phi
+        t2 = gemm(t1, Linv, b_tri=1)                                           # ... Linv
+        return tri_op(t2, 1)                                                   # symmetrise
+
+
+class LowerCholesky(Function):
+    """transform_to(constraints.lower_cholesky) (gp.py:220): tril(raw,-1) + diag(exp(diag raw))."""
+
+    @staticmethod
+    def forward(ctx, raw):
+        raw = _c(raw)
+        out = torch.empty_like(raw)
+        call("lower_cholesky_fwd", raw.dtype, ptr(raw), ptr(out), c_i(raw.shape[-1]), c_i(raw.shape[0]))
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (out,) = ctx.saved_tensors
+        g = _c(g)
+        graw = torch.empty_like(g)
+        call("lower_cholesky_bwd", g.dtype, ptr(g), ptr(out), ptr(graw), c_i(g.shape[-1]), c_i(g.shape[0]))
+        return graw
+
+
+class Whiten(Function):
+    """T = Linv Lu (lower), q = Linv mu — the quantities torch computes with solve_triangular inside
+    kl_divergence(qU, pU) (torch kl.py) and that the predictive variance needs as Lu^T Lc^-T."""
+
+    @staticmethod
+    def forward(ctx, Linv, Lu, mu):
+        Linv, Lu, mu = _c(Linv), _c(Lu), _c(mu)
+        T = gemm(Linv, Lu, a_tri=1, b_tri=1, d_tri=1)
+        q = gemm(Linv, mu.unsqueeze(-1), a_tri=1).squeeze(-1)
+        ctx.save_for_backward(Linv, Lu, mu)
+        return T, q
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gT, gq):
+        Linv, Lu, mu = ctx.saved_tensors
+        gLinv = torch.zeros_like(Linv)
+        gLu = gmu = None
+        if gT is not None:
+            gT = _c(gT)
+            gemm(gT, Lu, tb=True, out=gLinv, b_tri=2, d_tri=1)
+            gLu = gemm(Linv, gT, ta=True, a_tri=2, d_tri=1)
+        if gq is not None:
+            gq = _c(gq).unsqueeze(-1)
+            gemm(gq, mu.unsqueeze(-1), tb=True, beta=1.0, out=gLinv, d_tri=1)
+            gmu = gemm(Linv, gq, ta=True, a_tri=2).squeeze(-1)
+        return gLinv, gLu, gmu
+
+
+# ------------------------------------------------------------------------------------------------
+# K3 / K4
+# ------------------------------------------------------------------------------------------------
+class Predict(Function):
+    """SVGP predictive mean and variance (gp.py:218-225 + utilities.py:382-397), see csrc/predict.cu."""
+
+    @staticmethod
+    def forward(ctx, Kxx, Kzx, Linv, T, q):
+        Kxx, Kzx, Linv, T, q = _c(Kxx), _c(Kzx), _c(Linv), _c(T), _c(q)
+        dt = Kzx.dtype
+        L, M, N = Kzx.shape
+        A = torch.empty_like(Kzx)
+        C = torch.empty_like(Kzx)
+        mean = torch.empty((L, N), dtype=dt, device=Kzx.device)
+        var = torch.empty_like(mean)
+        call("svgp_predict_fwd", dt, ptr(Kzx), ptr(Linv), ptr(T), ptr(q), ptr(Kxx), ptr(A), ptr(C), ptr(mean), ptr(var),
+             c_i(M), c_i(N), c_i(L))
+        ctx.save_for_backward(Kzx, Linv, T, q, A, C)
+        return mean, var
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gm, gv):
+        Kzx, Linv, T, q, A, C = ctx.saved_tensors
+        dt = Kzx.dtype
+        L, M, N = Kzx.shape
+        gm = _c(gm) if gm is not None else torch.zeros((L, N), dtype=dt, device=Kzx.device)
+        gv = _c(gv) if gv is not None else torch.zeros((L, N), dtype=dt, device=Kzx.device)
+        gA = torch.empty_like(Kzx)
+        gKzx = torch.empty_like(Kzx)
+        gLinv = torch.zeros_like(Linv)
+        gT = torch.zeros_like(T)
+        gq = torch.empty_like(q)
+        call("svgp_predict_bwd", dt, ptr(Kzx), ptr(Linv), ptr(T), ptr(q), ptr(A), ptr(C), ptr(gm), ptr(gv), ptr(gA),
+             ptr(gKzx), ptr(gLinv), ptr(gT), ptr(gq), c_i(M), c_i(N), c_i(L))
+        return gv, gKzx, gLinv, gT, gq
+
+
+# ------------------------------------------------------------------------------------------------
+# K5
+# ------------------------------------------------------------------------------------------------
+class MvnKL(Function):
+    """kl_divergence(MVN(mu, Lu), MVN(0, Lc)) per factor (utilities.py:481,616; torch kl.py)."""
+
+    @staticmethod
+    def forward(ctx, T, q, Lc, Lu):
+        T, q, Lc, Lu = _c(T), _c(q), _c(Lc), _c(Lu)
+        L, M, _ = T.shape
+        kl = torch.empty(L, dtype=T.dtype, device=T.device)
+        call("mvn_kl_fwd", T.dtype, ptr(T), ptr(q), ptr(Lc), ptr(Lu), ptr(kl), c_i(M), c_i(L))
+        ctx.save_for_backward(T, q, Lc, Lu)
+        return kl
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        T, q, Lc, Lu = ctx.saved_tensors
+        L, M, _ = T.shape
+        g = _c(g)
+        gT, gLc, gLu, gq = torch.empty_like(T), torch.empty_like(T), torch.empty_like(T), torch.empty_like(q)
+        call("mvn_kl_bwd", T.dtype, ptr(g), ptr(T), ptr(q), ptr(Lc), ptr(Lu), ptr(gT), ptr(gq), ptr(gLc), ptr(gLu),
+             c_i(M), c_i(L))
+        return gT, gq, gLc, gLu
+
+
+# ------------------------------------------------------------------------------------------------
+# K7
+# ------------------------------------------------------------------------------------------------
+class PoissonLL(Function):
+    """mean_E sum_{g,n} Poisson log-lik of y under rate = softplus(V) (w(W) @ exp(mean + eps*sd)),
+    with all gradients produced by the same pass (csrc/poisson.cu)."""
+
+    @staticmethod
+    def forward(ctx, y, idx, W, V, mean, spread, eps, n_var, clamp_min, w_softplus, with_lgamma):
+        y, W, V, mean, spread, eps = _c(y), _c(W), _c(V), _c(mean), _c(spread), _c(eps)
+        dt = W.dtype
+        G, F = W.shape
+        B = mean.shape[1]
+        E = eps.shape[0]
+        assert y.shape[0] == G and mean.shape[0] == F and eps.shape[1] == F and eps.shape[2] == B
+        if idx is not None:
+            idx = _c(idx.to(device=W.device, dtype=torch.int64))
+        else:
+            assert y.shape[1] == B
+        lib = _cabi.lib()
+        suf = "f32" if dt == torch.float32 else "f64"
+        ws_bytes = int(getattr(lib, f"gpz_poisson_workspace_bytes_{suf}")(c_i(G), c_i(F), c_i(B)))
+        ws = torch.empty(ws_bytes // 8 + 1, dtype=torch.float64, device=W.device)
+        ll = torch.empty(1, dtype=torch.float64, device=W.device)
+        gW = torch.empty_like(W)
+        gV = torch.empty(B, dtype=dt, device=W.device)
+        gmean = torch.empty_like(mean)
+        gspread = torch.empty_like(spread)
+        call("poisson_fwdbwd", dt, ptr(y), c_i64(y.shape[1]), ptr(idx), ptr(W), c_i(int(w_softplus)), ptr(V), ptr(mean),
+             ptr(spread), ptr(eps), c_i(G), c_i(F), c_i(B), c_i(E), c_i(int(n_var)), scalar(dt, clamp_min),
+             c_i(int(with_lgamma)), ptr(ll), ptr(gW), ptr(gV), ptr(gmean), ptr(gspread), ptr(ws), c_i64(ws_bytes))
+        ctx.save_for_backward(gW, gV, gmean, gspread, idx)
+        ctx.nV = V.shape[0]
+        return ll.to(dt).reshape(())
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        gW, gV, gmean, gspread, idx = ctx.saved_tensors
+        if idx is not None:
+            full = torch.zeros(ctx.nV, dtype=gV.dtype, device=gV.device)
+            full.index_add_(0, idx, gV)
+            gV = full
+        return None, None, g * gW, g * gV, g * gmean, g * gspread, None, None, None, None, None
+
+
+def poisson_rate(W, V, idx, F, w_softplus=True):
+    """Materialised Poisson rate E x G x B (compatibility path, likelihoods.py:83-85); differentiable
+    through `_PoissonRate`."""
+    return _PoissonRate.apply(W, V, idx, F, w_softplus)
+
+
+class _PoissonRate(Function):
+    @staticmethod
+    def forward(ctx, W, V, idx, F, w_softplus):
+        W, V, F = _c(W), _c(V), _c(F)
+        dt = W.dtype
+        G, nF = W.shape
+        E, _, B = F.shape
+        if idx is not None:
+            idx = _c(idx.to(device=W.device, dtype=torch.int64))
+        rate = torch.empty((E, G, B), dtype=dt, device=W.device)
+        call("poisson_rate", dt, ptr(W), c_i(int(w_softplus)), ptr(V), ptr(idx), ptr(F), ptr(rate), c_i(G), c_i(nF), c_i(B),
+             c_i(E))
+        ctx.save_for_backward(W, V, F, idx, rate)
+        ctx.w_softplus = w_softplus
+        return rate
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        # rate = spV[n] * sum_f w[g,f] ef[e,f,n]; the three contractions below are our own batched GEMM.
+        W, V, F, idx, rate = ctx.saved_tensors
+        g = _c(g)
+        E, G, B = g.shape
+        Vb = V if idx is None else V[idx]
+        spV = torch.nn.functional.softplus(Vb)
+        ef = torch.exp(F)                                              # E x nF x B
+        w = torch.nn.functional.softplus(W) if ctx.w_softplus else W
+        gz = g * spV                                                   # d/d(zr)
+        gF = gemm(w.unsqueeze(0).expand(E, -1, -1).contiguous(), gz, ta=True) * ef
+        gw = gemm(gz, ef, tb=True).sum(0)
+        if ctx.w_softplus:
+            gw = gw * torch.sigmoid(W)
+        gVb = (g * rate).sum((0, 1)) / spV * torch.sigmoid(Vb)
+        if idx is not None:
+            gV = torch.zeros_like(V)
+            gV.index_add_(0, idx, gVb)
+        else:
+            gV = gVb
+        return gw, gV, None, gF, None

@@ -1,0 +1,226 @@
+"""Sparse GP modules with GPzoo's `gpzoo.gp` surface (SVGP, MGGP_SVGP, WSVGP, MGGP_WSVGP, VNNGP,
+GaussianPrior) on top of the fused CUDA kernels.
+
+Constructor arguments, parameter names/shapes (`Z`, `Lu`, `mu`, `groupsZ`), the `jitter`/`K` attributes and
+the returned `(qF, qU, pU)` distributions follow the reference (gp.py:7-399).  Users overwrite the
+parameters after construction (scalar GP -> L-batched), so shapes are resolved at call time.
+
+Inside `forward` the reference's chain cholesky -> cholesky_solve -> Lu Lu^T -> svgp_forward is replaced by
+CholeskyInverse -> Whiten -> Predict (functional.py); `kl_divergence(qU, pU)` on the returned distributions
+dispatches to the fused KL kernel through `register_kl`.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+from torch import distributions
+from torch.distributions import constraints
+from torch.distributions.kl import register_kl
+
+from . import functional as F
+
+
+class VariationalMVN(distributions.MultivariateNormal):
+    """qU = N(mu, Lu Lu^T) carrying the whitened factors so that KL(qU || pU) needs no further solves."""
+
+    def __init__(self, loc, scale_tril, gpz_state):
+        super().__init__(loc, scale_tril=scale_tril, validate_args=False)
+        self._gpz_state = gpz_state          # (T, q, Lc, Lu) L-batched tensors, batched flag
+
+
+class PriorMVN(distributions.MultivariateNormal):
+    """pU = N(0, Lc Lc^T)."""
+
+    def __init__(self, loc, scale_tril):
+        super().__init__(loc, scale_tril=scale_tril, validate_args=False)
+
+
+@register_kl(VariationalMVN, PriorMVN)
+def _kl_variational_prior(qU, pU):
+    T, q, Lc, Lu, batched = qU._gpz_state
+    kl = F.MvnKL.apply(T, q, Lc, Lu)
+    return kl if batched else kl[0]
+
+
+def _as3(t):
+    return t if t.dim() == 3 else t.unsqueeze(0)
+
+
+class _SparseGPBase(nn.Module):
+    clamp_min = 1e-6
+
+    def _init_params(self, kernel, dim, M, jitter):
+        self.kernel = kernel
+        self.jitter = jitter
+        self.Z = nn.Parameter(torch.randn((M, dim)))
+        self.Lu = nn.Parameter(torch.randn((M, M)))
+        self.mu = nn.Parameter(torch.zeros((M,)))
+        self.constraint = constraints.lower_cholesky
+
+    # -- kernel calls -------------------------------------------------------------------------------
+    def _kernel_matrices(self, X, groupsX=None):
+        if groupsX is not None:
+            gZ = self.groupsZ
+            Kxx = self.kernel(X, X, groupsX, groupsX, diag=True)
+            Kzx = self.kernel(self.Z, X, gZ, groupsX)
+            Kzz = self.kernel(self.Z, self.Z, gZ, gZ, _jitter=self.jitter)      # add_jitter fused (gp.py:209/360)
+        else:
+            Kxx = self.kernel(X, X, diag=True)
+            Kzx = self.kernel(self.Z, X)
+            Kzz = self.kernel(self.Z, self.Z, _jitter=self.jitter)
+        return Kxx, Kzx, Kzz
+
+    def _whitened(self, Kzz):
+        """Lc, Linv, Lu, T, q with a common leading L."""
+        Kzz = _as3(Kzz)
+        mu = self.mu if self.mu.dim() == 2 else self.mu.unsqueeze(0)
+        Lu_raw = _as3(self.Lu)
+        L = max(Kzz.shape[0], mu.shape[0], Lu_raw.shape[0])
+        Lc, Linv = F.CholeskyInverse.apply(Kzz)
+        if Lc.shape[0] != L:
+            Lc, Linv = Lc.expand(L, -1, -1), Linv.expand(L, -1, -1)
+        Lu = F.LowerCholesky.apply(Lu_raw.to(Kzz.dtype))
+        if Lu.shape[0] != L:
+            Lu = Lu.expand(L, -1, -1)
+        if mu.shape[0] != L:
+            mu = mu.expand(L, -1)
+        T, q = F.Whiten.apply(Linv, Lu, mu.to(Kzz.dtype))
+        return Lc, Linv, Lu, T, q, L
+
+    def moments(self, X, groupsX=None):
+        """Fused predictive moments: returns dict(mean, var (unclamped), T, q, Lc, Lu), all L-batched."""
+        Kxx, Kzx, Kzz = self._kernel_matrices(X, groupsX)
+        Lc, Linv, Lu, T, q, L = self._whitened(Kzz)
+        Kzx = _as3(Kzx)
+        Kxx = Kxx if Kxx.dim() == 2 else Kxx.unsqueeze(0)
+        if Kzx.shape[0] != L:
+            Kzx, Kxx = Kzx.expand(L, -1, -1), Kxx.expand(L, -1)
+        mean, var = F.Predict.apply(Kxx, Kzx, Linv, T, q)
+        return dict(mean=mean, var=var, T=T, q=q, Lc=Lc, Lu=Lu)
+
+    def _batched(self):
+        return self.mu.dim() == 2 or self.Lu.dim() == 3 or getattr(self.kernel, "_batched", False)
+
+    def _distributions(self, m):
+        b = self._batched()
+        mean, var = (m["mean"], m["var"]) if b else (m["mean"][0], m["var"][0])
+        Lu, Lc = (m["Lu"], m["Lc"]) if b else (m["Lu"][0], m["Lc"][0])
+        qF = distributions.Normal(mean, torch.clamp(var, min=self.clamp_min) ** 0.5, validate_args=False)
+        mu = self.mu.to(Lu.dtype)
+        qU = VariationalMVN(mu, Lu, (m["T"], m["q"], m["Lc"], m["Lu"], b))
+        pU = PriorMVN(torch.zeros_like(mu), Lc)
+        return qF, qU, pU
+
+
+class SVGP(_SparseGPBase):
+    """Titsias/Hensman sparse variational GP (gp.py:149-232)."""
+    clamp_min = 1e-6                                   # gp.py:228
+
+    def __init__(self, kernel, dim=1, M=50, jitter=1e-4):
+        super().__init__()
+        self._init_params(kernel, dim, M, jitter)
+        self.precompute_distance = False               # attribute kept (gp.py:157); the method it shadows is dead code
+
+    def kernel_forward(self, X, Z, **args):
+        return self.kernel(X, Z, **args)
+
+    def forward_kernels(self, X, Z=None, **args):
+        Kxx, Kzx, Kzz = self.kernel(X, X, diag=True), self.kernel(self.Z, X), self.kernel(self.Z, self.Z)
+        return Kxx, Kzx, Kzz
+
+    def forward(self, X, verbose=False):
+        return self._distributions(self.moments(X))
+
+
+class MGGP_SVGP(_SparseGPBase):
+    """SVGP with a multi-group kernel; owns the inducing points' group labels (gp.py:329-382)."""
+    clamp_min = 5e-2                                   # gp.py:378
+
+    def __init__(self, kernel, dim=1, M=50, jitter=1e-4, n_groups=2):
+        super().__init__()
+        self.kernel = kernel
+        self.jitter = jitter
+        self.Z = nn.Parameter(torch.randn((M, dim)))
+        self.groupsZ = nn.Parameter(torch.randint(0, n_groups, (M,)).type(torch.LongTensor), requires_grad=False)
+        self.Lu = nn.Parameter(torch.randn((M, M)))
+        self.mu = nn.Parameter(torch.zeros((M,)))
+        self.constraint = constraints.lower_cholesky
+
+    def forward(self, X, groupsX, verbose=False):
+        return self._distributions(self.moments(X, groupsX))
+
+    def moments(self, X, groupsX=None):
+        if groupsX is None:
+            raise TypeError("MGGP_SVGP needs groupsX")
+        return super().moments(X, groupsX)
+
+
+class WSVGP(_SparseGPBase):
+    """Whitened SVGP (gp.py:235-322): W = Kxz Lc^-T, var = (Kxx - sum W^2) + sum (W Lu)^2, pZ = None.
+    Same fused predict kernel with T := Lu and q := mu.  The reference clamps (Kxx - sum W^2) at 0 before adding
+    the second term (gp.py:287) — a guard against round-off only (the term is >= 0 in exact arithmetic);
+    here the sum is formed in one pass and clamped at 0 as a whole."""
+    clamp_min = 0.0
+
+    def __init__(self, kernel, dim=1, M=50, jitter=1e-4):
+        super().__init__()
+        self._init_params(kernel, dim, M, jitter)
+
+    def kernel_forward(self, X, Z, **args):
+        return self.kernel(X, Z, **args)
+
+    def forward_kernels(self, X, **args):
+        return self._kernel_matrices(X, args.get("groupsX"))
+
+    def _whitened_moments(self, Kxx, Kzx, Kzz):
+        Kzz, Kzx = _as3(Kzz), _as3(Kzx)
+        Kxx = Kxx if Kxx.dim() == 2 else Kxx.unsqueeze(0)
+        mu = self.mu if self.mu.dim() == 2 else self.mu.unsqueeze(0)
+        Lu = F.LowerCholesky.apply(_as3(self.Lu).to(Kzz.dtype))
+        L = max(Kzz.shape[0], mu.shape[0], Lu.shape[0])
+        Lc, Linv = F.CholeskyInverse.apply(Kzz)
+        ex = lambda t: t if t.shape[0] == L else t.expand(L, *t.shape[1:])
+        mean, var = F.Predict.apply(ex(Kxx), ex(Kzx), ex(Linv), ex(Lu), ex(mu.to(Kzz.dtype)))
+        return mean, var, Lu
+
+    def forward(self, X, verbose=False, **args):
+        Kxx, Kzx, Kzz = self.forward_kernels(X, **args)
+        mean, var, Lu = self._whitened_moments(Kxx, Kzx, Kzz)
+        b = self._batched()
+        if not b:
+            mean, var, Lu = mean[0], var[0], Lu[0]
+        qF = distributions.Normal(mean, torch.clamp(var, min=0.0) ** 0.5, validate_args=False)
+        qZ = distributions.MultivariateNormal(self.mu.to(Lu.dtype), scale_tril=Lu, validate_args=False)
+        return qF, qZ, None
+
+
+class MGGP_WSVGP(WSVGP):
+    """gp.py:385-399."""
+
+    def __init__(self, kernel, dim=1, M=50, n_groups=2, jitter=1e-4):
+        super().__init__(kernel, dim, M, jitter)
+        self.groupsZ = nn.Parameter(torch.randint(0, n_groups, (M,)).type(torch.LongTensor), requires_grad=False)
+
+
+class GaussianPrior(nn.Module):
+    """Non-spatial mean-field factors (gp.py:125-146): per-spot mean and softplus(scale), prior N(0, scale_pf).
+    O(L*N) element-wise parameters; their fused use is inside the Poisson likelihood kernel."""
+
+    def __init__(self, y, L=10):
+        super().__init__()
+        D, N = y.shape
+        self.mean = nn.Parameter(torch.randn(size=(L, N)))
+        self.scale = nn.Parameter(torch.rand(size=(L, N)))
+        self.scale_pf = 1.0
+
+    def _make(self, mean, scale_raw):
+        scale = torch.nn.functional.softplus(scale_raw)
+        qF = distributions.Normal(mean, scale, validate_args=False)
+        pF = distributions.Normal(torch.zeros_like(mean), self.scale_pf * torch.ones_like(scale), validate_args=False)
+        return qF, pF
+
+    def forward(self):
+        return self._make(self.mean, self.scale)
+
+    def forward_batched(self, idx):
+        return self._make(self.mean[:, idx], self.scale[:, idx])

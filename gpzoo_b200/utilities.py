@@ -1,0 +1,91 @@
+"""Hot-path helpers and training loops with GPzoo's `gpzoo.utilities` names.
+
+Only the functions on or next to the ELBO path are provided: the data
+preparation / plotting helpers of the reference (utilities.py:14-23, 38-375, 421-448) are CPU
+pre-processing and out of scope.  The training loops call the fused `model.elbo(...)`.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import functional as F
+from .kernels import embed_distance_matrix as _embed_distance_matrix  # noqa: F401  (utilities.py:459-469)
+
+
+def whitened_KL(mz, Lz):
+    """0.5 (-2 sum log diag Lz + |Lz|_F^2 + |mz|^2 - M)   (utilities.py:27-36).
+
+    = KL(N(mz, Lz Lz^T) || N(0, I)): the fused KL kernel with Lc = I (so T = Lz, q = mz).  Accepts a single GP
+    (Lz M x M) like the reference, and additionally L-batched inputs (returning one value per factor), for
+    which the reference's torch.diagonal call is wrong."""
+    single = Lz.dim() == 2
+    Lz3 = Lz.unsqueeze(0) if single else Lz
+    mz2 = mz.unsqueeze(0) if mz.dim() == 1 else mz
+    eye = torch.eye(Lz3.shape[-1], dtype=Lz3.dtype, device=Lz3.device).expand_as(Lz3).contiguous()
+    kl = F.MvnKL.apply(Lz3.contiguous(), mz2.contiguous(), eye, Lz3.contiguous())
+    return kl[0] if single else kl
+
+
+def add_jitter(K, jitter=1e-3):
+    """In-place diagonal jitter, returns the same tensor (utilities.py:407-418).  The GP modules fuse the jitter
+    into the kernel-matrix build instead; this stays for user code."""
+    K.diagonal(dim1=-2, dim2=-1).add_(jitter)
+    return K
+
+
+def _step(model, optimizer, elbo_fn, clamp_W):
+    optimizer.zero_grad(set_to_none=True)
+    loss = -elbo_fn()
+    loss.backward()
+    optimizer.step()
+    with torch.no_grad():
+        for w in clamp_W:
+            w.clamp_(min=0.0)                      # utilities.py:523-524, 623
+    return loss.detach()
+
+
+def _finish(losses):
+    F.check_cholesky_info()
+    return [float(v) for v in torch.stack(losses).cpu()] if losses else []
+
+
+def train(model, optimizer, X, y, device=None, steps=200, E=20, **kwargs):
+    """Full-batch loop (utilities.py:471-493).  The per-step `loss.item()` sync of the reference is replaced
+    by one transfer at the end."""
+    losses = [_step(model, optimizer, lambda: model.elbo(X, y, E=E, **kwargs), ()) for _ in range(steps)]
+    return _finish(losses)
+
+
+def _sample_idx(N, batch_size, device):
+    # utilities.py:605 draws torch.multinomial(ones(N), batch_size) on the CPU; randperm on the device is the
+    # same distribution (uniform without replacement) with no host round-trip.
+    return torch.randperm(N, device=device)[:batch_size]
+
+
+def train_batched(model, optimizer, X, y, device=None, steps=200, E=20, batch_size=1000, **kwargs):
+    """Minibatch loop (utilities.py:600-631), including the W >= 0 clamp after each update."""
+    losses = []
+    for _ in range(steps):
+        idx = _sample_idx(X.shape[0], batch_size, X.device)
+        kw = dict(kwargs)
+        if "groupsX" in kw:
+            kw["groupsX"] = kw["groupsX"][idx]
+        losses.append(_step(model, optimizer, lambda: model.elbo(X, y, idx=idx, E=E, **kw), (model.W,)))
+    return _finish(losses)
+
+
+def train_hybrid(model, optimizer, X, y, device=None, steps=200, E=20, **kwargs):
+    """utilities.py:531-563 (two KL terms; W, W2 clamped)."""
+    ws = [w for w in (getattr(model, "W", None), getattr(model, "W2", None)) if w is not None]
+    losses = [_step(model, optimizer, lambda: model.elbo(X, y, E=E, **kwargs), ws) for _ in range(steps)]
+    return _finish(losses)
+
+
+def train_hybrid_batched(model, optimizer, X, y, device=None, steps=200, E=20, batch_size=1000, **kwargs):
+    """utilities.py:498-529; uses the y*log(rate)-rate form of the log-likelihood (utilities.py:507)."""
+    ws = [w for w in (getattr(model, "W", None), getattr(model, "W2", None)) if w is not None]
+    losses = []
+    for _ in range(steps):
+        idx = _sample_idx(X.shape[0], batch_size, X.device)
+        losses.append(_step(model, optimizer, lambda: model.elbo(X, y, idx=idx, E=E, with_lgamma=False, **kwargs), ws))
+    return _finish(losses)

@@ -1,0 +1,126 @@
+/* gpzoo_b200 C ABI — the drop-in boundary of the B200-native sparse-GP ELBO hot path.
+ *
+ * The reference (luisdiaz1997/GPzoo) has no FFI: its boundary is the PyTorch nn.Module surface
+ * (gpzoo.kernels / gpzoo.gp / gpzoo.likelihoods).  The host side of this project keeps that surface in
+ * Python (package gpzoo_b200) and reaches the CUDA kernels exclusively through the entry points below,
+ * loaded with ctypes from libgpzoo_b200.so.  Each entry point names the reference call site it replaces
+ * (paths relative to the reference's gpzoo/ directory).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer borrowed from the caller (the library never allocates or frees);
+ *     scratch space is passed in and sized by the matching *_workspace_bytes query;
+ *   - tensors are row-major, innermost dimension contiguous; batch (factor) index L outermost;
+ *   - `stream` is a cudaStream_t passed as void*; all work is asynchronous on that stream;
+ *   - return value: 0 on success, -cudaError_t on a CUDA failure, <= -1000 for argument errors;
+ *   - suffix _f32 / _f64 selects the arithmetic type (fp64 exists for the 1e-10 parity check);
+ *   - no global state; re-entrant; thread-safe per stream.
+ */
+#ifndef GPZOO_B200_H
+#define GPZOO_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+
+int gpz_abi_version(void);
+/* cudaGetErrorString for -rc, or a library message for rc <= -1000 */
+const char* gpz_error_string(int rc);
+
+/* ---- K1 kernel-matrix build: kernels.py:114-130 (RBF), 141-155 (NSF_RBF), 172-191 (MGGP_RBF),
+ *      204-228 (MGGP_NSF_RBF); jitter = utilities.py:407-418 (add_jitter) fused on the diagonal.
+ *      out[l,i,j] = sigma_l^2 exp(-0.5 |x1_i-x2_j|^2/(ls_l^2 den))/den^p_half (+ jitter if i==j),
+ *      den = a_l r2[g1_i,g2_j] + 1.  Pass a=r2=g1=g2=NULL, ng=0 for the plain RBF. */
+int gpz_kernel_build_fwd_f32(const float* x1, const float* x2, const float* sigma, const float* ls, const float* a,
+                             const float* r2, const int64_t* g1, const int64_t* g2, int n1, int n2, int D, int L, int ng,
+                             float p_half, float jitter, float* out, void* stream);
+int gpz_kernel_build_fwd_f64(const double* x1, const double* x2, const double* sigma, const double* ls, const double* a,
+                             const double* r2, const int64_t* g1, const int64_t* g2, int n1, int n2, int D, int L, int ng,
+                             double p_half, double jitter, double* out, void* stream);
+/* backward of the above (autograd of kernels.py forward): G = dLoss/dout; g_x1/g_x2/g_a may be NULL */
+int gpz_kernel_build_bwd_f32(const float* x1, const float* x2, const float* sigma, const float* ls, const float* a,
+                             const float* r2, const int64_t* g1, const int64_t* g2, int n1, int n2, int D, int L, int ng,
+                             float p_half, const float* G, float* g_x1, float* g_x2, float* g_sigma, float* g_ls, float* g_a,
+                             void* stream);
+int gpz_kernel_build_bwd_f64(const double* x1, const double* x2, const double* sigma, const double* ls, const double* a,
+                             const double* r2, const int64_t* g1, const int64_t* g2, int n1, int n2, int D, int L, int ng,
+                             double p_half, const double* G, double* g_x1, double* g_x2, double* g_sigma, double* g_ls,
+                             double* g_a, void* stream);
+/* kernels.py:118,123-124 (return_distance=True): Euclidean distances n1 x n2 */
+int gpz_cdist_f32(const float* x1, const float* x2, float* out, int n1, int n2, int D, void* stream);
+int gpz_cdist_f64(const double* x1, const double* x2, double* out, int n1, int n2, int D, void* stream);
+
+/* ---- K2 batched Cholesky: gp.py:213, 360, 55, 270 (torch.linalg.cholesky).  A (L x M x M) is overwritten by
+ *      its lower factor (upper triangle zeroed); info[l] = 0 or (1-based) index of the first non-positive pivot. */
+int gpz_potrf_f32(float* A, int M, int L, int* info, void* stream);
+int gpz_potrf_f64(double* A, int M, int L, int* info, void* stream);
+/* X = Lc^-1 (lower).  With it the two triangular solves of gp.py:218 (torch.cholesky_solve) and the solves
+ * inside kl_divergence(qU,pU) (torch kl.py) become triangular products.  tmp: L x 64 x M scratch. */
+int gpz_trtri_f32(const float* Lc, float* X, float* tmp, int M, int L, void* stream);
+int gpz_trtri_f64(const double* Lc, double* X, double* tmp, int M, int L, void* stream);
+/* strided-batched D = alpha op(A) op(B) + beta D with triangular-structure skipping (see csrc/gemm_simt.cuh):
+ * S = Lu Lu^T (gp.py:221), W@(S-Kzz) (utilities.py:395) and the O(M^3) backward products are built from it. */
+int gpz_gemm_f32(int ta, int tb, int m, int n, int k, float alpha, const float* A, int64_t lda, int64_t sA, const float* B,
+                 int64_t ldb, int64_t sB, float beta, float* D, int64_t ldd, int64_t sD, int batch, int a_tri, int b_tri,
+                 int d_tri, int splitk, void* stream);
+int gpz_gemm_f64(int ta, int tb, int m, int n, int k, double alpha, const double* A, int64_t lda, int64_t sA,
+                 const double* B, int64_t ldb, int64_t sB, double beta, double* D, int64_t ldd, int64_t sD, int batch,
+                 int a_tri, int b_tri, int d_tri, int splitk, void* stream);
+/* gp.py:220 transform_to(lower_cholesky): out = tril(raw,-1) + diag(exp(diag raw)), and its backward */
+int gpz_lower_cholesky_fwd_f32(const float* raw, float* out, int M, int L, void* stream);
+int gpz_lower_cholesky_fwd_f64(const double* raw, double* out, int M, int L, void* stream);
+int gpz_lower_cholesky_bwd_f32(const float* g, const float* out, float* graw, int M, int L, void* stream);
+int gpz_lower_cholesky_bwd_f64(const double* g, const double* out, double* graw, int M, int L, void* stream);
+/* mode 0: tril with halved diagonal (Cholesky backward Phi); 1: (X+X^T)/2 (out != in); 2: tril */
+int gpz_tri_op_f32(const float* in, float* out, int M, int L, int mode, void* stream);
+int gpz_tri_op_f64(const double* in, double* out, int M, int L, int mode, void* stream);
+
+/* ---- K3/K4 fused predictive mean and variance: gp.py:218-225 + utilities.py:382-397 (svgp_forward).
+ *      Inputs Kzx (L x M x N), Linv = Lc^-1, T = Linv Lu, q = Linv mu, kxx (L x N).
+ *      Outputs A = Linv Kzx, C = T^T A (both L x M x N, kept for the backward), mean, var (L x N). */
+int gpz_svgp_predict_fwd_f32(const float* Kzx, const float* Linv, const float* T, const float* q, const float* kxx,
+                             float* A, float* C, float* mean, float* var, int M, int N, int L, void* stream);
+int gpz_svgp_predict_fwd_f64(const double* Kzx, const double* Linv, const double* T, const double* q, const double* kxx,
+                             double* A, double* C, double* mean, double* var, int M, int N, int L, void* stream);
+/* backward; C is overwritten (becomes gC), gA is scratch (L x M x N); gLinv and gT must be zero-filled by the caller */
+int gpz_svgp_predict_bwd_f32(const float* Kzx, const float* Linv, const float* T, const float* q, const float* A, float* C,
+                             const float* gm, const float* gv, float* gA, float* gKzx, float* gLinv, float* gT, float* gq,
+                             int M, int N, int L, void* stream);
+int gpz_svgp_predict_bwd_f64(const double* Kzx, const double* Linv, const double* T, const double* q, const double* A,
+                             double* C, const double* gm, const double* gv, double* gA, double* gKzx, double* gLinv,
+                             double* gT, double* gq, int M, int N, int L, void* stream);
+
+/* ---- K5 KL(qU || pU): utilities.py:481,616 -> torch kl.py MVN||MVN, from the whitened T, q */
+int gpz_mvn_kl_fwd_f32(const float* T, const float* q, const float* Lc, const float* Lu, float* kl, int M, int L, void* stream);
+int gpz_mvn_kl_fwd_f64(const double* T, const double* q, const double* Lc, const double* Lu, double* kl, int M, int L,
+                       void* stream);
+int gpz_mvn_kl_bwd_f32(const float* g, const float* T, const float* q, const float* Lc, const float* Lu, float* gT, float* gq,
+                       float* gLc, float* gLu, int M, int L, void* stream);
+int gpz_mvn_kl_bwd_f64(const double* g, const double* T, const double* q, const double* Lc, const double* Lu, double* gT,
+                       double* gq, double* gLc, double* gLu, int M, int L, void* stream);
+
+/* ---- K7 fused Poisson log-likelihood + loading contraction, forward and backward in one pass:
+ *      likelihoods.py:49-53 (get_rate), 80-97 (NSF2), 110-145 (Hybrid_NSF2), 226-253 (NSF), 304-330 (Hybrid_NSF);
+ *      utilities.py:479,507,611-614 (ELBO reduction); torch poisson.py log_prob.
+ *      spread[f,:] is a variance (clamped at clamp_min, gp.py:228/378/118) for f < n_var and a std-dev otherwise.
+ *      ll: one double on the device.  ws sized by gpz_poisson_workspace_bytes_*. */
+int64_t gpz_poisson_workspace_bytes_f32(int G, int F, int B);
+int64_t gpz_poisson_workspace_bytes_f64(int G, int F, int B);
+int gpz_poisson_fwdbwd_f32(const float* y, int64_t y_ld, const int64_t* idx, const float* W, int w_softplus, const float* V,
+                           const float* mean, const float* spread, const float* eps, int G, int F, int B, int E, int n_var,
+                           float clamp_min, int with_lgamma, double* ll, float* gW, float* gV, float* gmean, float* gspread,
+                           void* ws, int64_t ws_bytes, void* stream);
+int gpz_poisson_fwdbwd_f64(const double* y, int64_t y_ld, const int64_t* idx, const double* W, int w_softplus,
+                           const double* V, const double* mean, const double* spread, const double* eps, int G, int F, int B,
+                           int E, int n_var, double clamp_min, int with_lgamma, double* ll, double* gW, double* gV,
+                           double* gmean, double* gspread, void* ws, int64_t ws_bytes, void* stream);
+/* compatibility path: materialise pY.rate (E x G x B) for callers of model.forward() (likelihoods.py:83-85) */
+int gpz_poisson_rate_f32(const float* W, int w_softplus, const float* V, const int64_t* idx, const float* F, float* rate,
+                         int G, int nF, int B, int E, void* stream);
+int gpz_poisson_rate_f64(const double* W, int w_softplus, const double* V, const int64_t* idx, const double* F, double* rate,
+                         int G, int nF, int B, int E, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPZOO_B200_H */

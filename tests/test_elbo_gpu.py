@@ -1,0 +1,196 @@
+"""GPU parity proper: the module surface (gpzoo_b200.kernels / gp / likelihoods) against the golden vectors the
+UNMODIFIED reference produced (tests/golden/, oracle/gen_golden.py), for the fused `model.elbo` path and for the
+drop-in distribution-returning path.  Tolerances (BASELINE.json north_star): 1e-10 relative in fp64, 1e-4 in fp32
+(fp32 run compared with the reference's fp64 result), relative L2 per tensor."""
+import pytest
+import torch
+from torch import distributions
+
+from tests.helpers import load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = {torch.float64: 1e-10, torch.float32: 1e-4}
+
+
+def _P(t, dt):
+    return torch.nn.Parameter(t.to(DEV, dt) if t.is_floating_point() else t.to(DEV))
+
+
+def build_nsf(inp, dt):
+    import gpzoo_b200 as gz
+    L, M = inp["mu"].shape
+    D = inp["X"].shape[1]
+    mg = "groupsX" in inp
+    if mg:
+        ng = inp["group_distances"].shape[0]
+        kern = gz.kernels.MGGP_NSF_RBF(L=L, n_groups=ng)
+        kern.set_group_distances(inp["group_distances"].float())        # the reference embeds in fp32
+        kern.embedding = torch.nn.Parameter(kern.embedding.to(DEV, dt), requires_grad=False)
+        kern.group_diff_param = _P(inp["gdp"], dt)
+        gp = gz.gp.MGGP_SVGP(kern, dim=D, M=M, jitter=inp["jitter"], n_groups=ng)
+        gp.groupsZ = torch.nn.Parameter(inp["groupsZ"].to(DEV), requires_grad=False)
+    else:
+        kern = gz.kernels.NSF_RBF(L=L)
+        gp = gz.gp.SVGP(kern, dim=D, M=M, jitter=inp["jitter"])
+    kern.sigma, kern.lengthscale = _P(inp["sigma"], dt), _P(inp["lengthscale"], dt)
+    gp.Z, gp.mu, gp.Lu = _P(inp["Z"], dt), _P(inp["mu"], dt), _P(inp["Lu_raw"], dt)
+    model = gz.likelihoods.NSF2(gp, inp["y"], L=L)
+    model.W, model.V = _P(inp["W"], dt), _P(inp["V"], dt)
+    named = dict(Z=gp.Z, sigma=kern.sigma, lengthscale=kern.lengthscale, mu=gp.mu, Lu_raw=gp.Lu, W=model.W, V=model.V)
+    if mg:
+        named["gdp"] = kern.group_diff_param
+    return model, named
+
+
+def _check_grads(named, ggrad, tol):
+    for k, v in ggrad.items():
+        g = named[k].grad
+        assert g is not None, k
+        assert relerr(g, v) < tol, (k, relerr(g, v))
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+@pytest.mark.parametrize("name", ["nsf_svgp_box", "nsf_svgp_slideseq", "nsf_svgp_1d", "nsf_mggp"])
+def test_nsf_fused_elbo(name, dt):
+    inp, gout, ggrad = load_golden(name)
+    model, named = build_nsf(inp, dt)
+    kw = {"groupsX": inp["groupsX"].to(DEV)} if "groupsX" in inp else {}
+    elbo, parts = model.elbo(inp["X"].to(DEV, dt), inp["y"].to(DEV, dt), E=inp["eps"].shape[0],
+                             eps=inp["eps"].to(DEV, dt), return_parts=True, **kw)
+    tol = TOL[dt]
+    assert relerr(elbo, gout["elbo"]) < tol
+    assert relerr(parts["ll"], gout["ll"]) < tol and relerr(parts["kl"], gout["kl"]) < tol
+    assert relerr(parts["mean"], gout["mean"]) < tol
+    cmin = 5e-2 if "groupsX" in inp else 1e-6
+    assert relerr(parts["var"].clamp(min=cmin), gout["var"]) < tol
+    (-elbo).backward()
+    for p in named.values():
+        p.grad.neg_()
+    _check_grads(named, ggrad, tol)
+    assert torch.equal(named["Lu_raw"].grad.triu(1), torch.zeros_like(named["Lu_raw"].grad))   # upper triangle == 0
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_nsf_dropin_distributions(dt):
+    """The reference's own training-loop expression on the returned distributions (utilities.py:479-481)."""
+    inp, gout, ggrad = load_golden("nsf_svgp_box")
+    model, named = build_nsf(inp, dt)
+    pY, qF, qU, pU = model(X=inp["X"].to(DEV, dt), E=inp["eps"].shape[0], eps=inp["eps"].to(DEV, dt))
+    ELBO = pY.log_prob(inp["y"].to(DEV, dt)).mean(axis=0).sum()
+    ELBO = ELBO - torch.sum(distributions.kl_divergence(qU, pU))
+    tol = TOL[dt]
+    assert relerr(ELBO, gout["elbo"]) < tol
+    assert relerr(qF.mean, gout["mean"]) < tol and relerr(qF.scale ** 2, gout["var"]) < tol
+    assert relerr(qU.scale_tril, gout["Lu"]) < tol and relerr(pU.scale_tril, gout["Lc"]) < tol
+    (-ELBO).backward()
+    for p in named.values():
+        p.grad.neg_()
+    _check_grads(named, ggrad, tol)
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_nsf_minibatch(dt):
+    """forward_batched / elbo(idx=...) with the y*log(rate)-rate likelihood form (utilities.py:507)."""
+    inp, gout, ggrad = load_golden("nsf_svgp_box_batched")
+    model, named = build_nsf(inp, dt)
+    idx = inp["idx"].to(DEV)
+    eps = inp["eps"][:, :, inp["idx"]].to(DEV, dt)
+    elbo = model.elbo(inp["X"].to(DEV, dt), inp["y"].to(DEV, dt), idx=idx, E=eps.shape[0], eps=eps, with_lgamma=False)
+    tol = TOL[dt]
+    assert relerr(elbo, gout["elbo"]) < tol
+    (-elbo).backward()
+    for p in named.values():
+        p.grad.neg_()
+    _check_grads(named, ggrad, tol)
+    assert int((named["V"].grad != 0).sum()) == len(idx)
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_svgp_gaussian_config1(dt):
+    import gpzoo_b200 as gz
+    inp, gout, ggrad = load_golden("svgp_gaussian")
+    kern = gz.kernels.RBF()
+    kern.sigma, kern.lengthscale = _P(inp["sigma"], dt), _P(inp["lengthscale"], dt)
+    gp = gz.gp.SVGP(kern, dim=inp["X"].shape[1], M=inp["mu"].shape[0], jitter=inp["jitter"])
+    gp.Z, gp.mu, gp.Lu = _P(inp["Z"], dt), _P(inp["mu"], dt), _P(inp["Lu_raw"], dt)
+    model = gz.likelihoods.GaussianLikelihood(gp)
+    model.noise = _P(inp["noise"], dt)
+    pY, qF, qU, pU = model(X=inp["X"].to(DEV, dt), E=inp["eps"].shape[0], eps=inp["eps"].to(DEV, dt))
+    assert qF.mean.shape == inp["y"].shape
+    ELBO = pY.log_prob(inp["y"].to(DEV, dt)).mean(axis=0).sum() - torch.sum(distributions.kl_divergence(qU, pU))
+    tol = TOL[dt]
+    assert relerr(ELBO, gout["elbo"]) < tol and relerr(qF.mean, gout["mean"]) < tol
+    (-ELBO).backward()
+    named = dict(Z=gp.Z, sigma=kern.sigma, lengthscale=kern.lengthscale, mu=gp.mu, Lu_raw=gp.Lu, noise=model.noise)
+    for p in named.values():
+        p.grad.neg_()
+    _check_grads(named, ggrad, tol)
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_hybrid(dt):
+    import gpzoo_b200 as gz
+    inp, gout, ggrad = load_golden("nsf_hybrid")
+    L, M = inp["mu"].shape
+    T = inp["Wcf"].shape[1]
+    kern = gz.kernels.NSF_RBF(L=L)
+    kern.sigma, kern.lengthscale = _P(inp["sigma"], dt), _P(inp["lengthscale"], dt)
+    gp = gz.gp.SVGP(kern, dim=2, M=M, jitter=inp["jitter"])
+    gp.Z, gp.mu, gp.Lu = _P(inp["Z"], dt), _P(inp["mu"], dt), _P(inp["Lu_raw"], dt)
+    prior = gz.gp.GaussianPrior(inp["y"], L=T)
+    prior.mean, prior.scale = _P(inp["cf_mean"], dt), _P(inp["cf_scale"], dt)
+    model = gz.likelihoods.Hybrid_NSF2(gp, prior, inp["y"], L=L, T=T)
+    model.sf.W, model.cf.W, model.V = _P(inp["W"], dt), _P(inp["Wcf"], dt), _P(inp["V"], dt)
+    idx = inp["idx"].to(DEV)
+    eps = inp["eps"][:, :, inp["idx"]].to(DEV, dt)
+    eps2 = inp["eps2"][:, :, inp["idx"]].to(DEV, dt)
+    named = dict(Z=gp.Z, sigma=kern.sigma, lengthscale=kern.lengthscale, mu=gp.mu, Lu_raw=gp.Lu, W=model.sf.W,
+                 V=model.V, Wcf=model.cf.W, cf_mean=prior.mean, cf_scale=prior.scale)
+    tol = TOL[dt]
+    elbo = model.elbo(inp["X"].to(DEV, dt), inp["y"].to(DEV, dt), idx=idx, E=eps.shape[0], eps=eps, eps2=eps2)
+    assert relerr(elbo, gout["elbo"]) < tol
+    (-elbo).backward()
+    for p in named.values():
+        p.grad.neg_()
+    _check_grads(named, ggrad, tol)
+    # drop-in 6-tuple
+    for p in named.values():
+        p.grad = None
+    pY, qF1, qU, pU, qF2, pF2 = model.forward_batched(X=inp["X"].to(DEV, dt), idx=idx, E=eps.shape[0], eps=eps, eps2=eps2)
+    E2 = pY.log_prob(inp["y"].to(DEV, dt)[:, idx]).mean(axis=0).sum() - distributions.kl_divergence(qU, pU).sum() \
+        - distributions.kl_divergence(qF2, pF2).sum()
+    assert relerr(E2, gout["elbo"]) < tol
+
+
+def test_size_independent_properties_fp32():
+    """Properties that hold at any size (checked at a mid size the oracle would be slow on):
+    sharding the spots and summing the per-shard likelihood terms and gradients reproduces the un-sharded step
+    (the data-parallel identity), and the ELBO is invariant to a permutation of the spots."""
+    import gpzoo_b200 as gz
+    from gpzoo_b200 import synthetic
+    prob = synthetic.nsf_problem(N=4096, M=256, L=4, G=64, E=1, seed=2, coord_scale=100.0, lengthscale=9.0,
+                                 jitter=1e-1, dtype=torch.float32, device=DEV)
+    model, named = build_nsf(prob, torch.float32)
+    X, y, eps = prob["X"], prob["y"], prob["eps"]
+    e0, p0 = model.elbo(X, y, E=1, eps=eps, return_parts=True)
+    e0.backward()
+    g0 = {k: v.grad.clone() for k, v in named.items()}
+    perm = torch.randperm(4096, device=DEV)
+    with torch.no_grad():
+        model.V.copy_(model.V[perm])
+    e1 = model.elbo(X[perm], y[:, perm], E=1, eps=eps[:, :, perm])
+    assert relerr(e1, e0) < 1e-5
+    with torch.no_grad():
+        model.V.copy_(model.V[torch.argsort(perm)])
+    for v in named.values():
+        v.grad = None
+    ll_sum = 0
+    for sh in range(4):
+        idx = torch.arange(sh * 1024, (sh + 1) * 1024, device=DEV)
+        e, p = model.elbo(X, y, idx=idx, E=1, eps=eps[:, :, idx], return_parts=True)
+        (p["ll"] - (p["kl"].sum() if sh == 0 else 0)).backward()      # KL counted once
+        ll_sum = ll_sum + p["ll"].detach()
+    assert relerr(ll_sum, p0["ll"]) < 1e-5
+    for k, v in named.items():
+        assert relerr(v.grad, g0[k]) < 2e-4, k

@@ -1,0 +1,239 @@
+"""GPU: each CUDA kernel (through the C ABI) against the CPU oracle / plain fp64 torch on seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import GOLDEN, relerr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _tol(dt):
+    return 1e-11 if dt == torch.float64 else 2e-5
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+@pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
+def test_gemm_layouts(dt, ta, tb):
+    from gpzoo_b200 import functional as F
+    g = torch.Generator().manual_seed(0)
+    b, m, n, k = 3, 150, 77, 203
+    A = torch.randn((b, k, m) if ta else (b, m, k), generator=g, dtype=torch.float64)
+    B = torch.randn((b, n, k) if tb else (b, k, n), generator=g, dtype=torch.float64)
+    ref = (A.transpose(1, 2) if ta else A) @ (B.transpose(1, 2) if tb else B)
+    out = F.gemm(A.to(DEV, dt), B.to(DEV, dt), ta=ta, tb=tb)
+    assert relerr(out, ref) < _tol(dt)
+    out2 = F.gemm(A.to(DEV, dt), B.to(DEV, dt), ta=ta, tb=tb, splitk=4)
+    assert relerr(out2, ref) < _tol(dt)
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_gemm_triangular_flags(dt):
+    from gpzoo_b200 import functional as F
+    g = torch.Generator().manual_seed(1)
+    b, m = 2, 300
+    Lo = torch.tril(torch.randn(b, m, m, generator=g, dtype=torch.float64))
+    R = torch.randn(b, m, 190, generator=g, dtype=torch.float64)
+    assert relerr(F.gemm(Lo.to(DEV, dt), R.to(DEV, dt), a_tri=1), Lo @ R) < _tol(dt)
+    assert relerr(F.gemm(Lo.to(DEV, dt), R.to(DEV, dt), ta=True, a_tri=2), Lo.transpose(1, 2) @ R) < _tol(dt)
+    Lo2 = torch.tril(torch.randn(b, m, m, generator=g, dtype=torch.float64))
+    assert relerr(F.gemm(Lo.to(DEV, dt), Lo2.to(DEV, dt), a_tri=1, b_tri=1, d_tri=1), Lo @ Lo2) < _tol(dt)
+    out = F.gemm(R.to(DEV, dt), R.to(DEV, dt), tb=True, d_tri=1, splitk=2)
+    assert relerr(out, torch.tril(R @ R.transpose(1, 2))) < _tol(dt)
+    up = F.gemm(Lo.to(DEV, dt), Lo2.to(DEV, dt), ta=True, tb=True, a_tri=2, b_tri=2)
+    assert relerr(up, Lo.transpose(1, 2) @ Lo2.transpose(1, 2)) < _tol(dt)
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+@pytest.mark.parametrize("M", [25, 64, 200, 515])
+def test_cholesky_and_inverse(dt, M):
+    from gpzoo_b200 import functional as F
+    g = torch.Generator().manual_seed(M)
+    L = 3
+    Q = torch.randn(L, M, M, generator=g, dtype=torch.float64)
+    K = Q @ Q.transpose(1, 2) / M + torch.eye(M, dtype=torch.float64)
+    Lc, Linv = F.CholeskyInverse.apply(K.to(DEV, dt))
+    ref = torch.linalg.cholesky(K)
+    tol = 1e-11 if dt == torch.float64 else 5e-5
+    assert relerr(Lc, ref) < tol
+    assert relerr(Linv, torch.linalg.inv(ref)) < tol
+    assert torch.equal(Lc.triu(1), torch.zeros_like(Lc)) and torch.equal(Linv.triu(1), torch.zeros_like(Linv))
+
+
+def test_cholesky_not_pd_raises():
+    from gpzoo_b200 import functional as F
+    K = torch.eye(40, dtype=torch.float64).repeat(2, 1, 1)
+    K[1, 17, 17] = -1.0
+    with pytest.raises(torch.linalg.LinAlgError):
+        F.CholeskyInverse.apply(K.to(DEV))
+
+
+def test_cholesky_backward_fp64():
+    from gpzoo_b200 import functional as F
+    g = torch.Generator().manual_seed(7)
+    L, M = 2, 90
+    Q = torch.randn(L, M, M, generator=g, dtype=torch.float64)
+    K = (Q @ Q.transpose(1, 2) / M + torch.eye(M, dtype=torch.float64))
+    w1 = torch.randn(L, M, M, generator=g, dtype=torch.float64)
+    w2 = torch.randn(L, M, M, generator=g, dtype=torch.float64)
+    Kc = K.clone().requires_grad_(True)
+    Lr = torch.linalg.cholesky(Kc)
+    ((Lr * w1).sum() + (torch.linalg.inv(Lr) * w2.tril()).sum()).backward()
+    Kg = K.to(DEV).requires_grad_(True)
+    Lc, Linv = F.CholeskyInverse.apply(Kg)
+    ((Lc * w1.to(DEV)).sum() + (Linv * w2.tril().to(DEV)).sum()).backward()
+    sym = lambda t: 0.5 * (t + t.transpose(1, 2))
+    assert relerr(sym(Kg.grad), sym(Kc.grad)) < 1e-10
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_kernel_build_vs_oracle(dt):
+    from oracle import gpzoo_oracle as O
+    import gpzoo_b200 as gz
+    z = {k: torch.from_numpy(v) for k, v in np.load(GOLDEN + "/kernels.npz").items()}
+    X, Z, gX, gZ = z["X"], z["Z"], z["gX"], z["gZ"]
+    tol = 1e-12 if dt == torch.float64 else 3e-6
+    k = gz.kernels.RBF(sigma=1.3, lengthscale=0.7).to(DEV)
+    assert relerr(k(X.to(DEV, dt), Z.to(DEV, dt)), z["rbf"]) < max(tol, 1e-7)     # ctor rounds params to fp32
+    nk = gz.kernels.NSF_RBF(sigma=1.1, lengthscale=0.9, L=3).to(DEV).to(dt)
+    with torch.no_grad():
+        nk.lengthscale.copy_(z["nsf_rbf_ls"].to(DEV, dt))
+        nk.sigma.copy_((1.1 * torch.ones(3, 1, 1)).double().to(DEV, dt))
+    assert relerr(nk(X.to(DEV, dt), Z.to(DEV, dt)), z["nsf_rbf"]) < tol
+    assert relerr(nk(X.to(DEV, dt), X.to(DEV, dt), diag=True), O.rbf_diag(X, nk.sigma.detach().cpu().double())) < tol
+    mk = gz.kernels.MGGP_NSF_RBF(sigma=1.2, lengthscale=0.8, group_diff_param=1.3, n_groups=4, L=2).to(DEV).double().to(dt)
+    mk.embedding = torch.nn.Parameter(z["mggp_embedding"].to(DEV, dt), requires_grad=False)
+    out = mk(X.to(DEV, dt), Z.to(DEV, dt), gX.to(DEV), gZ.to(DEV))
+    assert relerr(out, z["mggp_nsf_rbf"]) < max(tol, 1e-7)
+    mr = gz.kernels.MGGP_RBF(sigma=1.2, lengthscale=0.8, group_diff_param=1.7, n_groups=4).to(DEV)
+    mr.embedding = z["mggp_embedding"].to(DEV, dt)
+    assert relerr(mr(X.to(DEV, dt), Z.to(DEV, dt), gX.to(DEV), gZ.to(DEV)), z["mggp_rbf"]) < max(tol, 1e-7)
+    # default embedding (ones - eye): same-group r^2 = 0, cross-group ~1.000002
+    e = gz.kernels.embed_distance_matrix(torch.ones(4, 4) - torch.eye(4))
+    assert relerr(O.squared_dist(e, e), O.squared_dist(z["mggp_default_embedding"].float(), z["mggp_default_embedding"].float())) < 1e-5
+    # return_distance
+    _, d = k(X.to(DEV, dt), Z.to(DEV, dt), return_distance=True)
+    assert relerr(d, torch.cdist(X, Z, compute_mode="donot_use_mm_for_euclid_dist")) < tol
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+@pytest.mark.parametrize("mg", [False, True])
+def test_kernel_build_backward(dt, mg):
+    """Gradients w.r.t. both point sets and all hyper-parameters vs autograd of the oracle (ragged sizes)."""
+    from oracle import gpzoo_oracle as O
+    from gpzoo_b200 import functional as F
+    g = torch.Generator().manual_seed(3)
+    n1, n2, L, ng = 37, 1030, 3, 4
+    x1 = torch.randn(n1, 2, generator=g, dtype=torch.float64)
+    x2 = torch.randn(n2, 2, generator=g, dtype=torch.float64)
+    sg = 1 + 0.1 * torch.rand(L, generator=g, dtype=torch.float64)
+    ls = 0.8 + 0.4 * torch.rand(L, generator=g, dtype=torch.float64)
+    gdp = 0.5 + torch.rand(L, generator=g, dtype=torch.float64)
+    emb = torch.randn(ng, ng, generator=g, dtype=torch.float64)
+    g1 = torch.randint(0, ng, (n1,), generator=g)
+    g2 = torch.randint(0, ng, (n2,), generator=g)
+    Wt = torch.randn(L, n1, n2, generator=g, dtype=torch.float64)
+    leaves = [t.clone().requires_grad_(True) for t in (x1, x2, sg, ls, gdp)]
+    a, b, s, l, gd = leaves
+    if mg:
+        Kref = O.mggp_nsf_rbf(a, b, g1, g2, s.reshape(L, 1, 1), l.reshape(L, 1, 1), gd.reshape(L, 1, 1), emb)
+    else:
+        Kref = O.nsf_rbf(a, b, s.reshape(L, 1, 1), l.reshape(L, 1, 1))
+    (Kref * Wt).sum().backward()
+    dl = [t.detach().to(DEV, dt).requires_grad_(True) for t in (x1, x2, sg, ls, gdp)]
+    a2, b2, s2, l2, gd2 = dl
+    if mg:
+        d = emb[:, None, :] - emb[None, :, :]
+        r2 = (d * d).sum(-1).to(DEV, dt)
+        K = F.KernelBuild.apply(a2, b2, s2, l2, gd2 ** 2, r2, g1.to(DEV), g2.to(DEV), 1.0, 0.0)
+    else:
+        K = F.KernelBuild.apply(a2, b2, s2, l2, None, None, None, None, 1.0, 0.0)
+    tol = 1e-11 if dt == torch.float64 else 2e-5
+    assert relerr(K, Kref) < tol
+    (K * Wt.to(DEV, dt)).sum().backward()
+    for i, (r, c) in enumerate(zip(leaves, dl)):
+        if i == 4 and not mg:
+            continue
+        assert relerr(c.grad, r.grad) < tol, i
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_predict_and_kl_vs_oracle(dt):
+    """Whiten + Predict + MvnKL against the reference formulation (cholesky_solve, W(S-Kzz)W, torch KL)."""
+    from oracle import gpzoo_oracle as O
+    from gpzoo_b200 import functional as F
+    g = torch.Generator().manual_seed(5)
+    L, M, N = 2, 70, 333
+    Z = torch.rand(M, 2, generator=g, dtype=torch.float64) * 4
+    X = torch.rand(N, 2, generator=g, dtype=torch.float64) * 4
+    sg = torch.ones(L, 1, 1, dtype=torch.float64)
+    ls = torch.tensor([0.6, 0.9], dtype=torch.float64).reshape(L, 1, 1)
+    mu = torch.randn(L, M, generator=g, dtype=torch.float64)
+    Lu_raw = 0.1 * torch.randn(L, M, M, generator=g, dtype=torch.float64)
+    leaves = [t.clone().requires_grad_(True) for t in (mu, Lu_raw)]
+    Kzx, Kzz, Kxx = O.nsf_rbf(Z, X, sg, ls), O.nsf_rbf(Z, Z, sg, ls), O.rbf_diag(X, sg)
+    Kzx_r, Kzz_r = Kzx.clone().requires_grad_(True), Kzz.clone().requires_grad_(True)
+    mean, var, Lu, Lc = O.svgp(Kxx, Kzx_r, Kzz_r, leaves[0], leaves[1], 1e-2, -1e30)
+    kl = O.mvn_kl(leaves[0], Lu, Lc)
+    wm = torch.randn(L, N, generator=g, dtype=torch.float64)
+    wv = torch.randn(L, N, generator=g, dtype=torch.float64)
+    ((mean * wm).sum() + (var * wv).sum() - kl.sum()).backward()
+
+    dev = lambda t: t.detach().to(DEV, dt)
+    mu_d, Lur_d = dev(mu).requires_grad_(True), dev(Lu_raw).requires_grad_(True)
+    Kzx_d = dev(Kzx).requires_grad_(True)
+    Kzz_d = dev(Kzz + 1e-2 * torch.eye(M, dtype=torch.float64)).requires_grad_(True)
+    Lc_d, Linv_d = F.CholeskyInverse.apply(Kzz_d)
+    Lu_d = F.LowerCholesky.apply(Lur_d)
+    T_d, q_d = F.Whiten.apply(Linv_d, Lu_d, mu_d)
+    mean_d, var_d = F.Predict.apply(dev(Kxx.contiguous()), Kzx_d, Linv_d, T_d, q_d)
+    kl_d = F.MvnKL.apply(T_d, q_d, Lc_d, Lu_d)
+    tol = 1e-10 if dt == torch.float64 else 1e-4
+    assert relerr(mean_d, mean) < tol and relerr(var_d, var) < tol and relerr(kl_d, kl) < tol
+    ((mean_d * dev(wm)).sum() + (var_d * dev(wv)).sum() - kl_d.sum()).backward()
+    sym = lambda t: 0.5 * (t + t.transpose(1, 2))
+    assert relerr(mu_d.grad, leaves[0].grad) < tol
+    assert relerr(Lur_d.grad, leaves[1].grad) < tol
+    assert relerr(Kzx_d.grad, Kzx_r.grad) < tol
+    assert relerr(sym(Kzz_d.grad), sym(Kzz_r.grad)) < tol
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+@pytest.mark.parametrize("case", ["full", "idx", "hybrid_raw"])
+def test_poisson_fused_vs_oracle(dt, case):
+    from oracle import gpzoo_oracle as O
+    from gpzoo_b200 import functional as F
+    g = torch.Generator().manual_seed(9)
+    G, Fn, Ntot, E = 45, 5, 300, 3
+    nvar = 3
+    y = torch.poisson(torch.rand(G, Ntot, generator=g, dtype=torch.float64) * 2, generator=g)
+    idx = torch.randperm(Ntot, generator=g)[:170] if case != "full" else None
+    B = Ntot if idx is None else len(idx)
+    W = torch.rand(G, Fn, generator=g, dtype=torch.float64)
+    V = 1 + 0.2 * torch.randn(Ntot, generator=g, dtype=torch.float64)
+    mean = 0.3 * torch.randn(Fn, B, generator=g, dtype=torch.float64)
+    spread = 0.05 + 0.3 * torch.rand(Fn, B, generator=g, dtype=torch.float64)
+    spread[0, :7] = 1e-3                                   # exercise the variance clamp (5e-2)
+    eps = torch.randn(E, Fn, B, generator=g, dtype=torch.float64)
+    soft = case != "hybrid_raw"
+    leaves = [t.clone().requires_grad_(True) for t in (W, V, mean, spread)]
+    Wl, Vl, ml, sl = leaves
+    sd = torch.cat((torch.clamp(sl[:nvar], min=5e-2).sqrt(), sl[nvar:]), 0)
+    Fs = ml + eps * sd
+    rate = O.poisson_rate(Wl, Fs, Vl if idx is None else Vl[idx], softplus_W=soft)
+    ll = O.poisson_loglik(y if idx is None else y[:, idx], rate, with_lgamma=True)
+    ll.backward()
+    dl = [t.detach().to(DEV, dt).requires_grad_(True) for t in (W, V, mean, spread)]
+    out = F.PoissonLL.apply(y.to(DEV, dt), None if idx is None else idx.to(DEV), dl[0], dl[1], dl[2], dl[3], eps.to(DEV, dt),
+                            nvar, 5e-2, soft, True)
+    out.backward()
+    tol = 1e-11 if dt == torch.float64 else 3e-5
+    assert relerr(out, ll) < tol
+    for r, c in zip(leaves, dl):
+        assert relerr(c.grad, r.grad) < tol
+    # compatibility path: materialised rate and its backward
+    dl2 = [t.detach().to(DEV, dt).requires_grad_(True) for t in (W, V)]
+    Fd = Fs.detach().to(DEV, dt).requires_grad_(True)
+    r2 = F.poisson_rate(dl2[0], dl2[1], None if idx is None else idx.to(DEV), Fd, soft)
+    assert relerr(r2, rate) < tol
