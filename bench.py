@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py — NSF-SVGP ELBO forward+backward steps/sec on B200 (BASELINE.json metric), 1..8 GPUs.
+
+Workload (BASELINE.json configs[1]): NSF2(SVGP(NSF_RBF)), N=32768 spots, M=1024 inducing points, L=10 factors,
+G=2000 genes, E=1, fp32, synthetic Slide-seq-shaped data (gpzoo_b200.synthetic.nsf_problem).
+One step = ELBO forward + backward producing every parameter gradient (+ all-reduce of the shared-parameter
+gradients when N>1); the optimiser update is excluded.  Multi-GPU: the spots are sharded across
+ranks (strong scaling, fixed global N), shared gradients summed with one NCCL all-reduce.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the reference's CPU PyTorch path (oracle port) instead.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(N=32768, M=1024, L=10, G=2000, E=1, D=2, coord_scale=100.0, lengthscale=1.7, jitter=0.1, seed=1)
+METRIC = "NSF-SVGP ELBO fwd+bwd steps/sec"
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return dict(hbm=p["hbm_gbs"], tensor=p["bf16_tflops"], tensor_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    src="measured")
+    except Exception:
+        return dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    def __init__(self, index):
+        self.index, self.rows, self.stop_flag, self.t = index, [], False, None
+
+    def _run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def start(self):
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.t:
+            self.t.join(timeout=6)
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(self.rows))
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's CPU PyTorch path
+# ------------------------------------------------------------------------------------------------
+def _cpu_step_time(n_sample, steps, warmup):
+    import torch
+    from gpzoo_b200 import synthetic
+    from oracle import gpzoo_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    cfg = CFG
+    prob = synthetic.nsf_problem(N=n_sample, M=cfg["M"], L=cfg["L"], G=cfg["G"], E=cfg["E"], seed=cfg["seed"],
+                                 coord_scale=cfg["coord_scale"], lengthscale=cfg["lengthscale"], jitter=cfg["jitter"],
+                                 dtype=torch.float32)
+    p = O.NSFParams(**{k: prob[k].clone() for k in ("Z", "sigma", "lengthscale", "mu", "Lu_raw", "W", "V")}, jitter=prob["jitter"])
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.value_and_grads(lambda: O.nsf_svgp_terms(p, prob["X"], prob["y"], prob["eps"]), p.leaves())
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return sum(times) / len(times), torch.get_num_threads()
+
+
+def cpu_reference_full_step(steps, warmup, n1=256, n2=1024):
+    """Time the oracle port (the reference's op sequence on CPU torch, fp32, all host threads) on a bounded sample and
+    extrapolate to the full N: the step costs t(N) = a + b N (a: the O(M^3) Cholesky / KL work, b: everything per spot),
+    fitted from `steps` timed steps at N=n1 and one at N=n2."""
+    t1, cores = _cpu_step_time(n1, steps, warmup)
+    t2, _ = _cpu_step_time(n2, 1, 0)
+    b = max(0.0, (t2 - t1) / (n2 - n1))
+    a = max(0.0, t1 - b * n1)
+    full = a + b * CFG["N"]
+    note = (f"oracle port of the reference CPU path (torch {cores} threads, fp32), M/L/G full: {t1:.2f} s/step at N={n1} "
+            f"({steps} timed), {t2:.2f} s at N={n2}; affine fit t = {a:.2f} + {b * 1e3:.3f} ms x N extrapolated to N={CFG['N']}")
+    return full, cores, note
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    full, cores, note = cpu_reference_full_step(args.steps, args.warmup)
+    val = 1.0 / full
+    line = dict(metric=METRIC, value=val, unit="steps/s", impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=full * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload="NSF2(SVGP(NSF_RBF)) N=32768 M=1024 L=10 G=2000 E=1 (BASELINE.json configs[1])", parallelism="cpu"),
+                cpu_baseline=dict(value=val, unit="steps/s", cores=cores, kind="port", sample=note),
+                e2e=dict(value=val, unit="steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def build_model(prob, dt, dev):
+    import torch
+    import gpzoo_b200 as gz
+    P = lambda t: torch.nn.Parameter(t.to(dev, dt))
+    L, M = prob["mu"].shape
+    kern = gz.kernels.NSF_RBF(L=L)
+    kern.sigma, kern.lengthscale = P(prob["sigma"]), P(prob["lengthscale"])
+    gp = gz.gp.SVGP(kern, dim=prob["X"].shape[1], M=M, jitter=prob["jitter"])
+    gp.Z, gp.mu, gp.Lu = P(prob["Z"]), P(prob["mu"]), P(prob["Lu_raw"])
+    model = gz.likelihoods.NSF2(gp, prob["y"][:, :1], L=L)
+    model.W, model.V = P(prob["W"]), P(prob["V"])
+    shared = [gp.Z, kern.sigma, kern.lengthscale, gp.mu, gp.Lu, model.W]
+    return model, shared
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import gpzoo_b200 as gz
+    from gpzoo_b200 import _cabi, functional, synthetic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    functional.set_sync_checks(False)          # Cholesky info is checked once, after the timed region
+    dt = torch.float32
+    c = CFG
+    prob = synthetic.nsf_problem(N=c["N"], M=c["M"], L=c["L"], G=c["G"], E=c["E"], seed=c["seed"], coord_scale=c["coord_scale"],
+                                 lengthscale=c["lengthscale"], jitter=c["jitter"], dtype=dt)
+    n_loc = c["N"] // world
+    sl = slice(rank * n_loc, (rank + 1) * n_loc)
+    # host (pinned) copies of this rank's shard: the e2e leg copies them in every step
+    hX = prob["X"][sl].contiguous().pin_memory()
+    hy = prob["y"][:, sl].contiguous().pin_memory()
+    prob_loc = dict(prob)
+    prob_loc["V"] = prob["V"][sl].contiguous()
+    model, shared = build_model(prob_loc, dt, dev)
+    X, y = hX.to(dev), hy.to(dev)
+    eps = prob["eps"][:, :, sl].contiguous().to(dev)
+    flat = torch.zeros(sum(p.numel() for p in shared) + 1, dtype=dt, device=dev)
+
+    def step(Xd, yd, epsd):
+        for p in model.parameters():
+            p.grad = None
+        elbo = model.elbo(Xd, yd, E=c["E"], eps=epsd, kl_weight=1.0 / world)
+        (-elbo).backward()
+        if world > 1:
+            o = 0
+            for p in shared:
+                flat[o:o + p.numel()].copy_(p.grad.reshape(-1))
+                o += p.numel()
+            flat[o] = elbo.detach()
+            dist.all_reduce(flat)
+            o = 0
+            for p in shared:
+                p.grad.copy_(flat[o:o + p.numel()].view_as(p.grad))
+                o += p.numel()
+            return flat[o]
+        return elbo.detach()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / n
+
+    for _ in range(max(3, args.warmup)):
+        step(X, y, eps)
+    functional.check_cholesky_info()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    k0 = _cabi.kernel_launches()
+    _cabi.profile = {}
+    ms = timed(lambda: step(X, y, eps), args.steps)
+    prof, _cabi.profile = _cabi.profile, None
+    launches = (_cabi.kernel_launches() - k0) // args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    functional.check_cholesky_info()
+
+    # e2e: this rank's inputs start in pinned host memory every step, the loss is read back to the host
+    def e2e_step():
+        Xd = hX.to(dev, non_blocking=True)
+        yd = hy.to(dev, non_blocking=True)
+        return float(step(Xd, yd, None))          # eps drawn on the device, loss D2H
+
+    ms_e2e = None
+    if not args.no_e2e:
+        for _ in range(2):
+            e2e_step()
+        ms_e2e = timed(e2e_step, max(2, args.steps // 2))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    N, M, L, G, E = n_loc, c["M"], c["L"], c["G"], c["E"]
+    algo = {   # per-call algorithmic work on ONE rank: ("hbm", bytes) or ("tensor", flops)
+        "svgp_predict_fwd": ("tensor", 2.0 * L * M * M * N),
+        "svgp_predict_bwd": ("tensor", 4.0 * L * M * M * N),
+        "kernel_build_fwd": ("hbm", 4.0 * L * M * N),
+        "kernel_build_bwd": ("hbm", 4.0 * L * M * N),
+        "poisson_fwdbwd": ("hbm", 4.0 * G * N + 4.0 * (3 * E * L * N + 2 * G * L + 2 * N)),
+    }
+    per_call = {}
+    for name, evs in prof.items():
+        tot = sum(a.elapsed_time(b) for a, b in evs)
+        per_call[name] = dict(ms_per_step=tot / args.steps, calls_per_step=len(evs) / args.steps)
+    kernels = []
+    for name, (bound, work) in algo.items():
+        if name not in per_call:
+            continue
+        evs = prof[name]
+        # kernel_build_fwd is called for Kzx (big) and Kzz (small): take the largest call of each step
+        dur = sorted((a.elapsed_time(b) for a, b in evs), reverse=True)[:args.steps]
+        avg = sum(dur) / len(dur)
+        if bound == "hbm":
+            ach, peak, unit = work / avg / 1e6, pk["hbm"], "GB/s"
+        else:
+            ach, peak, unit = work / avg / 1e9, pk["tensor_sustained"], "TFLOP/s"
+        kernels.append(dict(kernel=name, bound=bound, ms=avg, achieved=ach, peak=peak, unit=unit, frac=ach / peak))
+    dom = max(kernels, key=lambda k: k["ms"]) if kernels else None
+    roofline = None
+    if dom:
+        roofline = dict(kernel=dom["kernel"], bound=dom["bound"], achieved=dom["achieved"], peak=dom["peak"], unit=dom["unit"],
+                        frac=dom["frac"], traffic=None, peak_source=pk["src"] + (" (bf16 dense, sustained)" if dom["bound"] == "tensor" else ""))
+    h2d = hX.numel() * 4 + hy.numel() * 4
+    line = dict(metric=METRIC, value=1e3 / ms, unit="steps/s", n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
+                ms_per_step=ms, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload="NSF2(SVGP(NSF_RBF)) N=32768 M=1024 L=10 G=2000 E=1 (BASELINE.json configs[1])",
+                            spots_per_gpu=n_loc, parallelism=f"dp{world} over spots", l2="inputs larger than L2 (y 262 MB, Kzx 1.3 GB)",
+                            inducing="jittered 32x32 grid"),
+                clocks=clocks, gpu_launches=int(launches),
+                e2e=(dict(value=1e3 / ms_e2e, unit="steps/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4) if ms_e2e else None),
+                roofline=roofline, kernels=kernels, per_call_ms=per_call)
+    if world == 1 and not args.no_cpu_baseline:
+        full, cores, note = cpu_reference_full_step(1, 1)
+        line["cpu_baseline"] = dict(value=1.0 / full, unit="steps/s", cores=cores, kind="port", sample=note)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
+    ap.add_argument("--N", type=int, default=None, help="override the number of spots (debugging only)")
+    args = ap.parse_args()
+    if args.N:
+        CFG["N"] = args.N
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

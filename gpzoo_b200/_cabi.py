@@ -37,6 +37,7 @@ def lib():
                 l.gpz_error_string.restype = ctypes.c_char_p
                 l.gpz_error_string.argtypes = [c_i]
                 l.gpz_abi_version.restype = c_i
+                l.gpz_launch_count.restype = ctypes.c_longlong
                 for suf in ("f32", "f64"):
                     getattr(l, f"gpz_poisson_workspace_bytes_{suf}").restype = c_i64
                 _lib = l
@@ -66,12 +67,27 @@ def stream():
     return c_p(torch.cuda.current_stream().cuda_stream)
 
 
+profile = None             # set to {} to record CUDA events around every C-ABI call (bench.py roofline numbers)
+
+
+def kernel_launches():
+    """Number of CUDA kernels the library has launched so far in this process."""
+    return int(lib().gpz_launch_count())
+
+
 def call(name, dtype, *args):
     """Invoke gpz_<name>_<f32|f64>(*args, stream) and raise on a non-zero return code."""
     global launch_count
     suf, _ = _suffix(dtype)
     fn = getattr(lib(), f"gpz_{name}_{suf}")
-    rc = fn(*args, stream())
+    if profile is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        rc = fn(*args, stream())
+        ev1.record()
+        profile.setdefault(name, []).append((ev0, ev1))
+    else:
+        rc = fn(*args, stream())
     launch_count += 1
     if rc != 0:
         raise GpzError(f"gpz_{name}_{suf} failed: {lib().gpz_error_string(rc).decode()} (rc={rc})")

@@ -11,3 +11,9 @@ extern "C" const char* gpz_error_string(int rc) {
   if (rc < 0 && rc > -1000) return cudaGetErrorString((cudaError_t)(-rc));
   return "gpzoo_b200: unknown error";
 }
+
+#include <atomic>
+static std::atomic<long long> g_launches{0};
+extern "C" void gpz_count_launch_(void) { g_launches.fetch_add(1, std::memory_order_relaxed); }
+// number of CUDA kernels this library has launched in this process (bench.py "gpu_launches")
+extern "C" long long gpz_launch_count(void) { return g_launches.load(); }

@@ -7,8 +7,11 @@
 #define GPZ_ERR_BADARG (-1000)
 #define GPZ_ERR_UNSUPPORTED (-1001)
 
+// after every kernel launch: count it (gpz_launch_count) and surface launch errors
+extern "C" void gpz_count_launch_(void);
 #define GPZ_CHECK_LAUNCH()                                  \
   do {                                                      \
+    gpz_count_launch_();                                    \
     cudaError_t e__ = cudaGetLastError();                   \
     if (e__ != cudaSuccess) return -(int)e__;               \
   } while (0)

@@ -115,12 +115,12 @@ __global__ void __launch_bounds__(KB_THREADS) kbuild_fwd_kernel(const KBArgs<T> 
 // One CTA covers KB_ROWS rows x (KB_THREADS*4) columns; the L accumulators live in registers.
 template <typename T, bool MG, bool ALIGNED>
 __global__ void __launch_bounds__(KB_THREADS) kbuild_bwd_kernel(const KBArgs<T> a, const T* __restrict__ G, int l0, int Lc,
-                                                                 T* __restrict__ g_x1, T* __restrict__ g_x2,
-                                                                 T* __restrict__ g_sigma, T* __restrict__ g_ls,
-                                                                 T* __restrict__ g_a) {
+                                                                 double* __restrict__ g_x1, T* __restrict__ g_x2,
+                                                                 double* __restrict__ g_sigma, double* __restrict__ g_ls,
+                                                                 double* __restrict__ g_a) {
   __shared__ T s_c[KB_LMAX], s_s2[KB_LMAX], s_a[KB_LMAX];
   __shared__ T s_r2[MG ? KB_GMAX * KB_GMAX : 1];
-  __shared__ T s_red[32];
+  __shared__ double s_red[32];
   __shared__ T s_row[KB_ROWS][KB_DMAX][KB_THREADS / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int l = tid; l < Lc; l += KB_THREADS) {
@@ -225,9 +225,9 @@ __global__ void __launch_bounds__(KB_THREADS) kbuild_bwd_kernel(const KBArgs<T> 
   if (g_x1 != nullptr) {
     for (int e = tid; e < (i1 - i0) * a.D; e += KB_THREADS) {
       const int ii = e / a.D, d = e % a.D;
-      T r = T(0);
+      double r = 0.0;
 #pragma unroll
-      for (int wv = 0; wv < KB_THREADS / 32; ++wv) r += s_row[ii][d][wv];
+      for (int wv = 0; wv < KB_THREADS / 32; ++wv) r += (double)s_row[ii][d][wv];
       atomicAdd(g_x1 + (int64_t)(i0 + ii) * a.D + d, -r);
     }
   }
@@ -240,16 +240,30 @@ __global__ void __launch_bounds__(KB_THREADS) kbuild_bwd_kernel(const KBArgs<T> 
 #pragma unroll
   for (int l = 0; l < KB_LMAX; ++l) {
     if (l < Lc) {                                   // uniform across the block
-      T v = block_sum<T>(acc_s[l], s_red);
-      if (tid == 0) atomicAdd(g_sigma + l0 + l, v * T(2) / a.sigma[l0 + l]);
-      v = block_sum<T>(acc_l[l], s_red);
-      if (tid == 0) atomicAdd(g_ls + l0 + l, v / a.ls[l0 + l]);
+      double v = block_sum<double>((double)acc_s[l], s_red);
+      if (tid == 0) atomicAdd(g_sigma + l0 + l, v);
+      v = block_sum<double>((double)acc_l[l], s_red);
+      if (tid == 0) atomicAdd(g_ls + l0 + l, v);
       if (MG) {
-        v = block_sum<T>(acc_a[l], s_red);
-        if (tid == 0 && g_a != nullptr) atomicAdd(g_a + l0 + l, v);
+        v = block_sum<double>((double)acc_a[l], s_red);
+        if (tid == 0) atomicAdd(g_a + l0 + l, v);
       }
     }
   }
+}
+
+// double accumulators -> outputs:  g_sigma = 2 S/sigma, g_ls = Sl/ls, g_a = Sa, g_x1 = ws_x1
+template <typename T>
+__global__ void kbuild_bwd_finalize_kernel(const double* __restrict__ ws, const T* __restrict__ sigma, const T* __restrict__ ls, int L,
+                                           int n1D, T* __restrict__ g_sigma, T* __restrict__ g_ls, T* __restrict__ g_a,
+                                           T* __restrict__ g_x1) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < L) {
+    g_sigma[e] = (T)(2.0 * ws[e] / (double)sigma[e]);
+    g_ls[e] = (T)(ws[L + e] / (double)ls[e]);
+    if (g_a != nullptr) g_a[e] = (T)ws[2 * L + e];
+  }
+  if (g_x1 != nullptr && e < n1D) g_x1[e] = (T)ws[3 * L + e];
 }
 
 // plain Euclidean distance matrix (n1 x n2) by direct differences: kernel(X, Z, return_distance=True)
@@ -284,30 +298,33 @@ int kbuild_fwd(const KBArgs<T>& a, T* out, cudaStream_t st) {
 }
 
 template <typename T>
-int kbuild_bwd(const KBArgs<T>& a, const T* G, T* g_x1, T* g_x2, T* g_sigma, T* g_ls, T* g_a, cudaStream_t st) {
+int kbuild_bwd(const KBArgs<T>& a, const T* G, T* g_x1, T* g_x2, T* g_sigma, T* g_ls, T* g_a, double* ws, cudaStream_t st) {
   if (a.D < 1 || a.D > KB_DMAX || a.L < 1) return GPZ_ERR_UNSUPPORTED;
   const bool mg = a.g1 != nullptr;
   if (mg && (a.ng < 1 || a.ng > KB_GMAX)) return GPZ_ERR_UNSUPPORTED;
-  if (g_x1) GPZ_CUDA(cudaMemsetAsync(g_x1, 0, sizeof(T) * a.n1 * a.D, st));
+  const int n1D = a.n1 * a.D;
+  GPZ_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * (3 * (size_t)a.L + n1D), st));
   if (g_x2) GPZ_CUDA(cudaMemsetAsync(g_x2, 0, sizeof(T) * a.n2 * a.D, st));
-  GPZ_CUDA(cudaMemsetAsync(g_sigma, 0, sizeof(T) * a.L, st));
-  GPZ_CUDA(cudaMemsetAsync(g_ls, 0, sizeof(T) * a.L, st));
-  if (g_a) GPZ_CUDA(cudaMemsetAsync(g_a, 0, sizeof(T) * a.L, st));
-  if (a.n1 == 0 || a.n2 == 0) return GPZ_OK;
-  const bool al = (a.n2 % KB_VEC == 0) && ((reinterpret_cast<uintptr_t>(G) & 31) == 0);
-  dim3 grid((unsigned)cdiv(a.n2, (int64_t)KB_THREADS * KB_VEC), (unsigned)cdiv(a.n1, KB_ROWS));
-  for (int l0 = 0; l0 < a.L; l0 += KB_LMAX) {
-    const int Lc = min(KB_LMAX, a.L - l0);
-    // g_x1/g_x2 accumulate over all l-chunks (atomics), so every chunk launch adds its share
-    if (mg) {
-      if (al) kbuild_bwd_kernel<T, true, true><<<grid, KB_THREADS, 0, st>>>(a, G, l0, Lc, g_x1, g_x2, g_sigma, g_ls, g_a);
-      else kbuild_bwd_kernel<T, true, false><<<grid, KB_THREADS, 0, st>>>(a, G, l0, Lc, g_x1, g_x2, g_sigma, g_ls, g_a);
-    } else {
-      if (al) kbuild_bwd_kernel<T, false, true><<<grid, KB_THREADS, 0, st>>>(a, G, l0, Lc, g_x1, g_x2, g_sigma, g_ls, g_a);
-      else kbuild_bwd_kernel<T, false, false><<<grid, KB_THREADS, 0, st>>>(a, G, l0, Lc, g_x1, g_x2, g_sigma, g_ls, g_a);
+  double* w_sigma = ws; double* w_ls = ws + a.L; double* w_a = ws + 2 * a.L; double* w_x1 = ws + 3 * a.L;
+  if (a.n1 > 0 && a.n2 > 0) {
+    const bool al = (a.n2 % KB_VEC == 0) && ((reinterpret_cast<uintptr_t>(G) & 31) == 0);
+    dim3 grid((unsigned)cdiv(a.n2, (int64_t)KB_THREADS * KB_VEC), (unsigned)cdiv(a.n1, KB_ROWS));
+    for (int l0 = 0; l0 < a.L; l0 += KB_LMAX) {
+      const int Lc = min(KB_LMAX, a.L - l0);
+      // g_x1/g_x2 accumulate over all l-chunks (atomics), so every chunk launch adds its share
+      if (mg) {
+        if (al) kbuild_bwd_kernel<T, true, true><<<grid, KB_THREADS, 0, st>>>(a, G, l0, Lc, w_x1, g_x2, w_sigma, w_ls, w_a);
+        else kbuild_bwd_kernel<T, true, false><<<grid, KB_THREADS, 0, st>>>(a, G, l0, Lc, w_x1, g_x2, w_sigma, w_ls, w_a);
+      } else {
+        if (al) kbuild_bwd_kernel<T, false, true><<<grid, KB_THREADS, 0, st>>>(a, G, l0, Lc, w_x1, g_x2, w_sigma, w_ls, w_a);
+        else kbuild_bwd_kernel<T, false, false><<<grid, KB_THREADS, 0, st>>>(a, G, l0, Lc, w_x1, g_x2, w_sigma, w_ls, w_a);
+      }
+      GPZ_CHECK_LAUNCH();
     }
-    GPZ_CHECK_LAUNCH();
   }
+  const int tot = max(a.L, n1D);
+  kbuild_bwd_finalize_kernel<T><<<(unsigned)cdiv(tot, 256), 256, 0, st>>>(ws, a.sigma, a.ls, a.L, n1D, g_sigma, g_ls, g_a, g_x1);
+  GPZ_CHECK_LAUNCH();
   return GPZ_OK;
 }
 
@@ -325,9 +342,9 @@ using namespace gpz;
   extern "C" int gpz_kernel_build_bwd_##SUF(const T* x1, const T* x2, const T* sigma, const T* ls, const T* a,     \
                                             const T* r2, const int64_t* g1, const int64_t* g2, int n1, int n2,     \
                                             int D, int L, int ng, T p_half, const T* G, T* g_x1, T* g_x2,          \
-                                            T* g_sigma, T* g_ls, T* g_a, void* stream) {                           \
+                                            T* g_sigma, T* g_ls, T* g_a, double* ws, void* stream) {               \
     KBArgs<T> k{x1, x2, sigma, ls, a, r2, g1, g2, n1, n2, D, L, ng, p_half, T(0)};                                 \
-    return kbuild_bwd<T>(k, G, g_x1, g_x2, g_sigma, g_ls, g_a, (cudaStream_t)stream);                              \
+    return kbuild_bwd<T>(k, G, g_x1, g_x2, g_sigma, g_ls, g_a, ws, (cudaStream_t)stream);                          \
   }                                                                                                                \
   extern "C" int gpz_cdist_##SUF(const T* x1, const T* x2, T* out, int n1, int n2, int D, void* stream) {          \
     const int64_t total = (int64_t)n1 * n2;                                                                        \

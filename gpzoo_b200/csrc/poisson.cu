@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(PZ_SPOTS) poisson_kernel(const PoissonArgs<T> 
         }
         tS[gi][tid] = t;
       }
-      ll += (double)llc;
+      ll += (double)(llc * invE);
 #pragma unroll
       for (int f = 0; f < FMAX; ++f) {
         if (f < a.F && active) {

@@ -110,9 +110,10 @@ class KernelBuild(Function):
         g_sigma = torch.empty_like(sigma)
         g_ls = torch.empty_like(ls)
         g_a = torch.empty_like(a) if mg else None
+        ws = torch.empty(3 * L + n1 * D, dtype=torch.float64, device=x1.device)
         call("kernel_build_bwd", dt, ptr(x1), ptr(x2), ptr(sigma), ptr(ls), ptr(a), ptr(r2), ptr(g1), ptr(g2),
              c_i(n1), c_i(n2), c_i(D), c_i(L), c_i(r2.shape[0] if mg else 0), scalar(dt, ctx.p_half), ptr(G),
-             ptr(g_x1), ptr(g_x2), ptr(g_sigma), ptr(g_ls), ptr(g_a))
+             ptr(g_x1), ptr(g_x2), ptr(g_sigma), ptr(g_ls), ptr(g_a), ptr(ws))
         return g_x1, g_x2, g_sigma, g_ls, g_a, None, None, None, None, None
 
 

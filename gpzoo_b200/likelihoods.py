@@ -100,11 +100,12 @@ class _FusedPoissonMixin:
     def _gp(self):
         return self.prior if hasattr(self, "prior") else self.gp
 
-    def elbo(self, X, y, idx=None, E=1, eps=None, with_lgamma=True, return_parts=False, **kwargs):
+    def elbo(self, X, y, idx=None, E=1, eps=None, with_lgamma=True, return_parts=False, kl_weight=1.0, **kwargs):
         """ELBO = mean_E sum log p(y | F) - sum_l KL(qU_l || pU_l)   (utilities.py:479-481, 611-616).
 
         X: N x D (all spots); idx: optional minibatch indices (as forward_batched); y: G x N;
-        eps: optional E x L x B standard-normal draw (else drawn from the global RNG on the device)."""
+        eps: optional E x L x B standard-normal draw (else drawn from the global RNG on the device);
+        kl_weight: data-parallel ranks pass 1/world_size so that the all-reduced sum counts the KL once."""
         gp = self._gp()
         Xb = X if idx is None else X[idx]
         gX = kwargs.get("groupsX")
@@ -116,7 +117,7 @@ class _FusedPoissonMixin:
         ll = F.PoissonLL.apply(y, idx, W, self.V.to(mean.dtype), mean, var, eps, mean.shape[0], gp.clamp_min,
                                self._w_softplus, with_lgamma)
         kl = F.MvnKL.apply(m["T"], m["q"], m["Lc"], m["Lu"])
-        out = ll - kl.sum()
+        out = ll - kl_weight * kl.sum()
         if return_parts:
             return out, dict(ll=ll, kl=kl, mean=mean, var=var)
         return out

@@ -26,6 +26,8 @@ extern "C" {
 int gpz_abi_version(void);
 /* cudaGetErrorString for -rc, or a library message for rc <= -1000 */
 const char* gpz_error_string(int rc);
+/* number of CUDA kernels launched by this library in this process (bench.py reports it as gpu_launches) */
+long long gpz_launch_count(void);
 
 /* ---- K1 kernel-matrix build: kernels.py:114-130 (RBF), 141-155 (NSF_RBF), 172-191 (MGGP_RBF),
  *      204-228 (MGGP_NSF_RBF); jitter = utilities.py:407-418 (add_jitter) fused on the diagonal.
@@ -37,15 +39,16 @@ int gpz_kernel_build_fwd_f32(const float* x1, const float* x2, const float* sigm
 int gpz_kernel_build_fwd_f64(const double* x1, const double* x2, const double* sigma, const double* ls, const double* a,
                              const double* r2, const int64_t* g1, const int64_t* g2, int n1, int n2, int D, int L, int ng,
                              double p_half, double jitter, double* out, void* stream);
-/* backward of the above (autograd of kernels.py forward): G = dLoss/dout; g_x1/g_x2/g_a may be NULL */
+/* backward of the above (autograd of kernels.py forward): G = dLoss/dout; g_x1/g_x2/g_a may be NULL.
+ * ws: 3*L + n1*D doubles of scratch (parameter and x1 gradients are accumulated in fp64). */
 int gpz_kernel_build_bwd_f32(const float* x1, const float* x2, const float* sigma, const float* ls, const float* a,
                              const float* r2, const int64_t* g1, const int64_t* g2, int n1, int n2, int D, int L, int ng,
                              float p_half, const float* G, float* g_x1, float* g_x2, float* g_sigma, float* g_ls, float* g_a,
-                             void* stream);
+                             double* ws, void* stream);
 int gpz_kernel_build_bwd_f64(const double* x1, const double* x2, const double* sigma, const double* ls, const double* a,
                              const double* r2, const int64_t* g1, const int64_t* g2, int n1, int n2, int D, int L, int ng,
                              double p_half, const double* G, double* g_x1, double* g_x2, double* g_sigma, double* g_ls,
-                             double* g_a, void* stream);
+                             double* g_a, double* ws, void* stream);
 /* kernels.py:118,123-124 (return_distance=True): Euclidean distances n1 x n2 */
 int gpz_cdist_f32(const float* x1, const float* x2, float* out, int n1, int n2, int D, void* stream);
 int gpz_cdist_f64(const double* x1, const double* x2, double* out, int n1, int n2, int D, void* stream);

@@ -73,7 +73,7 @@ def main():
     out, grads = ref_runner.run_vnngp(prob, K=4)
     save("nsf_vnngp", prob, out, grads, K=4)
 
-    prob = synthetic.nsf_problem(N=64, M=16, L=2, G=8, E=2, seed=41, coord_scale=2.0, jitter=1e-2)
+    prob = synthetic.nsf_problem(N=64, M=16, L=2, G=8, E=2, seed=41, coord_scale=2.0, jitter=1e-2, lengthscale=0.8)
     g = torch.Generator().manual_seed(42)
     extra = dict(Wcf=torch.rand(8, 3, generator=g, dtype=torch.float64),
                  cf_mean=0.3 * torch.randn(3, 64, generator=g, dtype=torch.float64),
