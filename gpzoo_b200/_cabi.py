@@ -80,6 +80,8 @@ def call(name, dtype, *args):
     global launch_count
     suf, _ = _suffix(dtype)
     fn = getattr(lib(), f"gpz_{name}_{suf}")
+    if fn.restype is not c_i:
+        fn.restype = c_i
     if profile is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()

@@ -34,7 +34,7 @@ template <typename T> struct KBArgs {
 template <typename T> struct Vec4 { T v[4]; };
 
 template <typename T, bool MG, bool ALIGNED>
-__global__ void __launch_bounds__(KB_THREADS) kbuild_fwd_kernel(const KBArgs<T> a, T* __restrict__ out) {
+__global__ void __launch_bounds__(KB_THREADS) kbuild_fwd_kernel(const KBArgs<T> a, T* __restrict__ out, T* __restrict__ out_lo) {
   __shared__ T s_c[KB_LMAX * 8], s_s2[KB_LMAX * 8], s_a[KB_LMAX * 8];
   __shared__ T s_r2[MG ? KB_GMAX * KB_GMAX : 1];
   const int tid = threadIdx.x;
@@ -102,6 +102,17 @@ __global__ void __launch_bounds__(KB_THREADS) kbuild_fwd_kernel(const KBArgs<T> 
         }
       } else {
         for (int v = 0; v < nv; ++v) o[v] = k.v[v];
+      }
+      if (sizeof(T) == 4 && out_lo != nullptr) {          // lo = x - tf32_trunc(x): second operand of the split-TF32 GEMMs
+        float lo[KB_VEC];
+#pragma unroll
+        for (int v = 0; v < KB_VEC; ++v) {
+          const float x = (float)k.v[v];
+          lo[v] = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+        }
+        float* ol = reinterpret_cast<float*>(out_lo) + ((int64_t)l * a.n1 + i) * a.n2 + j0;
+        if (ALIGNED && nv == KB_VEC) __stcs(reinterpret_cast<float4*>(ol), make_float4(lo[0], lo[1], lo[2], lo[3]));
+        else for (int v = 0; v < nv; ++v) ol[v] = lo[v];
       }
     }
   }
@@ -279,19 +290,20 @@ __global__ void cdist_kernel(const T* __restrict__ x1, const T* __restrict__ x2,
 }
 
 template <typename T>
-int kbuild_fwd(const KBArgs<T>& a, T* out, cudaStream_t st) {
+int kbuild_fwd(const KBArgs<T>& a, T* out, T* out_lo, cudaStream_t st) {
   if (a.D < 1 || a.D > KB_DMAX || a.L < 1 || a.L > KB_LMAX * 8) return GPZ_ERR_UNSUPPORTED;
   const bool mg = a.g1 != nullptr;
   if (mg && (a.ng < 1 || a.ng > KB_GMAX)) return GPZ_ERR_UNSUPPORTED;
   if (a.n1 == 0 || a.n2 == 0) return GPZ_OK;
-  const bool al = (a.n2 % KB_VEC == 0) && ((reinterpret_cast<uintptr_t>(out) & 31) == 0);
+  const bool al = (a.n2 % KB_VEC == 0) && ((reinterpret_cast<uintptr_t>(out) & 31) == 0) &&
+                  ((reinterpret_cast<uintptr_t>(out_lo) & 15) == 0);
   dim3 grid((unsigned)cdiv(a.n2, (int64_t)KB_THREADS * KB_VEC), (unsigned)cdiv(a.n1, KB_ROWS));
   if (mg) {
-    if (al) kbuild_fwd_kernel<T, true, true><<<grid, KB_THREADS, 0, st>>>(a, out);
-    else kbuild_fwd_kernel<T, true, false><<<grid, KB_THREADS, 0, st>>>(a, out);
+    if (al) kbuild_fwd_kernel<T, true, true><<<grid, KB_THREADS, 0, st>>>(a, out, out_lo);
+    else kbuild_fwd_kernel<T, true, false><<<grid, KB_THREADS, 0, st>>>(a, out, out_lo);
   } else {
-    if (al) kbuild_fwd_kernel<T, false, true><<<grid, KB_THREADS, 0, st>>>(a, out);
-    else kbuild_fwd_kernel<T, false, false><<<grid, KB_THREADS, 0, st>>>(a, out);
+    if (al) kbuild_fwd_kernel<T, false, true><<<grid, KB_THREADS, 0, st>>>(a, out, out_lo);
+    else kbuild_fwd_kernel<T, false, false><<<grid, KB_THREADS, 0, st>>>(a, out, out_lo);
   }
   GPZ_CHECK_LAUNCH();
   return GPZ_OK;
@@ -335,9 +347,10 @@ using namespace gpz;
 #define GPZ_KB_IMPL(SUF, T)                                                                                        \
   extern "C" int gpz_kernel_build_fwd_##SUF(const T* x1, const T* x2, const T* sigma, const T* ls, const T* a,     \
                                             const T* r2, const int64_t* g1, const int64_t* g2, int n1, int n2,     \
-                                            int D, int L, int ng, T p_half, T jitter, T* out, void* stream) {      \
+                                            int D, int L, int ng, T p_half, T jitter, T* out, T* out_lo,           \
+                                            void* stream) {                                                        \
     KBArgs<T> k{x1, x2, sigma, ls, a, r2, g1, g2, n1, n2, D, L, ng, p_half, jitter};                               \
-    return kbuild_fwd<T>(k, out, (cudaStream_t)stream);                                                            \
+    return kbuild_fwd<T>(k, out, out_lo, (cudaStream_t)stream);                                                    \
   }                                                                                                                \
   extern "C" int gpz_kernel_build_bwd_##SUF(const T* x1, const T* x2, const T* sigma, const T* ls, const T* a,     \
                                             const T* r2, const int64_t* g1, const int64_t* g2, int n1, int n2,     \

@@ -48,7 +48,8 @@ __global__ void __launch_bounds__(256) predict_reduce_kernel(const T* __restrict
 template <typename T>
 __global__ void __launch_bounds__(256) predict_bwd_prep_kernel(const T* __restrict__ A, T* __restrict__ C, const T* __restrict__ q,
                                                                 const T* __restrict__ gm, const T* __restrict__ gv,
-                                                                T* __restrict__ gA, int M, int N, int rows_per_cta) {
+                                                                T* __restrict__ gA, T* __restrict__ Clo, int M, int N,
+                                                                int rows_per_cta) {
   const int l = blockIdx.z;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
@@ -57,7 +58,12 @@ __global__ void __launch_bounds__(256) predict_bwd_prep_kernel(const T* __restri
   for (int m = m0; m < m1; ++m) {
     const int64_t e = ((int64_t)l * M + m) * N + n;
     const T av = A[e], cv = C[e];
-    C[e] = T(2) * cv * gvn;
+    const T gc = T(2) * cv * gvn;
+    C[e] = gc;
+    if (sizeof(T) == 4 && Clo != nullptr) {
+      const float x = (float)gc;
+      reinterpret_cast<float*>(Clo)[e] = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    }
     gA[e] = fma(q[(int64_t)l * M + m], gmn, T(-2) * av * gvn);
   }
 }
@@ -94,7 +100,7 @@ int predict_bwd(const T* Kzx, const T* Linv, const T* Tm, const T* q, const T* A
                 T* gA, T* gKzx, T* gLinv, T* gT, T* gq, int M, int N, int L, cudaStream_t st) {
   const int64_t sMM = (int64_t)M * M, sMN = (int64_t)M * N;
   const int rows = 64;
-  predict_bwd_prep_kernel<T><<<dim3((unsigned)cdiv(N, 256), (unsigned)cdiv(M, rows), L), 256, 0, st>>>(A, C, q, gm, gv, gA, M, N, rows);
+  predict_bwd_prep_kernel<T><<<dim3((unsigned)cdiv(N, 256), (unsigned)cdiv(M, rows), L), 256, 0, st>>>(A, C, q, gm, gv, gA, (T*)nullptr, M, N, rows);
   GPZ_CHECK_LAUNCH();
   rowdot_kernel<T><<<dim3(M, L), 256, 0, st>>>(A, gm, gq, M, N);
   GPZ_CHECK_LAUNCH();
@@ -118,9 +124,88 @@ int predict_bwd(const T* Kzx, const T* Linv, const T* Tm, const T* q, const T* A
   return rc;
 }
 
+// ---- tensor-core (tcgen05, split-TF32) variant of the same two entry points, fp32 only ----------------------------
+// ws layout (floats): [Linv_lo | TT | TT_lo | T_lo | LinvT | LinvT_lo], each L*M*M.
+static int tc_gemm(cudaStream_t st, int bk, int m, int n, int k, const float* A, const float* Alo, int64_t lda, int64_t sA,
+                   const float* B, const float* Blo, int64_t ldb, int64_t sB, const float* Cin, float* D, float* Dlo, int64_t ldd,
+                   int64_t sD, int batch, int a_tri, int d_tri, int splitk) {
+  return gpz_umma_gemm_f32(bk, m, n, k, 1.0f, A, Alo, lda, sA, B, Blo, ldb, sB, Cin, D, Dlo, ldd, sD, batch, a_tri, 0, d_tri, splitk,
+                           3, (void*)st);
+}
+
+static int predict_fwd_tc(const float* Kzx, const float* Kzx_lo, const float* Linv, const float* Tm, const float* q, const float* kxx,
+                          float* A, float* A_lo, float* C, float* mean, float* var, float* ws, int M, int N, int L, cudaStream_t st) {
+  const int64_t sMM = (int64_t)M * M, sMN = (int64_t)M * N, W = sMM * L;
+  float* Linv_lo = ws; float* TT = ws + W; float* TT_lo = ws + 2 * W;
+  int rc = gpz_tf32_lo_f32(Linv, Linv_lo, W, (void*)st);
+  if (rc) return rc;
+  rc = gpz_transpose_lo_f32(Tm, TT, TT_lo, M, L, (void*)st);
+  if (rc) return rc;
+  // A = Linv Kzx  (lower-triangular product == TRSM Lc A = Kzx)
+  rc = tc_gemm(st, 0, M, N, M, Linv, Linv_lo, M, sMM, Kzx, Kzx_lo, N, sMN, nullptr, A, A_lo, N, sMN, L, 1, 0, 1);
+  if (rc) return rc;
+  // C = T^T A     (upper-triangular product)
+  rc = tc_gemm(st, 0, M, N, M, TT, TT_lo, M, sMM, A, A_lo, N, sMN, nullptr, C, nullptr, N, sMN, L, 2, 0, 1);
+  if (rc) return rc;
+  predict_reduce_kernel<float><<<dim3((unsigned)cdiv(N, 256), L), 256, sizeof(float) * M, st>>>(A, C, q, kxx, mean, var, M, N);
+  GPZ_CHECK_LAUNCH();
+  return GPZ_OK;
+}
+
+static int predict_bwd_tc(const float* Kzx, const float* Kzx_lo, const float* Linv, const float* Tm, const float* q, const float* A,
+                          const float* A_lo, float* C, float* C_lo, const float* gm, const float* gv, float* gA, float* gA_lo,
+                          float* gKzx, float* gLinv, float* gT, float* gq, float* ws, int M, int N, int L, cudaStream_t st) {
+  const int64_t sMM = (int64_t)M * M, sMN = (int64_t)M * N, W = sMM * L;
+  float* T_lo = ws + 3 * W; float* LinvT = ws + 4 * W; float* LinvT_lo = ws + 5 * W;
+  int rc = gpz_tf32_lo_f32(Tm, T_lo, W, (void*)st);
+  if (rc) return rc;
+  rc = gpz_transpose_lo_f32(Linv, LinvT, LinvT_lo, M, L, (void*)st);
+  if (rc) return rc;
+  const int rows = 64;
+  // C <- gC = 2 C gv (+ lo part);  gA <- -2 A gv + q gm^T
+  predict_bwd_prep_kernel<float><<<dim3((unsigned)cdiv(N, 256), (unsigned)cdiv(M, rows), L), 256, 0, st>>>(A, C, q, gm, gv, gA, C_lo,
+                                                                                                        M, N, rows);
+  GPZ_CHECK_LAUNCH();
+  rowdot_kernel<float><<<dim3(M, L), 256, 0, st>>>(A, gm, gq, M, N);
+  GPZ_CHECK_LAUNCH();
+  int splitk = 1;
+  {
+    const int64_t tiles = cdiv(M, 128) * cdiv(M, 256) * L / 2 + 1;
+    while (splitk < 32 && tiles * splitk < 148 * 2 && N / (splitk * 2) >= 1024) splitk *= 2;
+  }
+  // gT = tril(A gC^T)   (reduction over the N spots, both operands K-major)
+  rc = tc_gemm(st, 1, M, M, N, A, A_lo, N, sMN, C, C_lo, N, sMN, nullptr, gT, nullptr, M, sMM, L, 0, 1, splitk);
+  if (rc) return rc;
+  // gA = T gC + gA
+  rc = tc_gemm(st, 0, M, N, M, Tm, T_lo, M, sMM, C, C_lo, N, sMN, gA, gA, gA_lo, N, sMN, L, 1, 0, 1);
+  if (rc) return rc;
+  // gKzx = Linv^T gA
+  rc = tc_gemm(st, 0, M, N, M, LinvT, LinvT_lo, M, sMM, gA, gA_lo, N, sMN, nullptr, gKzx, nullptr, N, sMN, L, 2, 0, 1);
+  if (rc) return rc;
+  // gLinv = tril(gA Kzx^T)
+  return tc_gemm(st, 1, M, M, N, gA, gA_lo, N, sMN, Kzx, Kzx_lo, N, sMN, nullptr, gLinv, nullptr, M, sMM, L, 0, 1, splitk);
+}
+
 }  // namespace gpz
 
 using namespace gpz;
+
+extern "C" int gpz_svgp_predict_tc_supported(int M, int N) { return (M % 4 == 0 && N % 4 == 0 && M >= 64 && N >= 256) ? 1 : 0; }
+
+extern "C" int gpz_svgp_predict_fwd_tc_f32(const float* Kzx, const float* Kzx_lo, const float* Linv, const float* T, const float* q,
+                                           const float* kxx, float* A, float* A_lo, float* C, float* mean, float* var, float* ws,
+                                           int M, int N, int L, void* stream) {
+  if (!gpz_svgp_predict_tc_supported(M, N) || L <= 0) return GPZ_ERR_UNSUPPORTED;
+  return predict_fwd_tc(Kzx, Kzx_lo, Linv, T, q, kxx, A, A_lo, C, mean, var, ws, M, N, L, (cudaStream_t)stream);
+}
+extern "C" int gpz_svgp_predict_bwd_tc_f32(const float* Kzx, const float* Kzx_lo, const float* Linv, const float* T, const float* q,
+                                           const float* A, const float* A_lo, float* C, float* C_lo, const float* gm, const float* gv,
+                                           float* gA, float* gA_lo, float* gKzx, float* gLinv, float* gT, float* gq, float* ws, int M,
+                                           int N, int L, void* stream) {
+  if (!gpz_svgp_predict_tc_supported(M, N) || L <= 0) return GPZ_ERR_UNSUPPORTED;
+  return predict_bwd_tc(Kzx, Kzx_lo, Linv, T, q, A, A_lo, C, C_lo, gm, gv, gA, gA_lo, gKzx, gLinv, gT, gq, ws, M, N, L,
+                        (cudaStream_t)stream);
+}
 
 #define GPZ_PREDICT_IMPL(SUF, T)                                                                                      \
   extern "C" int gpz_svgp_predict_fwd_##SUF(const T* Kzx, const T* Linv, const T* Tm, const T* q, const T* kxx, T* A, \

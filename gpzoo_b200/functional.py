@@ -12,7 +12,7 @@ from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
 from . import _cabi
-from ._cabi import c_i, c_i64, c_p, call, ptr, scalar
+from ._cabi import c_f, c_i, c_i64, c_p, call, ptr, scalar
 
 # When True (default) a non-positive-definite Kzz raises torch.linalg.LinAlgError right away like the
 # reference's torch.linalg.cholesky (one device sync).  Throughput runs may turn it off and call
@@ -76,7 +76,7 @@ class KernelBuild(Function):
     Replaces kernels.py:114-130 / 141-155 / 172-191 / 204-228 (+ utilities.py:407-418 add_jitter)."""
 
     @staticmethod
-    def forward(ctx, x1, x2, sigma, ls, a, r2, g1, g2, p_half, jitter):
+    def forward(ctx, x1, x2, sigma, ls, a, r2, g1, g2, p_half, jitter, want_lo=False):
         x1, x2, sigma, ls = _c(x1), _c(x2), _c(sigma), _c(ls)
         dt = x1.dtype
         n1, D = x1.shape
@@ -86,17 +86,23 @@ class KernelBuild(Function):
         if mg:
             a, r2, g1, g2 = _c(a), _c(r2), _c(g1), _c(g2)
         out = torch.empty((L, n1, n2), dtype=dt, device=x1.device)
+        want_lo = bool(want_lo) and dt == torch.float32
+        out_lo = torch.empty_like(out) if want_lo else None
         call("kernel_build_fwd", dt, ptr(x1), ptr(x2), ptr(sigma), ptr(ls), ptr(a if mg else None),
              ptr(r2 if mg else None), ptr(g1 if mg else None), ptr(g2 if mg else None), c_i(n1), c_i(n2), c_i(D), c_i(L),
-             c_i(r2.shape[0] if mg else 0), scalar(dt, p_half), scalar(dt, jitter), ptr(out))
+             c_i(r2.shape[0] if mg else 0), scalar(dt, p_half), scalar(dt, jitter), ptr(out), ptr(out_lo))
         ctx.save_for_backward(x1, x2, sigma, ls, a if mg else None, r2 if mg else None, g1 if mg else None,
                               g2 if mg else None)
         ctx.p_half = p_half
+        ctx.want_lo = want_lo
+        if want_lo:
+            ctx.mark_non_differentiable(out_lo)
+            return out, out_lo
         return out
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, G):
+    def backward(ctx, G, *unused):
         x1, x2, sigma, ls, a, r2, g1, g2 = ctx.saved_tensors
         dt = x1.dtype
         G = _c(G)
@@ -114,7 +120,7 @@ class KernelBuild(Function):
         call("kernel_build_bwd", dt, ptr(x1), ptr(x2), ptr(sigma), ptr(ls), ptr(a), ptr(r2), ptr(g1), ptr(g2),
              c_i(n1), c_i(n2), c_i(D), c_i(L), c_i(r2.shape[0] if mg else 0), scalar(dt, ctx.p_half), ptr(G),
              ptr(g_x1), ptr(g_x2), ptr(g_sigma), ptr(g_ls), ptr(g_a), ptr(ws))
-        return g_x1, g_x2, g_sigma, g_ls, g_a, None, None, None, None, None
+        return g_x1, g_x2, g_sigma, g_ls, g_a, None, None, None, None, None, None
 
 
 def cdist(x1, x2):
@@ -220,11 +226,20 @@ class Whiten(Function):
 # ------------------------------------------------------------------------------------------------
 # K3 / K4
 # ------------------------------------------------------------------------------------------------
+USE_TENSOR_CORES = True      # fp32: route the N-proportional contractions through the tcgen05 split-TF32 kernels
+
+
+def tensor_core_predict_ok(dtype, M, N):
+    return (USE_TENSOR_CORES and dtype == torch.float32
+            and bool(_cabi.lib().gpz_svgp_predict_tc_supported(c_i(int(M)), c_i(int(N)))))
+
+
 class Predict(Function):
-    """SVGP predictive mean and variance (gp.py:218-225 + utilities.py:382-397), see csrc/predict.cu."""
+    """SVGP predictive mean and variance (gp.py:218-225 + utilities.py:382-397), see csrc/predict.cu.
+    fp32 with Kzx_lo given: tcgen05 split-TF32 GEMMs (csrc/umma_gemm.cu); otherwise exact CUDA-core GEMMs."""
 
     @staticmethod
-    def forward(ctx, Kxx, Kzx, Linv, T, q):
+    def forward(ctx, Kxx, Kzx, Linv, T, q, Kzx_lo=None):
         Kxx, Kzx, Linv, T, q = _c(Kxx), _c(Kzx), _c(Linv), _c(T), _c(q)
         dt = Kzx.dtype
         L, M, N = Kzx.shape
@@ -232,15 +247,28 @@ class Predict(Function):
         C = torch.empty_like(Kzx)
         mean = torch.empty((L, N), dtype=dt, device=Kzx.device)
         var = torch.empty_like(mean)
-        call("svgp_predict_fwd", dt, ptr(Kzx), ptr(Linv), ptr(T), ptr(q), ptr(Kxx), ptr(A), ptr(C), ptr(mean), ptr(var),
-             c_i(M), c_i(N), c_i(L))
-        ctx.save_for_backward(Kzx, Linv, T, q, A, C)
+        tc = Kzx_lo is not None and tensor_core_predict_ok(dt, M, N)
+        ctx.tc = tc
+        if tc:
+            Kzx_lo = _c(Kzx_lo)
+            A_lo = torch.empty_like(Kzx)
+            ws = torch.empty(6 * L * M * M, dtype=dt, device=Kzx.device)
+            call("svgp_predict_fwd_tc", dt, ptr(Kzx), ptr(Kzx_lo), ptr(Linv), ptr(T), ptr(q), ptr(Kxx), ptr(A), ptr(A_lo), ptr(C),
+                 ptr(mean), ptr(var), ptr(ws), c_i(M), c_i(N), c_i(L))
+            ctx.save_for_backward(Kzx, Linv, T, q, A, C, Kzx_lo, A_lo, ws)
+        else:
+            call("svgp_predict_fwd", dt, ptr(Kzx), ptr(Linv), ptr(T), ptr(q), ptr(Kxx), ptr(A), ptr(C), ptr(mean), ptr(var),
+                 c_i(M), c_i(N), c_i(L))
+            ctx.save_for_backward(Kzx, Linv, T, q, A, C)
         return mean, var
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gm, gv):
-        Kzx, Linv, T, q, A, C = ctx.saved_tensors
+        if ctx.tc:
+            Kzx, Linv, T, q, A, C, Kzx_lo, A_lo, ws = ctx.saved_tensors
+        else:
+            Kzx, Linv, T, q, A, C = ctx.saved_tensors
         dt = Kzx.dtype
         L, M, N = Kzx.shape
         gm = _c(gm) if gm is not None else torch.zeros((L, N), dtype=dt, device=Kzx.device)
@@ -250,9 +278,39 @@ class Predict(Function):
         gLinv = torch.zeros_like(Linv)
         gT = torch.zeros_like(T)
         gq = torch.empty_like(q)
-        call("svgp_predict_bwd", dt, ptr(Kzx), ptr(Linv), ptr(T), ptr(q), ptr(A), ptr(C), ptr(gm), ptr(gv), ptr(gA),
-             ptr(gKzx), ptr(gLinv), ptr(gT), ptr(gq), c_i(M), c_i(N), c_i(L))
-        return gv, gKzx, gLinv, gT, gq
+        if ctx.tc:
+            C_lo = torch.empty_like(Kzx)
+            gA_lo = torch.empty_like(Kzx)
+            call("svgp_predict_bwd_tc", dt, ptr(Kzx), ptr(Kzx_lo), ptr(Linv), ptr(T), ptr(q), ptr(A), ptr(A_lo), ptr(C), ptr(C_lo),
+                 ptr(gm), ptr(gv), ptr(gA), ptr(gA_lo), ptr(gKzx), ptr(gLinv), ptr(gT), ptr(gq), ptr(ws), c_i(M), c_i(N), c_i(L))
+        else:
+            call("svgp_predict_bwd", dt, ptr(Kzx), ptr(Linv), ptr(T), ptr(q), ptr(A), ptr(C), ptr(gm), ptr(gv), ptr(gA),
+                 ptr(gKzx), ptr(gLinv), ptr(gT), ptr(gq), c_i(M), c_i(N), c_i(L))
+        return gv, gKzx, gLinv, gT, gq, None
+
+
+def umma_gemm(A, B, b_kmajor, Alo=None, Blo=None, Cin=None, alpha=1.0, want_lo=False, a_tri=0, b_tri=0, d_tri=0, splitk=1,
+              n_terms=3):
+    """Direct access to the tcgen05 split-TF32 batched GEMM (fp32).  A: (b, m, k); B: (b, k, n) or, b_kmajor, (b, n, k)."""
+    bsz, m, k = A.shape
+    n = B.shape[1] if b_kmajor else B.shape[2]
+    lo = lambda x: tf32_lo(x)
+    if n_terms == 3:
+        Alo = lo(A) if Alo is None else Alo
+        Blo = lo(B) if Blo is None else Blo
+    D = torch.zeros((bsz, m, n), dtype=torch.float32, device=A.device)
+    Dlo = torch.empty_like(D) if want_lo else None
+    call("umma_gemm", torch.float32, c_i(int(b_kmajor)), c_i(m), c_i(n), c_i(k), c_f(alpha), ptr(A), ptr(Alo), c_i64(A.shape[2]),
+         c_i64(A.shape[1] * A.shape[2]), ptr(B), ptr(Blo), c_i64(B.shape[2]), c_i64(B.shape[1] * B.shape[2]), ptr(Cin), ptr(D),
+         ptr(Dlo), c_i64(n), c_i64(m * n), c_i(bsz), c_i(a_tri), c_i(b_tri), c_i(d_tri), c_i(splitk), c_i(n_terms))
+    return (D, Dlo) if want_lo else D
+
+
+def tf32_lo(x):
+    x = _c(x)
+    lo = torch.empty_like(x)
+    call("tf32_lo", torch.float32, ptr(x), ptr(lo), c_i64(x.numel()))
+    return lo
 
 
 # ------------------------------------------------------------------------------------------------

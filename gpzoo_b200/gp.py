@@ -58,15 +58,17 @@ class _SparseGPBase(nn.Module):
         self.constraint = constraints.lower_cholesky
 
     # -- kernel calls -------------------------------------------------------------------------------
-    def _kernel_matrices(self, X, groupsX=None):
+    def _kernel_matrices(self, X, groupsX=None, want_lo=False):
+        """Kxx (diag), Kzx, Kzz (+jitter).  want_lo: Kzx comes back as (Kzx, Kzx_lo) for the tensor-core path."""
+        kw = {"_want_lo": True} if want_lo else {}
         if groupsX is not None:
             gZ = self.groupsZ
             Kxx = self.kernel(X, X, groupsX, groupsX, diag=True)
-            Kzx = self.kernel(self.Z, X, gZ, groupsX)
+            Kzx = self.kernel(self.Z, X, gZ, groupsX, **kw)
             Kzz = self.kernel(self.Z, self.Z, gZ, gZ, _jitter=self.jitter)      # add_jitter fused (gp.py:209/360)
         else:
             Kxx = self.kernel(X, X, diag=True)
-            Kzx = self.kernel(self.Z, X)
+            Kzx = self.kernel(self.Z, X, **kw)
             Kzz = self.kernel(self.Z, self.Z, _jitter=self.jitter)
         return Kxx, Kzx, Kzz
 
@@ -89,13 +91,20 @@ class _SparseGPBase(nn.Module):
 
     def moments(self, X, groupsX=None):
         """Fused predictive moments: returns dict(mean, var (unclamped), T, q, Lc, Lu), all L-batched."""
-        Kxx, Kzx, Kzz = self._kernel_matrices(X, groupsX)
+        want_lo = F.tensor_core_predict_ok(X.dtype, self.Z.shape[0], X.shape[0])
+        Kxx, Kzx, Kzz = self._kernel_matrices(X, groupsX, want_lo)
+        Kzx_lo = None
+        if want_lo:
+            Kzx, Kzx_lo = Kzx
         Lc, Linv, Lu, T, q, L = self._whitened(Kzz)
         Kzx = _as3(Kzx)
         Kxx = Kxx if Kxx.dim() == 2 else Kxx.unsqueeze(0)
+        if Kzx_lo is not None:
+            Kzx_lo = _as3(Kzx_lo)
         if Kzx.shape[0] != L:
             Kzx, Kxx = Kzx.expand(L, -1, -1), Kxx.expand(L, -1)
-        mean, var = F.Predict.apply(Kxx, Kzx, Linv, T, q)
+            Kzx_lo = Kzx_lo.expand(L, -1, -1) if Kzx_lo is not None else None
+        mean, var = F.Predict.apply(Kxx, Kzx, Linv, T, q, Kzx_lo)
         return dict(mean=mean, var=var, T=T, q=q, Lc=Lc, Lu=Lu)
 
     def _batched(self):

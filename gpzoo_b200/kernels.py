@@ -43,16 +43,21 @@ class _RBFBase(nn.Module):
     def _group_coeff(self):
         return None
 
-    def _build(self, X, Z, groupsX=None, groupsZ=None, jitter=0.0):
+    def _build(self, X, Z, groupsX=None, groupsZ=None, jitter=0.0, want_lo=False):
         sigma, ls = self._params()
         dt = X.dtype
         sigma, ls = sigma.to(dt), ls.to(dt)
         if groupsX is not None:
             a = self._group_coeff().to(dt)
             r2 = _r2_table(self.embedding, dt).to(X.device)
-            K = F.KernelBuild.apply(X, Z, sigma, ls, a, r2, groupsX, groupsZ, 0.5 * float(self.input_dim), float(jitter))
+            K = F.KernelBuild.apply(X, Z, sigma, ls, a, r2, groupsX, groupsZ, 0.5 * float(self.input_dim), float(jitter),
+                                    want_lo)
         else:
-            K = F.KernelBuild.apply(X, Z, sigma, ls, None, None, None, None, 1.0, float(jitter))
+            K = F.KernelBuild.apply(X, Z, sigma, ls, None, None, None, None, 1.0, float(jitter), want_lo)
+        if want_lo and isinstance(K, tuple):          # (K, K_lo): lo part for the split-TF32 tensor-core GEMMs
+            return K if self._batched else (K[0][0], K[1][0])
+        if want_lo:
+            return K if self._batched else K[0], None
         return K if self._batched else K[0]
 
     def _diag(self, X):
@@ -74,10 +79,10 @@ class RBF(_RBFBase):
         self.lengthscale = nn.Parameter(torch.tensor(lengthscale))
         self.input_dim = 2
 
-    def forward(self, X, Z, diag=False, return_distance=False, _jitter=0.0):
+    def forward(self, X, Z, diag=False, return_distance=False, _jitter=0.0, _want_lo=False):
         if diag:
             return self._diag(X)
-        K = self._build(X, Z, jitter=_jitter)
+        K = self._build(X, Z, jitter=_jitter, want_lo=_want_lo)
         if return_distance:
             return K, F.cdist(X, Z)
         return K
@@ -107,10 +112,10 @@ class MGGP_RBF(RBF):
     def _group_coeff(self):
         return _flat(self.group_diff_param)
 
-    def forward(self, X, Z, groupsX, groupsZ, diag=False, _jitter=0.0):
+    def forward(self, X, Z, groupsX, groupsZ, diag=False, _jitter=0.0, _want_lo=False):
         if diag:
             return self._diag(X)
-        return self._build(X, Z, groupsX, groupsZ, jitter=_jitter)
+        return self._build(X, Z, groupsX, groupsZ, jitter=_jitter, want_lo=_want_lo)
 
 
 class MGGP_NSF_RBF(NSF_RBF):
@@ -128,10 +133,10 @@ class MGGP_NSF_RBF(NSF_RBF):
     def _group_coeff(self):
         return _flat(self.group_diff_param) ** 2
 
-    def forward(self, X, Z, groupsX, groupsZ, diag=False, _jitter=0.0):
+    def forward(self, X, Z, groupsX, groupsZ, diag=False, _jitter=0.0, _want_lo=False):
         if diag:
             return self._diag(X)
-        return self._build(X, Z, groupsX, groupsZ, jitter=_jitter)
+        return self._build(X, Z, groupsX, groupsZ, jitter=_jitter, want_lo=_want_lo)
 
 
 class batched_RBF(_RBFBase):
@@ -153,10 +158,10 @@ class batched_RBF(_RBFBase):
         n = max(s.numel(), l.numel())
         return s.expand(n), l.expand(n)
 
-    def forward(self, X, Z, diag=False, _jitter=0.0):
+    def forward(self, X, Z, diag=False, _jitter=0.0, _want_lo=False):
         if diag:
             return self._diag(X)
-        return self._build(X, Z, jitter=_jitter)
+        return self._build(X, Z, jitter=_jitter, want_lo=_want_lo)
 
 
 class batched_MGGP_RBF(batched_RBF):
@@ -175,8 +180,8 @@ class batched_MGGP_RBF(batched_RBF):
         n = self._params()[0].numel()
         return torch.abs(_flat(self.group_diff_param)).expand(n)
 
-    def forward(self, X, Z, groupsX, groupsZ, diag=False, _jitter=0.0):
+    def forward(self, X, Z, groupsX, groupsZ, diag=False, _jitter=0.0, _want_lo=False):
         if diag:
             return self._diag(X)
         self.input_dim = X.shape[-1]
-        return self._build(X, Z, groupsX, groupsZ, jitter=_jitter)
+        return self._build(X, Z, groupsX, groupsZ, jitter=_jitter, want_lo=_want_lo)

@@ -32,13 +32,14 @@ long long gpz_launch_count(void);
 /* ---- K1 kernel-matrix build: kernels.py:114-130 (RBF), 141-155 (NSF_RBF), 172-191 (MGGP_RBF),
  *      204-228 (MGGP_NSF_RBF); jitter = utilities.py:407-418 (add_jitter) fused on the diagonal.
  *      out[l,i,j] = sigma_l^2 exp(-0.5 |x1_i-x2_j|^2/(ls_l^2 den))/den^p_half (+ jitter if i==j),
- *      den = a_l r2[g1_i,g2_j] + 1.  Pass a=r2=g1=g2=NULL, ng=0 for the plain RBF. */
+ *      den = a_l r2[g1_i,g2_j] + 1.  Pass a=r2=g1=g2=NULL, ng=0 for the plain RBF.
+ *      out_lo (optional, f32 only): lo = out - tf32_trunc(out), the second operand of the split-TF32 GEMMs. */
 int gpz_kernel_build_fwd_f32(const float* x1, const float* x2, const float* sigma, const float* ls, const float* a,
                              const float* r2, const int64_t* g1, const int64_t* g2, int n1, int n2, int D, int L, int ng,
-                             float p_half, float jitter, float* out, void* stream);
+                             float p_half, float jitter, float* out, float* out_lo, void* stream);
 int gpz_kernel_build_fwd_f64(const double* x1, const double* x2, const double* sigma, const double* ls, const double* a,
                              const double* r2, const int64_t* g1, const int64_t* g2, int n1, int n2, int D, int L, int ng,
-                             double p_half, double jitter, double* out, void* stream);
+                             double p_half, double jitter, double* out, double* out_lo, void* stream);
 /* backward of the above (autograd of kernels.py forward): G = dLoss/dout; g_x1/g_x2/g_a may be NULL.
  * ws: 3*L + n1*D doubles of scratch (parameter and x1 gradients are accumulated in fp64). */
 int gpz_kernel_build_bwd_f32(const float* x1, const float* x2, const float* sigma, const float* ls, const float* a,
@@ -93,6 +94,18 @@ int gpz_svgp_predict_bwd_f64(const double* Kzx, const double* Linv, const double
                              double* C, const double* gm, const double* gv, double* gA, double* gKzx, double* gLinv,
                              double* gT, double* gq, int M, int N, int L, void* stream);
 
+/* tensor-core (tcgen05 split-TF32) variant of the two calls above, fp32 only.  Kzx_lo: lo part of Kzx (kernel_build out_lo);
+ * A_lo, C_lo, gA_lo: L x M x N scratch kept between forward and backward / inside the backward; ws: 6*L*M*M floats
+ * (the same buffer must be passed to forward and backward).  gLinv and gT must be zero-filled by the caller. */
+int gpz_svgp_predict_tc_supported(int M, int N);
+int gpz_svgp_predict_fwd_tc_f32(const float* Kzx, const float* Kzx_lo, const float* Linv, const float* T, const float* q,
+                                const float* kxx, float* A, float* A_lo, float* C, float* mean, float* var, float* ws, int M, int N,
+                                int L, void* stream);
+int gpz_svgp_predict_bwd_tc_f32(const float* Kzx, const float* Kzx_lo, const float* Linv, const float* T, const float* q,
+                                const float* A, const float* A_lo, float* C, float* C_lo, const float* gm, const float* gv, float* gA,
+                                float* gA_lo, float* gKzx, float* gLinv, float* gT, float* gq, float* ws, int M, int N, int L,
+                                void* stream);
+
 /* ---- K5 KL(qU || pU): utilities.py:481,616 -> torch kl.py MVN||MVN, from the whitened T, q */
 int gpz_mvn_kl_fwd_f32(const float* T, const float* q, const float* Lc, const float* Lu, float* kl, int M, int L, void* stream);
 int gpz_mvn_kl_fwd_f64(const double* T, const double* q, const double* Lc, const double* Lu, double* kl, int M, int L,
@@ -122,6 +135,18 @@ int gpz_poisson_rate_f32(const float* W, int w_softplus, const float* V, const i
                          int G, int nF, int B, int E, void* stream);
 int gpz_poisson_rate_f64(const double* W, int w_softplus, const double* V, const int64_t* idx, const double* F, double* rate,
                          int G, int nF, int B, int E, void* stream);
+
+/* ---- tcgen05 / TMA batched GEMM in split-TF32 arithmetic (fp32 hot path of K3/K4 and their backward; csrc/umma_gemm.cu).
+ *      D = alpha A op(B) (+ Cin), A m x k K-major; op(B): b_kmajor=0 -> B is k x n (n contiguous), 1 -> B is n x k.
+ *      Alo/Blo: lo = x - tf32_trunc(x) parts (n_terms=3) or NULL (n_terms=1); Dlo (optional) receives the lo part of D.
+ *      Replaces the cuBLAS GEMMs behind torch.cholesky_solve / W@(S-Kzz) (gp.py:218, utilities.py:395) and autograd's. */
+int gpz_umma_gemm_supported(int b_kmajor, int m, int n, int k, int64_t lda, int64_t ldb, int64_t ldd);
+int gpz_umma_gemm_f32(int b_kmajor, int m, int n, int k, float alpha, const float* A, const float* Alo, int64_t lda, int64_t sA,
+                      const float* B, const float* Blo, int64_t ldb, int64_t sB, const float* Cin, float* D, float* Dlo,
+                      int64_t ldd, int64_t sD, int batch, int a_tri, int b_tri, int d_tri, int splitk, int n_terms, void* stream);
+/* lo = x - tf32_trunc(x) (flat array);  xt = x^T per M x M matrix with optional lo part */
+int gpz_tf32_lo_f32(const float* x, float* lo, int64_t n, void* stream);
+int gpz_transpose_lo_f32(const float* x, float* xt, float* xt_lo, int M, int L, void* stream);
 
 #ifdef __cplusplus
 }

@@ -237,3 +237,69 @@ def test_poisson_fused_vs_oracle(dt, case):
     Fd = Fs.detach().to(DEV, dt).requires_grad_(True)
     r2 = F.poisson_rate(dl2[0], dl2[1], None if idx is None else idx.to(DEV), Fd, soft)
     assert relerr(r2, rate) < tol
+
+
+@pytest.mark.parametrize("bk", [0, 1])
+def test_umma_gemm_split_tf32(bk):
+    """tcgen05/TMA split-TF32 GEMM vs fp64: ragged sizes, batch, triangular skipping, Cin, lo output, split-K."""
+    from gpzoo_b200 import functional as F
+    g = torch.Generator().manual_seed(11)
+    b, m, n, k = 2, 300, 520, 200
+    A = torch.randn(b, m, k, generator=g)
+    B = torch.randn((b, n, k) if bk else (b, k, n), generator=g)
+    ref = A.double() @ (B.double().transpose(1, 2) if bk else B.double())
+    out, lo = F.umma_gemm(A.to(DEV), B.to(DEV), bk, want_lo=True)
+    assert relerr(out, ref) < 2e-6
+    assert relerr(out.double() - lo.double(), (out.view(torch.int32) & -8192).view(torch.float32)) < 1e-12
+    one = F.umma_gemm(A.to(DEV), B.to(DEV), bk, n_terms=1)                  # plain TF32: only ~1e-3
+    assert 1e-5 < relerr(one, ref) < 3e-3
+    Cin = torch.randn(b, m, n, generator=g)
+    out2 = F.umma_gemm(A.to(DEV), B.to(DEV), bk, Cin=Cin.to(DEV), alpha=0.5)
+    assert relerr(out2, 0.5 * ref + Cin.double()) < 2e-6
+    out3 = F.umma_gemm(A.to(DEV), B.to(DEV), bk, splitk=3)
+    assert relerr(out3, ref) < 2e-6
+    # square, triangular A (lower) and lower-triangular output
+    m2 = 384
+    Lo = torch.tril(torch.randn(b, m2, m2, generator=g))
+    R = torch.randn((b, 640, m2) if bk else (b, m2, 640), generator=g)
+    refL = Lo.double() @ (R.double().transpose(1, 2) if bk else R.double())
+    assert relerr(F.umma_gemm(Lo.to(DEV), R.to(DEV), bk, a_tri=1), refL) < 2e-6
+    Up = Lo.transpose(1, 2).contiguous()
+    refU = Up.double() @ (R.double().transpose(1, 2) if bk else R.double())
+    assert relerr(F.umma_gemm(Up.to(DEV), R.to(DEV), bk, a_tri=2), refU) < 2e-6
+    if bk:
+        S = torch.randn(b, m2, 1000, generator=g)
+        refS = torch.tril(S.double() @ S.double().transpose(1, 2))
+        assert relerr(F.umma_gemm(S.to(DEV), S.to(DEV), 1, d_tri=1, splitk=2), refS) < 2e-6
+
+
+def test_predict_tensor_core_path_vs_exact():
+    """fp32 tensor-core predict (split-TF32) against the fp64 CUDA-core path on the same inputs, fwd and bwd."""
+    from gpzoo_b200 import functional as F
+    g = torch.Generator().manual_seed(13)
+    L, M, N = 2, 192, 768
+    Z = torch.rand(M, 2, generator=g, dtype=torch.float64) * 10
+    X = torch.rand(N, 2, generator=g, dtype=torch.float64) * 10
+    sg = torch.ones(L, dtype=torch.float64)
+    ls = torch.tensor([0.7, 1.0], dtype=torch.float64)
+    mu = torch.randn(L, M, generator=g, dtype=torch.float64)
+    Lur = 0.1 * torch.randn(L, M, M, generator=g, dtype=torch.float64)
+    wm = torch.randn(L, N, generator=g, dtype=torch.float64)
+    wv = torch.randn(L, N, generator=g, dtype=torch.float64)
+    res = {}
+    for dt in (torch.float64, torch.float32):
+        d = lambda t: t.to(DEV, dt)
+        Zd, mud, Lud = d(Z).requires_grad_(True), d(mu).requires_grad_(True), d(Lur).requires_grad_(True)
+        lsd = d(ls).requires_grad_(True)
+        out = F.KernelBuild.apply(Zd, d(X), d(sg), lsd, None, None, None, None, 1.0, 0.0, dt == torch.float32)
+        Kzx, Kzx_lo = out if isinstance(out, tuple) else (out, None)
+        Kzz = F.KernelBuild.apply(Zd, Zd, d(sg), lsd, None, None, None, None, 1.0, 0.05)
+        Lc, Linv = F.CholeskyInverse.apply(Kzz)
+        Lu = F.LowerCholesky.apply(Lud)
+        T, q = F.Whiten.apply(Linv, Lu, mud)
+        Kxx = d(sg)[:, None].expand(-1, N).contiguous() ** 2
+        mean, var = F.Predict.apply(Kxx, Kzx, Linv, T, q, Kzx_lo)
+        ((mean * d(wm)).sum() + (var * d(wv)).sum()).backward()
+        res[dt] = dict(mean=mean, var=var, gZ=Zd.grad, gmu=mud.grad, gLu=Lud.grad, gls=lsd.grad)
+    for k in res[torch.float64]:
+        assert relerr(res[torch.float32][k], res[torch.float64][k]) < 1e-4, k
