@@ -237,7 +237,9 @@ def run_ours(args):
     algo = {   # per-call algorithmic work on ONE rank: ("hbm", bytes) or ("tensor", flops)
         "svgp_predict_fwd": ("tensor", 2.0 * L * M * M * N),
         "svgp_predict_bwd": ("tensor", 4.0 * L * M * M * N),
-        "kernel_build_fwd": ("hbm", 4.0 * L * M * N),
+        "svgp_predict_fwd_tc": ("tensor", 2.0 * L * M * M * N),
+        "svgp_predict_bwd_tc": ("tensor", 4.0 * L * M * M * N),
+        "kernel_build_fwd": ("hbm", 8.0 * L * M * N),      # Kzx and its tf32 lo part
         "kernel_build_bwd": ("hbm", 4.0 * L * M * N),
         "poisson_fwdbwd": ("hbm", 4.0 * G * N + 4.0 * (3 * E * L * N + 2 * G * L + 2 * N)),
     }

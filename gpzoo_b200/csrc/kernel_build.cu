@@ -124,12 +124,12 @@ __global__ void __launch_bounds__(KB_THREADS) kbuild_fwd_kernel(const KBArgs<T> 
 //   g_a[l]     += sum G K0 (0.5 d2/(ls^2 den^2) - p_half/den) r2             (MG)
 //   g_x1[i,:]  -= sum_{l,j} G K0 (x1_i - x2_j)/(ls^2 den) ;  g_x2[j,:] += same
 // One CTA covers KB_ROWS rows x (KB_THREADS*4) columns; the L accumulators live in registers.
-template <typename T, bool MG, bool ALIGNED>
+template <typename T, bool MG, bool ALIGNED, int LMAX>
 __global__ void __launch_bounds__(KB_THREADS) kbuild_bwd_kernel(const KBArgs<T> a, const T* __restrict__ G, int l0, int Lc,
                                                                  double* __restrict__ g_x1, T* __restrict__ g_x2,
                                                                  double* __restrict__ g_sigma, double* __restrict__ g_ls,
                                                                  double* __restrict__ g_a) {
-  __shared__ T s_c[KB_LMAX], s_s2[KB_LMAX], s_a[KB_LMAX];
+  __shared__ T s_c[LMAX], s_s2[LMAX], s_a[LMAX];
   __shared__ T s_r2[MG ? KB_GMAX * KB_GMAX : 1];
   __shared__ double s_red[32];
   __shared__ T s_row[KB_ROWS][KB_DMAX][KB_THREADS / 32];
@@ -153,9 +153,9 @@ __global__ void __launch_bounds__(KB_THREADS) kbuild_bwd_kernel(const KBArgs<T> 
     for (int d = 0; d < KB_DMAX; ++d) xj[d][v] = (v < nv && d < a.D) ? a.x2[(j0 + v) * a.D + d] : T(0);
     gj[v] = (MG && v < nv) ? (int)a.g2[j0 + v] : 0;
   }
-  T acc_s[KB_LMAX], acc_l[KB_LMAX], acc_a[MG ? KB_LMAX : 1];
+  T acc_s[LMAX], acc_l[LMAX], acc_a[MG ? LMAX : 1];
 #pragma unroll
-  for (int l = 0; l < KB_LMAX; ++l) { acc_s[l] = T(0); acc_l[l] = T(0); if (MG) acc_a[l] = T(0); }
+  for (int l = 0; l < LMAX; ++l) { acc_s[l] = T(0); acc_l[l] = T(0); if (MG) acc_a[l] = T(0); }
   T gx2[KB_DMAX][KB_VEC];
 #pragma unroll
   for (int d = 0; d < KB_DMAX; ++d)
@@ -179,25 +179,30 @@ __global__ void __launch_bounds__(KB_THREADS) kbuild_bwd_kernel(const KBArgs<T> 
       for (int v = 0; v < KB_VEC; ++v) r2[v] = s_r2[gi * a.ng + gj[v]];
     }
     if (nv > 0) {
+      // phase 1: issue every load of this row (one 16-byte vector per factor) before any is used
+      T g[LMAX][KB_VEC];
 #pragma unroll
-      for (int l = 0; l < KB_LMAX; ++l) {
+      for (int l = 0; l < LMAX; ++l) {
+        const T* gp = G + ((int64_t)(l0 + (l < Lc ? l : 0)) * a.n1 + i) * a.n2 + j0;
+        if (ALIGNED && nv == KB_VEC) {
+          if (sizeof(T) == 4) {
+            const float4 t = __ldcs(reinterpret_cast<const float4*>(gp));
+            g[l][0] = t.x; g[l][1] = t.y; g[l][2] = t.z; g[l][3] = t.w;
+          } else {
+            const double2 t0 = __ldcs(reinterpret_cast<const double2*>(gp));
+            const double2 t1 = __ldcs(reinterpret_cast<const double2*>(gp) + 1);
+            g[l][0] = t0.x; g[l][1] = t0.y; g[l][2] = t1.x; g[l][3] = t1.y;
+          }
+        } else {
+#pragma unroll
+          for (int v = 0; v < KB_VEC; ++v) g[l][v] = v < nv ? gp[v] : T(0);
+        }
+      }
+      // phase 2: recompute K and accumulate
+#pragma unroll
+      for (int l = 0; l < LMAX; ++l) {
         if (l < Lc) {
           const T c = s_c[l], s2 = s_s2[l];
-          const T* gp = G + ((int64_t)(l0 + l) * a.n1 + i) * a.n2 + j0;
-          T g[KB_VEC];
-          if (ALIGNED && nv == KB_VEC) {
-            if (sizeof(T) == 4) {
-              const float4 t = __ldcs(reinterpret_cast<const float4*>(gp));
-              g[0] = t.x; g[1] = t.y; g[2] = t.z; g[3] = t.w;
-            } else {
-              const double2 t0 = __ldcs(reinterpret_cast<const double2*>(gp));
-              const double2 t1 = __ldcs(reinterpret_cast<const double2*>(gp) + 1);
-              g[0] = t0.x; g[1] = t0.y; g[2] = t1.x; g[3] = t1.y;
-            }
-          } else {
-#pragma unroll
-            for (int v = 0; v < KB_VEC; ++v) g[v] = v < nv ? gp[v] : T(0);
-          }
 #pragma unroll
           for (int v = 0; v < KB_VEC; ++v) {
             T k0, idn;
@@ -210,7 +215,7 @@ __global__ void __launch_bounds__(KB_THREADS) kbuild_bwd_kernel(const KBArgs<T> 
               idn = T(1);
               k0 = s2 * Num<T>::exp(c * d2[v]);
             }
-            const T gk = g[v] * k0;
+            const T gk = g[l][v] * k0;
             const T u = gk * (T(-2) * c) * idn;          // G K0 / (ls^2 den)
             acc_s[l] += gk;
             acc_l[l] = fma(u, d2[v], acc_l[l]);          // later divided by ls
@@ -249,7 +254,7 @@ __global__ void __launch_bounds__(KB_THREADS) kbuild_bwd_kernel(const KBArgs<T> 
         if (d < a.D) atomicAdd(g_x2 + (j0 + v) * a.D + d, gx2[d][v]);
   }
 #pragma unroll
-  for (int l = 0; l < KB_LMAX; ++l) {
+  for (int l = 0; l < LMAX; ++l) {
     if (l < Lc) {                                   // uniform across the block
       double v = block_sum<double>((double)acc_s[l], s_red);
       if (tid == 0) atomicAdd(g_sigma + l0 + l, v);
@@ -321,16 +326,23 @@ int kbuild_bwd(const KBArgs<T>& a, const T* G, T* g_x1, T* g_x2, T* g_sigma, T* 
   if (a.n1 > 0 && a.n2 > 0) {
     const bool al = (a.n2 % KB_VEC == 0) && ((reinterpret_cast<uintptr_t>(G) & 31) == 0);
     dim3 grid((unsigned)cdiv(a.n2, (int64_t)KB_THREADS * KB_VEC), (unsigned)cdiv(a.n1, KB_ROWS));
-    for (int l0 = 0; l0 < a.L; l0 += KB_LMAX) {
-      const int Lc = min(KB_LMAX, a.L - l0);
+    const int lmax = a.L <= 4 ? 4 : (a.L <= 8 ? 8 : (a.L <= 16 ? 16 : KB_LMAX));
+    for (int l0 = 0; l0 < a.L; l0 += lmax) {
+      const int Lc = min(lmax, a.L - l0);
       // g_x1/g_x2 accumulate over all l-chunks (atomics), so every chunk launch adds its share
-      if (mg) {
-        if (al) kbuild_bwd_kernel<T, true, true><<<grid, KB_THREADS, 0, st>>>(a, G, l0, Lc, w_x1, g_x2, w_sigma, w_ls, w_a);
-        else kbuild_bwd_kernel<T, true, false><<<grid, KB_THREADS, 0, st>>>(a, G, l0, Lc, w_x1, g_x2, w_sigma, w_ls, w_a);
-      } else {
-        if (al) kbuild_bwd_kernel<T, false, true><<<grid, KB_THREADS, 0, st>>>(a, G, l0, Lc, w_x1, g_x2, w_sigma, w_ls, w_a);
-        else kbuild_bwd_kernel<T, false, false><<<grid, KB_THREADS, 0, st>>>(a, G, l0, Lc, w_x1, g_x2, w_sigma, w_ls, w_a);
-      }
+#define GPZ_KB_LAUNCH(MGV, ALV, LM) \
+  kbuild_bwd_kernel<T, MGV, ALV, LM><<<grid, KB_THREADS, 0, st>>>(a, G, l0, Lc, w_x1, g_x2, w_sigma, w_ls, w_a)
+#define GPZ_KB_DISPATCH(LM)                                   \
+  do {                                                        \
+    if (mg) { if (al) GPZ_KB_LAUNCH(true, true, LM); else GPZ_KB_LAUNCH(true, false, LM); }     \
+    else { if (al) GPZ_KB_LAUNCH(false, true, LM); else GPZ_KB_LAUNCH(false, false, LM); }      \
+  } while (0)
+      if (lmax == 4) GPZ_KB_DISPATCH(4);
+      else if (lmax == 8) GPZ_KB_DISPATCH(8);
+      else if (lmax == 16) GPZ_KB_DISPATCH(16);
+      else GPZ_KB_DISPATCH(KB_LMAX);
+#undef GPZ_KB_DISPATCH
+#undef GPZ_KB_LAUNCH
       GPZ_CHECK_LAUNCH();
     }
   }

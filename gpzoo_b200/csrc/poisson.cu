@@ -43,12 +43,12 @@ template <typename T, int FMAX>
 __global__ void __launch_bounds__(PZ_SPOTS) poisson_kernel(const PoissonArgs<T> a) {
   extern __shared__ __align__(16) unsigned char pz_smem[];
   typedef T RowT[PZ_SPOTS + 1];
-  typedef T RowE[PZ_SPOTS];
+  typedef T RowE[FMAX];
   typedef T RowW[FMAX];
   typedef T AccW[PZ_GCH][FMAX];
   RowT* tS = reinterpret_cast<RowT*>(pz_smem);                         // [PZ_GCH][PZ_SPOTS+1]
-  RowE* efS = reinterpret_cast<RowE*>(tS + PZ_GCH);                    // [FMAX][PZ_SPOTS]
-  RowW* sW = reinterpret_cast<RowW*>(efS + FMAX);                      // [PZ_GCH][FMAX]
+  RowE* efS = reinterpret_cast<RowE*>(tS + PZ_GCH);                    // [PZ_SPOTS][FMAX]  (spot-major)
+  RowW* sW = reinterpret_cast<RowW*>(efS + PZ_SPOTS);                  // [PZ_GCH][FMAX]
   AccW* sAcc = reinterpret_cast<AccW*>(sW + PZ_GCH);                   // [4][PZ_GCH][FMAX]
   __shared__ double red[32];
 
@@ -100,26 +100,35 @@ __global__ void __launch_bounds__(PZ_SPOTS) poisson_kernel(const PoissonArgs<T> 
       }
       __syncthreads();               // previous phase B finished with tS / efS; sW visible
 #pragma unroll
-      for (int f = 0; f < FMAX; ++f) efS[f][tid] = ef[f];
+      for (int f = 0; f < FMAX; ++f) efS[tid][f] = ef[f];
       // ---- phase A: thread = spot ----
       T llc = T(0);
-      for (int gi = 0; gi < PZ_GCH; ++gi) {
-        T t = T(0);
-        if (active && g0 + gi < g_end) {
-          const T y = a.y[(int64_t)(g0 + gi) * a.y_ld + col];
-          T zr = T(0);
+#pragma unroll 1
+      for (int gb = 0; gb < PZ_GCH; gb += 8) {
+        T yv[8];                      // 8 independent coalesced loads in flight per thread
 #pragma unroll
-          for (int f = 0; f < FMAX; ++f) zr = fma(sW[gi][f], ef[f], zr);
-          const T r = spV * zr;
-          T lp = (y == T(0) ? T(0) : y * Num<T>::log(r)) - r;
-          if (a.with_lgamma && y > T(1.5)) lp -= Num<T>::lgamma(y + T(1));   // lgamma(1) = lgamma(2) = 0
-          llc += lp;
-          t = (y / zr - spV) * invE;
-          gVacc += (y - r) * invE;
+        for (int u = 0; u < 8; ++u)
+          yv[u] = (active && g0 + gb + u < g_end) ? __ldcs(a.y + (int64_t)(g0 + gb + u) * a.y_ld + col) : T(0);
 #pragma unroll
-          for (int f = 0; f < FMAX; ++f) pg[f] = fma(sW[gi][f], t, pg[f]);
+        for (int u = 0; u < 8; ++u) {
+          const int gi = gb + u;
+          T t = T(0);
+          if (active && g0 + gi < g_end) {
+            const T y = yv[u];
+            T zr = T(0);
+#pragma unroll
+            for (int f = 0; f < FMAX; ++f) zr = fma(sW[gi][f], ef[f], zr);
+            const T r = spV * zr;
+            T lp = (y == T(0) ? T(0) : y * Num<T>::log(r)) - r;
+            if (a.with_lgamma && y > T(1.5)) lp -= Num<T>::lgamma(y + T(1));   // lgamma(1) = lgamma(2) = 0
+            llc += lp;
+            t = (y / zr - spV) * invE;
+            gVacc += (y - r) * invE;
+#pragma unroll
+            for (int f = 0; f < FMAX; ++f) pg[f] = fma(sW[gi][f], t, pg[f]);
+          }
+          tS[gi][tid] = t;
         }
-        tS[gi][tid] = t;
       }
       ll += (double)(llc * invE);
 #pragma unroll
@@ -137,7 +146,7 @@ __global__ void __launch_bounds__(PZ_SPOTS) poisson_kernel(const PoissonArgs<T> 
       for (int k = 0; k < 32; ++k) {
         const T t = tS[lane][nb + k];
 #pragma unroll
-        for (int f = 0; f < FMAX; ++f) acc[f] = fma(t, efS[f][nb + k], acc[f]);
+        for (int f = 0; f < FMAX; ++f) acc[f] = fma(t, efS[nb + k][f], acc[f]);
       }
     }
 #pragma unroll
@@ -206,7 +215,7 @@ static void poisson_grid(int G, int B, int* nbx, int* nby, int* gpc) {
   *nbx = (int)cdiv(B, PZ_SPOTS);
   const int chunks = (int)cdiv(G, PZ_GCH);
   int by = 1;
-  if (*nbx < 296) by = (int)min((int64_t)chunks, cdiv(296, *nbx > 0 ? *nbx : 1));
+  if (*nbx < 1184) by = (int)min((int64_t)chunks, cdiv(1184, *nbx > 0 ? *nbx : 1));
   const int cpc = (int)cdiv(chunks, by);
   *gpc = cpc * PZ_GCH;
   *nby = (int)cdiv(G, *gpc);

@@ -314,6 +314,72 @@ def tf32_lo(x):
 
 
 # ------------------------------------------------------------------------------------------------
+# K6  VNNGP
+# ------------------------------------------------------------------------------------------------
+def vnngp_neighbors(X, Z, K):
+    """K nearest inducing points of every x (ascending distance, ties to the lower index) — gp.py:64."""
+    X, Z = _c(X.detach()), _c(Z.detach())
+    idx = torch.empty((X.shape[0], K), dtype=torch.int64, device=X.device)
+    call("vnngp_neighbors", X.dtype, ptr(X), ptr(Z), ptr(idx), c_i(X.shape[0]), c_i(Z.shape[0]), c_i(X.shape[1]), c_i(K))
+    return idx
+
+
+class OuterLower(Function):
+    """S = Lu Lu^T (gp.py:100-102 / 221) with gLu = tril((gS + gS^T) Lu)."""
+
+    @staticmethod
+    def forward(ctx, Lu):
+        Lu = _c(Lu)
+        ctx.save_for_backward(Lu)
+        return gemm(Lu, Lu, tb=True, a_tri=1, b_tri=2)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gS):
+        (Lu,) = ctx.saved_tensors
+        gS = _c(gS)
+        g = gemm(gS, Lu, b_tri=1)
+        gemm(gS, Lu, ta=True, b_tri=1, beta=1.0, out=g)
+        return tri_op(g, 2)
+
+
+class VnngpPredict(Function):
+    """Nearest-neighbour predictive mean / variance (gp.py:67-106), one warp per point (csrc/vnngp.cu)."""
+
+    @staticmethod
+    def forward(ctx, X, Z, sigma, ls, Kzz, S, mu, Kxx, nn, jitter):
+        X, Z, sigma, ls, Kzz, S, mu, Kxx = (_c(t) for t in (X, Z, sigma, ls, Kzz, S, mu, Kxx))
+        dt = Kzz.dtype
+        L, M, _ = Kzz.shape
+        N, D = X.shape
+        K = nn.shape[1]
+        mean = torch.empty((L, N), dtype=dt, device=X.device)
+        var = torch.empty_like(mean)
+        call("vnngp_fwd", dt, ptr(X), ptr(Z), ptr(sigma), ptr(ls), ptr(Kzz), ptr(S), ptr(mu), ptr(Kxx), ptr(nn), c_i(N), c_i(M),
+             c_i(D), c_i(L), c_i(K), scalar(dt, jitter), ptr(mean), ptr(var))
+        ctx.save_for_backward(X, Z, sigma, ls, Kzz, S, mu, Kxx, nn)
+        ctx.jitter = jitter
+        return mean, var
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gm, gv):
+        X, Z, sigma, ls, Kzz, S, mu, Kxx, nn = ctx.saved_tensors
+        dt = Kzz.dtype
+        L, M, _ = Kzz.shape
+        N, D = X.shape
+        K = nn.shape[1]
+        gm = _c(gm) if gm is not None else torch.zeros((L, N), dtype=dt, device=X.device)
+        gv = _c(gv) if gv is not None else torch.zeros((L, N), dtype=dt, device=X.device)
+        gKzz, gS = torch.empty_like(Kzz), torch.empty_like(S)
+        gmu, gZ = torch.empty_like(mu), torch.empty_like(Z)
+        gsl = torch.empty(2 * L, dtype=torch.float64, device=X.device)
+        call("vnngp_bwd", dt, ptr(X), ptr(Z), ptr(sigma), ptr(ls), ptr(Kzz), ptr(S), ptr(mu), ptr(Kxx), ptr(nn), c_i(N), c_i(M),
+             c_i(D), c_i(L), c_i(K), scalar(dt, ctx.jitter), ptr(gm), ptr(gv), ptr(gKzz), ptr(gS), ptr(gmu), ptr(gZ), ptr(gsl))
+        return None, gZ, gsl[:L].to(dt), gsl[L:].to(dt), gKzz, gS, gmu, gv, None, None
+
+
+# ------------------------------------------------------------------------------------------------
 # K5
 # ------------------------------------------------------------------------------------------------
 class MvnKL(Function):

@@ -211,6 +211,49 @@ class MGGP_WSVGP(WSVGP):
         self.groupsZ = nn.Parameter(torch.randint(0, n_groups, (M,)).type(torch.LongTensor), requires_grad=False)
 
 
+class VNNGP(_SparseGPBase):
+    """Nearest-neighbour variational GP (gp.py:7-122): each point conditions on its K nearest inducing points only.
+    KL(qU || pU) is still the full M-dimensional one (gp.py:119-120).  The reference's unconditional prints
+    (gp.py:32,65,79-81,84) are dropped."""
+    clamp_min = 5e-2                                   # gp.py:118
+
+    def __init__(self, kernel, dim=1, M=50, K=3, jitter=1e-4):
+        super().__init__()
+        self.kernel = kernel
+        self.jitter = jitter
+        self.K = K
+        self.Z = nn.Parameter(torch.randn((M, dim)))
+        self.Lu = nn.Parameter(torch.randn((M, M)))
+        self.mu = nn.Parameter(torch.zeros((M,)))
+        self.constraint = constraints.lower_cholesky
+
+    def neighbors(self, X):
+        """N x K int64 indices into Z, ascending distance (gp.py:64)."""
+        return F.vnngp_neighbors(X, self.Z.to(X.dtype), self.K)
+
+    def moments(self, X, groupsX=None):
+        dt = X.dtype
+        Kzz = _as3(self.kernel(self.Z, self.Z, _jitter=self.jitter))                 # first jitter (gp.py:55)
+        Kxx = self.kernel(X, X, diag=True)
+        Kxx = Kxx if Kxx.dim() == 2 else Kxx.unsqueeze(0)
+        Lc, Linv, Lu, T, q, L = self._whitened(Kzz)
+        if Kzz.shape[0] != L:
+            Kzz, Kxx = Kzz.expand(L, -1, -1), Kxx.expand(L, -1)
+        S = F.OuterLower.apply(Lu)
+        mu = self.mu if self.mu.dim() == 2 else self.mu.unsqueeze(0)
+        mu = (mu if mu.shape[0] == L else mu.expand(L, -1)).to(dt)
+        sigma = self.kernel.sigma.reshape(-1).to(dt)
+        ls = self.kernel.lengthscale.reshape(-1).to(dt)
+        if sigma.numel() != L:
+            sigma, ls = sigma.expand(L), ls.expand(L)
+        nn_idx = self.neighbors(X)
+        mean, var = F.VnngpPredict.apply(X, self.Z.to(dt), sigma, ls, Kzz, S, mu, Kxx, nn_idx, float(self.jitter))
+        return dict(mean=mean, var=var, T=T, q=q, Lc=Lc, Lu=Lu, nn=nn_idx)
+
+    def forward(self, X, verbose=False):
+        return self._distributions(self.moments(X))
+
+
 class GaussianPrior(nn.Module):
     """Non-spatial mean-field factors (gp.py:125-146): per-spot mean and softplus(scale), prior N(0, scale_pf).
     O(L*N) element-wise parameters; their fused use is inside the Poisson likelihood kernel."""

@@ -115,6 +115,27 @@ int gpz_mvn_kl_bwd_f32(const float* g, const float* T, const float* q, const flo
 int gpz_mvn_kl_bwd_f64(const double* g, const double* T, const double* q, const double* Lc, const double* Lu, double* gT,
                        double* gq, double* gLc, double* gLu, int M, int L, void* stream);
 
+/* ---- K6 VNNGP (gp.py:19-122).  neighbors: idx[n,:] = the K inducing points nearest to x_n, ascending distance, ties to the
+ *      lower index (gp.py:64 argsort(cdist)[:, :K]).  fwd: per point and factor the K x K system
+ *      kzz = Kzz[l][nn,nn] + jitter I, w = kzz^-1 kxz, mean = w.mu[nn], var = kxx + w^T S[nn,nn] w - w.kxz  (gp.py:67-106).
+ *      bwd: scatter-adds dL/dKzz, dL/dS (L x M x M), dL/dmu (L x M), dL/dZ (M x D, through kxz) and gsl = [dL/dsigma | dL/dls]
+ *      (2L doubles, through kxz); all outputs are zero-filled by the call.  K <= 16. */
+int gpz_vnngp_neighbors_f32(const float* X, const float* Z, int64_t* idx, int N, int M, int D, int K, void* stream);
+int gpz_vnngp_neighbors_f64(const double* X, const double* Z, int64_t* idx, int N, int M, int D, int K, void* stream);
+int gpz_vnngp_fwd_f32(const float* X, const float* Z, const float* sigma, const float* ls, const float* Kzz, const float* S,
+                      const float* mu, const float* kxx, const int64_t* nn, int N, int M, int D, int L, int K, float jitter,
+                      float* mean, float* var, void* stream);
+int gpz_vnngp_fwd_f64(const double* X, const double* Z, const double* sigma, const double* ls, const double* Kzz, const double* S,
+                      const double* mu, const double* kxx, const int64_t* nn, int N, int M, int D, int L, int K, double jitter,
+                      double* mean, double* var, void* stream);
+int gpz_vnngp_bwd_f32(const float* X, const float* Z, const float* sigma, const float* ls, const float* Kzz, const float* S,
+                      const float* mu, const float* kxx, const int64_t* nn, int N, int M, int D, int L, int K, float jitter,
+                      const float* gm, const float* gv, float* gKzz, float* gS, float* gmu, float* gZ, double* gsl, void* stream);
+int gpz_vnngp_bwd_f64(const double* X, const double* Z, const double* sigma, const double* ls, const double* Kzz, const double* S,
+                      const double* mu, const double* kxx, const int64_t* nn, int N, int M, int D, int L, int K, double jitter,
+                      const double* gm, const double* gv, double* gKzz, double* gS, double* gmu, double* gZ, double* gsl,
+                      void* stream);
+
 /* ---- K7 fused Poisson log-likelihood + loading contraction, forward and backward in one pass:
  *      likelihoods.py:49-53 (get_rate), 80-97 (NSF2), 110-145 (Hybrid_NSF2), 226-253 (NSF), 304-330 (Hybrid_NSF);
  *      utilities.py:479,507,611-614 (ELBO reduction); torch poisson.py log_prob.

@@ -194,3 +194,44 @@ def test_size_independent_properties_fp32():
     assert relerr(ll_sum, p0["ll"]) < 1e-5
     for k, v in named.items():
         assert relerr(v.grad, g0[k]) < 2e-4, k
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_vnngp_config3(dt):
+    """NSF2(VNNGP(NSF_RBF)): neighbour indices bit-exact, ELBO / moments / gradients vs the reference's golden."""
+    import gpzoo_b200 as gz
+    inp, gout, ggrad = load_golden("nsf_vnngp")
+    L, M = inp["mu"].shape
+    kern = gz.kernels.NSF_RBF(L=L)
+    kern.sigma, kern.lengthscale = _P(inp["sigma"], dt), _P(inp["lengthscale"], dt)
+    gp = gz.gp.VNNGP(kern, dim=2, M=M, K=inp["K"], jitter=inp["jitter"])
+    gp.Z, gp.mu, gp.Lu = _P(inp["Z"], dt), _P(inp["mu"], dt), _P(inp["Lu_raw"], dt)
+    model = gz.likelihoods.NSF2(gp, inp["y"], L=L)
+    model.W, model.V = _P(inp["W"], dt), _P(inp["V"], dt)
+    X = inp["X"].to(DEV, dt)
+    assert torch.equal(gp.neighbors(X).cpu(), gout["nn"])                       # bit-exact neighbour indexing
+    elbo, parts = model.elbo(X, inp["y"].to(DEV, dt), E=inp["eps"].shape[0], eps=inp["eps"].to(DEV, dt), return_parts=True)
+    tol = TOL[dt]
+    assert relerr(elbo, gout["elbo"]) < tol
+    assert relerr(parts["mean"], gout["mean"]) < tol and relerr(parts["var"].clamp(min=5e-2), gout["var"]) < tol
+    (-elbo).backward()
+    named = dict(Z=gp.Z, sigma=kern.sigma, lengthscale=kern.lengthscale, mu=gp.mu, Lu_raw=gp.Lu, W=model.W, V=model.V)
+    for p in named.values():
+        p.grad.neg_()
+    _check_grads(named, ggrad, tol)
+    # drop-in distributions
+    qF, qU, pU = gp(X)
+    assert relerr(qF.mean, gout["mean"]) < tol and relerr(qF.scale ** 2, gout["var"]) < tol
+
+
+def test_vnngp_neighbors_ties_and_sizes():
+    """Exact ties go to the lower index; K up to 16; matches a stable argsort of direct-difference distances."""
+    from gpzoo_b200 import functional as F
+    g = torch.Generator().manual_seed(4)
+    Z = torch.randint(0, 6, (300, 2), generator=g).double()          # lattice -> many exact ties
+    X = torch.randint(0, 6, (500, 2), generator=g).double() + 0.5
+    d = torch.cdist(X, Z, compute_mode="donot_use_mm_for_euclid_dist")
+    for K in (1, 3, 8, 13, 16):
+        ref = torch.sort(d, dim=1, stable=True).indices[:, :K]
+        got = F.vnngp_neighbors(X.to(DEV), Z.to(DEV), K).cpu()
+        assert torch.equal(got, ref), K

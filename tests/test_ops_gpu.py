@@ -249,28 +249,28 @@ def test_umma_gemm_split_tf32(bk):
     B = torch.randn((b, n, k) if bk else (b, k, n), generator=g)
     ref = A.double() @ (B.double().transpose(1, 2) if bk else B.double())
     out, lo = F.umma_gemm(A.to(DEV), B.to(DEV), bk, want_lo=True)
-    assert relerr(out, ref) < 2e-6
+    assert relerr(out, ref) < 5e-6
     assert relerr(out.double() - lo.double(), (out.view(torch.int32) & -8192).view(torch.float32)) < 1e-12
     one = F.umma_gemm(A.to(DEV), B.to(DEV), bk, n_terms=1)                  # plain TF32: only ~1e-3
     assert 1e-5 < relerr(one, ref) < 3e-3
     Cin = torch.randn(b, m, n, generator=g)
     out2 = F.umma_gemm(A.to(DEV), B.to(DEV), bk, Cin=Cin.to(DEV), alpha=0.5)
-    assert relerr(out2, 0.5 * ref + Cin.double()) < 2e-6
+    assert relerr(out2, 0.5 * ref + Cin.double()) < 5e-6
     out3 = F.umma_gemm(A.to(DEV), B.to(DEV), bk, splitk=3)
-    assert relerr(out3, ref) < 2e-6
+    assert relerr(out3, ref) < 5e-6
     # square, triangular A (lower) and lower-triangular output
     m2 = 384
     Lo = torch.tril(torch.randn(b, m2, m2, generator=g))
     R = torch.randn((b, 640, m2) if bk else (b, m2, 640), generator=g)
     refL = Lo.double() @ (R.double().transpose(1, 2) if bk else R.double())
-    assert relerr(F.umma_gemm(Lo.to(DEV), R.to(DEV), bk, a_tri=1), refL) < 2e-6
+    assert relerr(F.umma_gemm(Lo.to(DEV), R.to(DEV), bk, a_tri=1), refL) < 5e-6
     Up = Lo.transpose(1, 2).contiguous()
     refU = Up.double() @ (R.double().transpose(1, 2) if bk else R.double())
-    assert relerr(F.umma_gemm(Up.to(DEV), R.to(DEV), bk, a_tri=2), refU) < 2e-6
+    assert relerr(F.umma_gemm(Up.to(DEV), R.to(DEV), bk, a_tri=2), refU) < 5e-6
     if bk:
         S = torch.randn(b, m2, 1000, generator=g)
         refS = torch.tril(S.double() @ S.double().transpose(1, 2))
-        assert relerr(F.umma_gemm(S.to(DEV), S.to(DEV), 1, d_tri=1, splitk=2), refS) < 2e-6
+        assert relerr(F.umma_gemm(S.to(DEV), S.to(DEV), 1, d_tri=1, splitk=2), refS) < 2e-5
 
 
 def test_predict_tensor_core_path_vs_exact():
