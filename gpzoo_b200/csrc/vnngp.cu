@@ -35,9 +35,9 @@ __global__ void __launch_bounds__(128) knn_kernel(const T* __restrict__ X, const
   for (int k = 0; k < KMAX; ++k) { bd[k] = T(INFINITY); bi[k] = 0x7fffffff; }
   for (int m0 = 0; m0 < M; m0 += NN_TILE) {
     __syncthreads();
-    for (int e = threadIdx.x; e < NN_TILE * D; e += blockDim.x) {
-      const int r = e / D, d = e % D;
-      zs[r][d] = (m0 + r < M) ? Z[(int64_t)(m0 + r) * D + d] : T(0);
+    for (int e = threadIdx.x; e < NN_TILE * NN_DMAX; e += blockDim.x) {
+      const int r = e / NN_DMAX, d = e % NN_DMAX;
+      zs[r][d] = (m0 + r < M && d < D) ? Z[(int64_t)(m0 + r) * D + d] : T(0);
     }
     __syncthreads();
     const int mt = min(NN_TILE, M - m0);
