@@ -140,6 +140,7 @@ def run_ours(args):
     import torch.distributed as dist
     import gpzoo_b200 as gz
     from gpzoo_b200 import _cabi, functional, synthetic
+    from gpzoo_b200.distributed import FlatGradReducer, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -153,8 +154,9 @@ def run_ours(args):
     c = CFG
     prob = synthetic.nsf_problem(N=c["N"], M=c["M"], L=c["L"], G=c["G"], E=c["E"], seed=c["seed"], coord_scale=c["coord_scale"],
                                  lengthscale=c["lengthscale"], jitter=c["jitter"], dtype=dt)
-    n_loc = c["N"] // world
-    sl = slice(rank * n_loc, (rank + 1) * n_loc)
+    lo, hi = shard_range(c["N"], world, rank)
+    n_loc = hi - lo
+    sl = slice(lo, hi)
     # host (pinned) copies of this rank's shard: the e2e leg copies them in every step
     hX = prob["X"][sl].contiguous().pin_memory()
     hy = prob["y"][:, sl].contiguous().pin_memory()
@@ -163,26 +165,14 @@ def run_ours(args):
     model, shared = build_model(prob_loc, dt, dev)
     X, y = hX.to(dev), hy.to(dev)
     eps = prob["eps"][:, :, sl].contiguous().to(dev)
-    flat = torch.zeros(sum(p.numel() for p in shared) + 1, dtype=dt, device=dev)
+    reducer = FlatGradReducer(shared, device=dev, dtype=dt)
 
     def step(Xd, yd, epsd):
         for p in model.parameters():
             p.grad = None
         elbo = model.elbo(Xd, yd, E=c["E"], eps=epsd, kl_weight=1.0 / world)
         (-elbo).backward()
-        if world > 1:
-            o = 0
-            for p in shared:
-                flat[o:o + p.numel()].copy_(p.grad.reshape(-1))
-                o += p.numel()
-            flat[o] = elbo.detach()
-            dist.all_reduce(flat)
-            o = 0
-            for p in shared:
-                p.grad.copy_(flat[o:o + p.numel()].view_as(p.grad))
-                o += p.numel()
-            return flat[o]
-        return elbo.detach()
+        return reducer.all_reduce(elbo)      # one NCCL all-reduce of the flat shared-gradient buffer (+ ELBO)
 
     def barrier():
         if world > 1:
