@@ -163,6 +163,159 @@ template <typename T> int trtri(const T* Lc, T* X, T* tmp, int M, int L, cudaStr
   return GPZ_OK;
 }
 
+// ---- fused recursive Cholesky + inverse -------------------------------------------------------------
+// (Lc, X = Lc^-1) by divide and conquer: for A = [A11 .; A21 A22]
+//     (L11, X11) = rec(A11);  L21 = A21 X11^T;  A22 -= L21 L21^T;  (L22, X22) = rec(A22);  X21 = -X22 (L21 X11)
+// so all O(M^3) work is GEMMs (4 per internal node) and the only sequential kernel is the 64 x 64 leaf below, which
+// factors AND inverts its block in shared memory with 16-wide sub-blocking (a dozen block barriers instead of 128).
+template <typename T>
+__global__ void __launch_bounds__(256) chol_inv_leaf_kernel(const T* __restrict__ Wall, T* __restrict__ Lall, T* __restrict__ Xall,
+                                                             int M, int r0, int n, int* __restrict__ info) {
+  constexpr int SB = 16;
+  extern __shared__ __align__(16) unsigned char leaf_smem[];
+  typedef T Row[NB + 1];
+  Row* a = reinterpret_cast<Row*>(leaf_smem);
+  Row* x = a + NB;
+  __shared__ T sbuf[SB][SB + 1];
+  const int64_t off = (int64_t)blockIdx.x * M * M;
+  const T* W = Wall + off;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int i = e / NB, j = e % NB;
+    a[i][j] = (i < n && j <= i) ? W[(int64_t)(r0 + i) * M + r0 + j] : T(0);
+    x[i][j] = T(0);
+  }
+  __syncthreads();
+  // ---- Cholesky ----
+  for (int j0 = 0; j0 < n; j0 += SB) {
+    const int jn = min(SB, n - j0);
+    if (warp == 0) {                                   // (a) diagonal 16 x 16 block, lane = row
+      const int row = j0 + lane;
+      for (int j = j0; j < j0 + jn; ++j) {
+        const T d = a[j][j];
+        if (!(d > T(0)) && lane == 0 && info[blockIdx.x] == 0) info[blockIdx.x] = r0 + j + 1;
+        const T sd = Num<T>::sqrt(d);
+        __syncwarp();
+        if (lane < jn && row > j) {
+          const T v = a[row][j] / sd;
+          a[row][j] = v;
+        }
+        if (lane == 0) a[j][j] = sd;
+        __syncwarp();
+        if (lane < jn && row > j) {
+          const T v = a[row][j];
+          for (int k = j + 1; k <= row; ++k) a[row][k] -= v * a[k][j];
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    const int rest0 = j0 + jn;
+    if (rest0 < n) {
+      // (b) panel rows below: one thread per row
+      if (tid < n - rest0) {
+        const int i = rest0 + tid;
+        for (int c = 0; c < jn; ++c) {
+          T v = a[i][j0 + c];
+          for (int t = 0; t < c; ++t) v -= a[i][j0 + t] * a[j0 + c][j0 + t];
+          a[i][j0 + c] = v / a[j0 + c][j0 + c];
+        }
+      }
+      __syncthreads();
+      // (c) trailing update of the lower triangle
+      const int nr = n - rest0;
+      for (int e = tid; e < nr * nr; e += 256) {
+        const int i = rest0 + e / nr, k = rest0 + e % nr;
+        if (k <= i) {
+          T v = a[i][k];
+          for (int t = 0; t < jn; ++t) v -= a[i][j0 + t] * a[k][j0 + t];
+          a[i][k] = v;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // ---- inverse, 16-blocked:  diagonal blocks by substitution (thread = column), then block diagonals d = 1, 2, 3 ----
+  if (tid < n) {
+    const int c = tid, b0 = (c / SB) * SB, b1 = min(b0 + SB, n);
+    x[c][c] = T(1) / a[c][c];
+    for (int r = c + 1; r < b1; ++r) {
+      T v = T(0);
+      for (int t = c; t < r; ++t) v -= a[r][t] * x[t][c];
+      x[r][c] = v / a[r][r];
+    }
+  }
+  __syncthreads();
+  const int nblk = (n + SB - 1) / SB;
+  for (int d = 1; d < nblk; ++d) {
+    for (int bi = d; bi < nblk; ++bi) {
+      const int bj = bi - d;
+      // S = sum_{k=bj}^{bi-1} L[bi,k] X[k,bj]   (16 x 16), thread = one entry
+      const int ii = bi * SB + tid / SB, jj = bj * SB + tid % SB;
+      T sacc = T(0);
+      if (ii < n) {
+        for (int t = bj * SB; t < bi * SB; ++t) sacc += a[ii][t] * x[t][jj];
+      }
+      __syncthreads();                 // every thread finished reading x before the block below is written
+      // X[bi,bj] = -X[bi,bi] S : stage S in the (still zero) upper part? no - use registers via shared scratch row
+      sbuf[tid / SB][tid % SB] = sacc;
+      __syncthreads();
+      if (ii < n) {
+        T v = T(0);
+        const int li = tid / SB;
+        for (int t = 0; t <= li; ++t) v -= x[bi * SB + li][bi * SB + t] * sbuf[t][tid % SB];
+        x[ii][jj] = v;
+      }
+      __syncthreads();
+    }
+  }
+  T* Lm = Lall + off;
+  T* X = Xall + off;
+  for (int e = tid; e < n * n; e += 256) {
+    const int i = e / n, j = e % n;
+    Lm[(int64_t)(r0 + i) * M + r0 + j] = j <= i ? a[i][j] : T(0);
+    X[(int64_t)(r0 + i) * M + r0 + j] = j <= i ? x[i][j] : T(0);
+  }
+}
+
+template <typename T>
+static int chol_inv_rec(T* W, T* Lc, T* X, T* tmp, int M, int L, int r0, int n, int* info, cudaStream_t st) {
+  const int64_t sL = (int64_t)M * M;
+  if (n <= NB) {
+    constexpr int smem = (int)(2 * NB * (NB + 1) * sizeof(T));
+    GPZ_CUDA(cudaFuncSetAttribute(chol_inv_leaf_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    chol_inv_leaf_kernel<T><<<L, 256, smem, st>>>(W, Lc, X, M, r0, n, info);
+    GPZ_CHECK_LAUNCH();
+    return GPZ_OK;
+  }
+  const int nb = (int)cdiv(n, NB);
+  const int n1 = (nb / 2) * NB, n2 = n - n1;
+  int rc = chol_inv_rec<T>(W, Lc, X, tmp, M, L, r0, n1, info, st);
+  if (rc) return rc;
+  const int64_t o11 = (int64_t)r0 * M + r0, o21 = (int64_t)(r0 + n1) * M + r0, o22 = (int64_t)(r0 + n1) * M + r0 + n1;
+  // L21 = A21 X11^T
+  rc = gemm<T>(st, false, true, n2, n1, n1, T(1), W + o21, M, sL, X + o11, M, sL, T(0), Lc + o21, M, sL, L, 0, 2, 0);
+  if (rc) return rc;
+  // A22 -= L21 L21^T  (lower)
+  rc = gemm<T>(st, false, true, n2, n2, n1, T(-1), Lc + o21, M, sL, Lc + o21, M, sL, T(1), W + o22, M, sL, L, 0, 0, 1);
+  if (rc) return rc;
+  rc = chol_inv_rec<T>(W, Lc, X, tmp, M, L, r0 + n1, n2, info, st);
+  if (rc) return rc;
+  // tmp = L21 X11 ;  X21 = -X22 tmp
+  rc = gemm<T>(st, false, false, n2, n1, n1, T(1), Lc + o21, M, sL, X + o11, M, sL, T(0), tmp, M, sL, L, 0, 1, 0);
+  if (rc) return rc;
+  return gemm<T>(st, false, false, n2, n1, n2, T(-1), X + o22, M, sL, tmp, M, sL, T(0), X + o21, M, sL, L, 1, 0, 0);
+}
+
+// W: L x M x M copy of the (jittered) Kzz, destroyed; Lc, X: outputs; tmp: L x M x M scratch.
+template <typename T> int chol_inv(T* W, T* Lc, T* X, T* tmp, int M, int L, int* info, cudaStream_t st) {
+  const int64_t sL = (int64_t)M * M;
+  GPZ_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * L, st));
+  GPZ_CUDA(cudaMemsetAsync(Lc, 0, sizeof(T) * sL * L, st));
+  GPZ_CUDA(cudaMemsetAsync(X, 0, sizeof(T) * sL * L, st));
+  return chol_inv_rec<T>(W, Lc, X, tmp, M, L, 0, M, info, st);
+}
+
 // ---- element-wise O(M^2) helpers -------------------------------------------------------------------
 // lower-Cholesky transform (torch transforms.py LowerCholeskyTransform._call; gp.py:220):
 //   out = tril(raw,-1) + diag(exp(diag raw))
@@ -200,21 +353,29 @@ __global__ void tri_op_kernel(const T* __restrict__ in, T* __restrict__ out, int
 //   kl = sum log diag Lc - sum log diag Lu + 0.5 (|T|_F^2 + |q|^2 - M)         (torch kl.py MVN||MVN)
 template <typename T>
 __global__ void __launch_bounds__(256) mvn_kl_fwd_kernel(const T* __restrict__ Tm, const T* __restrict__ q, const T* __restrict__ Lc,
-                                                          const T* __restrict__ Lu, T* __restrict__ kl, int M) {
+                                                          const T* __restrict__ Lu, double* __restrict__ acc_out, int M) {
   __shared__ double red[32];
-  const int l = blockIdx.x;
+  const int l = blockIdx.y;
   const int64_t sL = (int64_t)M * M;
   double acc = 0.0;
-  for (int64_t e = threadIdx.x; e < sL; e += blockDim.x) {
-    const double t = (double)Tm[l * sL + e];
-    acc += 0.5 * t * t;
-  }
-  for (int i = threadIdx.x; i < M; i += blockDim.x) {
-    const double qq = (double)q[(int64_t)l * M + i];
-    acc += 0.5 * qq * qq + ::log((double)Lc[l * sL + (int64_t)i * M + i]) - ::log((double)Lu[l * sL + (int64_t)i * M + i]);
+  // rows are split over blockIdx.x (the full row is read: whitened_KL sums all of Lz like the reference)
+  for (int i = blockIdx.x; i < M; i += gridDim.x) {
+    const T* row = Tm + l * sL + (int64_t)i * M;
+    for (int j = threadIdx.x; j < M; j += blockDim.x) {
+      const double t = (double)row[j];
+      acc += 0.5 * t * t;
+    }
+    if (threadIdx.x == 0) {
+      const double qq = (double)q[(int64_t)l * M + i];
+      acc += 0.5 * qq * qq + ::log((double)Lc[l * sL + (int64_t)i * M + i]) - ::log((double)Lu[l * sL + (int64_t)i * M + i]);
+    }
   }
   acc = block_sum<double>(acc, red);
-  if (threadIdx.x == 0) kl[l] = (T)(acc - 0.5 * M);
+  if (threadIdx.x == 0) atomicAdd(acc_out + l, acc);
+}
+template <typename T> __global__ void mvn_kl_finish_kernel(const double* __restrict__ acc, T* __restrict__ kl, int M, int L) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < L) kl[l] = (T)(acc[l] - 0.5 * M);
 }
 // gT = g*T ; gq = g*q ; gLc = diag(g / Lc_ii) ; gLu = diag(-g / Lu_ii)
 template <typename T>
@@ -246,6 +407,10 @@ using namespace gpz;
     if (M <= 0 || L <= 0) return GPZ_ERR_BADARG;                                                                  \
     return trtri<T>(Lc, X, tmp, M, L, ST(stream));                                                               \
   }                                                                                                               \
+  extern "C" int gpz_chol_inv_##SUF(T* W, T* Lc, T* X, T* tmp, int M, int L, int* info, void* stream) {          \
+    if (M <= 0 || L <= 0) return GPZ_ERR_BADARG;                                                                  \
+    return chol_inv<T>(W, Lc, X, tmp, M, L, info, ST(stream));                                                   \
+  }                                                                                                               \
   extern "C" int gpz_gemm_##SUF(int ta, int tb, int m, int n, int k, T alpha, const T* A, int64_t lda, int64_t sA, \
                                 const T* B, int64_t ldb, int64_t sB, T beta, T* D, int64_t ldd, int64_t sD,      \
                                 int batch, int a_tri, int b_tri, int d_tri, int splitk, void* stream) {           \
@@ -271,9 +436,12 @@ using namespace gpz;
     GPZ_CHECK_LAUNCH();                                                                                           \
     return GPZ_OK;                                                                                                \
   }                                                                                                               \
-  extern "C" int gpz_mvn_kl_fwd_##SUF(const T* Tm, const T* q, const T* Lc, const T* Lu, T* kl, int M, int L,    \
-                                      void* stream) {                                                             \
-    mvn_kl_fwd_kernel<T><<<L, 256, 0, ST(stream)>>>(Tm, q, Lc, Lu, kl, M);                                       \
+  extern "C" int gpz_mvn_kl_fwd_##SUF(const T* Tm, const T* q, const T* Lc, const T* Lu, T* kl, double* ws, int M, \
+                                      int L, void* stream) {                                                      \
+    GPZ_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * L, ST(stream)));                                             \
+    mvn_kl_fwd_kernel<T><<<dim3((unsigned)min(M, 64), L), 256, 0, ST(stream)>>>(Tm, q, Lc, Lu, ws, M);           \
+    GPZ_CHECK_LAUNCH();                                                                                           \
+    mvn_kl_finish_kernel<T><<<(unsigned)cdiv(L, 128), 128, 0, ST(stream)>>>(ws, kl, M, L);                       \
     GPZ_CHECK_LAUNCH();                                                                                           \
     return GPZ_OK;                                                                                                \
   }                                                                                                               \

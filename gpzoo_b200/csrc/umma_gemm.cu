@@ -18,6 +18,8 @@
 // Triangular operands skip whole k-blocks; lower-triangular outputs skip whole tiles.
 #include <cuda.h>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "gpzoo_b200.h"
 
@@ -30,7 +32,7 @@ constexpr int B_BYTES = BN * BK * 4;          // 16 KB  (MN-major: 8 chunks x 16
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // raw + lo of both operands = 48 KB
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int NTHREADS = 192;
-constexpr uint32_t TMEM_COLS = 256;
+constexpr uint32_t TMEM_COLS = 512;      // two 128 x 256 fp32 accumulators
 
 struct Params {
   float* D; float* Dlo; const float* Cin;
@@ -105,23 +107,30 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
          ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t)layout << 61);
 }
 
-template <bool B_KMAJOR>
-__global__ void __launch_bounds__(NTHREADS, 1)
-umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
-                 const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo, const Params p) {
-  extern __shared__ unsigned char smem_raw[];
-  __shared__ uint32_t tmem_base_slot;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+struct TileInfo {
+  int b, i0, j0, kb0, nkb;     // batch entry, tile origin, first k-block, number of k-blocks (0 = nothing to do)
+};
 
-  const int mt = blockIdx.x, nt = blockIdx.y;
-  const int z = blockIdx.z, split = z % p.splitk, b = z / p.splitk;
-  const int i0 = mt * BM, j0 = nt * BN;
-  const int i1 = min(i0 + BM, p.m), j1 = min(j0 + BN, p.n);
-  if ((p.d_tri == 1 && j0 >= i1) || (p.d_tri == 2 && i0 >= j1)) return;
+// tile index -> coordinates.  mt (row tile) is the fastest index so that consecutively scheduled tiles share the same
+// B column block (L2 reuse); the dynamic scheduler balances the unequal k-ranges of triangular operands.
+__device__ __forceinline__ TileInfo tile_info(const Params& p, int t, int mtiles, int ntiles) {
+  TileInfo ti;
+  const int mt = t % mtiles;
+  int r = t / mtiles;
+  const int nt = r % ntiles;
+  r /= ntiles;
+  const int split = r % p.splitk;
+  ti.b = r / p.splitk;
+  ti.i0 = mt * BM;
+  ti.j0 = nt * BN;
+  const int i1 = min(ti.i0 + BM, p.m), j1 = min(ti.j0 + BN, p.n);
+  ti.kb0 = 0;
+  ti.nkb = 0;
+  if ((p.d_tri == 1 && ti.j0 >= i1) || (p.d_tri == 2 && ti.i0 >= j1)) return ti;
   int k_lo = 0, k_hi = p.k;
   if (p.a_tri == 1) k_hi = min(k_hi, i1);
-  if (p.a_tri == 2) k_lo = max(k_lo, i0);
-  if (p.b_tri == 1) k_lo = max(k_lo, j0);
+  if (p.a_tri == 2) k_lo = max(k_lo, ti.i0);
+  if (p.b_tri == 1) k_lo = max(k_lo, ti.j0);
   if (p.b_tri == 2) k_hi = min(k_hi, j1);
   const int kb0 = k_lo / BK;
   const int nkb_all = k_hi > kb0 * BK ? (k_hi - kb0 * BK + BK - 1) / BK : 0;
@@ -131,17 +140,43 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     kb_begin = split * chunk;
     kb_end = min(nkb_all, kb_begin + chunk);
   }
-  const int nkb = kb_end - kb_begin;
-  if (nkb <= 0) return;                                   // uniform for the CTA
+  ti.kb0 = kb0 + kb_begin;
+  ti.nkb = max(0, kb_end - kb_begin);
+  return ti;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent kernel: one CTA per SM, tiles handed out by an atomic counter.  The 512 TMEM columns hold two 128 x 256 fp32
+// accumulators, so the epilogue of tile i overlaps the MMAs of tile i+1.
+template <bool B_KMAJOR>
+__global__ void __launch_bounds__(NTHREADS, 1)
+umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
+                 const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo, const Params p,
+                 unsigned int* __restrict__ tile_counter, int total_tiles, int mtiles, int ntiles) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ int sched_tile[2];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* accum_bar = empty_bar + STAGES;
+  uint64_t* accum_full = empty_bar + STAGES;     // [2]
+  uint64_t* accum_empty = accum_full + 2;        // [2]
+  uint64_t* sched_full = accum_empty + 2;        // [2]
+  uint64_t* sched_empty = sched_full + 2;        // [2]
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    mbar_init(accum_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(accum_full + s, 1);
+      mbar_init(accum_empty + s, 4);             // one arrival per epilogue warp
+      mbar_init(sched_full + s, 1);
+      mbar_init(sched_empty + s, 5);             // MMA thread + 4 epilogue warps
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -152,35 +187,44 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_slot;
-
   const uint32_t tx_bytes = p.n_terms == 3 ? (uint32_t)STAGE_BYTES : (uint32_t)(A_BYTES + B_BYTES);
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== scheduler + TMA producer (one thread) =====
     if (lane == 0) {
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        mbar_wait(empty_bar + s, ph ^ 1u);
-        unsigned char* st = smem + s * STAGE_BYTES;
-        mbar_expect_tx(full_bar + s, tx_bytes);
-        const int kc = (kb0 + kb_begin + it) * BK;
-        tma_load_3d(&mapA, full_bar + s, st, kc, i0, b);
-        if (B_KMAJOR) {
-          tma_load_3d(&mapB, full_bar + s, st + 2 * A_BYTES, kc, j0, b);
-        } else {
-#pragma unroll
-          for (int c = 0; c < BN / 32; ++c)        // 32-column chunks: 16 k-rows x 128 B each, 2 KB apart
-            tma_load_3d(&mapB, full_bar + s, st + 2 * A_BYTES + c * 2048, j0 + c * 32, kc, b);
-        }
-        if (p.n_terms == 3) {
-          tma_load_3d(&mapAlo, full_bar + s, st + A_BYTES, kc, i0, b);
+      uint32_t it = 0;                                     // running k-block counter across tiles (stage ring position)
+      for (uint32_t iter = 0;; ++iter) {
+        const int slot = iter & 1;
+        mbar_wait(sched_empty + slot, ((iter >> 1) & 1u) ^ 1u);
+        const int t = (int)atomicAdd(tile_counter, 1u);
+        sched_tile[slot] = t < total_tiles ? t : -1;
+        mbar_arrive(sched_full + slot);                    // release: the tile index is visible to the waiters
+        if (t >= total_tiles) break;
+        const TileInfo ti = tile_info(p, t, mtiles, ntiles);
+        for (int kb = 0; kb < ti.nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(empty_bar + s, ph ^ 1u);
+          unsigned char* st = smem + s * STAGE_BYTES;
+          mbar_expect_tx(full_bar + s, tx_bytes);
+          const int kc = (ti.kb0 + kb) * BK;
+          tma_load_3d(&mapA, full_bar + s, st, kc, ti.i0, ti.b);
           if (B_KMAJOR) {
-            tma_load_3d(&mapBlo, full_bar + s, st + 2 * A_BYTES + B_BYTES, kc, j0, b);
+            tma_load_3d(&mapB, full_bar + s, st + 2 * A_BYTES, kc, ti.j0, ti.b);
           } else {
 #pragma unroll
-            for (int c = 0; c < BN / 32; ++c)
-              tma_load_3d(&mapBlo, full_bar + s, st + 2 * A_BYTES + B_BYTES + c * 2048, j0 + c * 32, kc, b);
+            for (int c = 0; c < BN / 32; ++c)        // 32-column chunks: 16 k-rows x 128 B each, 2 KB apart
+              tma_load_3d(&mapB, full_bar + s, st + 2 * A_BYTES + c * 2048, ti.j0 + c * 32, kc, ti.b);
+          }
+          if (p.n_terms == 3) {
+            tma_load_3d(&mapAlo, full_bar + s, st + A_BYTES, kc, ti.i0, ti.b);
+            if (B_KMAJOR) {
+              tma_load_3d(&mapBlo, full_bar + s, st + 2 * A_BYTES + B_BYTES, kc, ti.j0, ti.b);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BN / 32; ++c)
+                tma_load_3d(&mapBlo, full_bar + s, st + 2 * A_BYTES + B_BYTES + c * 2048, ti.j0 + c * 32, kc, ti.b);
+            }
           }
         }
       }
@@ -192,98 +236,130 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       // a_major [15]=0 (K), b_major [16], N>>3 [17,23), M>>4 [24,29)
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((B_KMAJOR ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) |
                              ((uint32_t)(BM >> 4) << 24);
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        mbar_wait(full_bar + s, ph);
+      uint32_t it = 0, acc_iter = 0;
+      for (uint32_t iter = 0;; ++iter) {
+        const int slot = iter & 1;
+        mbar_wait(sched_full + slot, (iter >> 1) & 1u);
+        const int t = sched_tile[slot];
+        mbar_arrive(sched_empty + slot);
+        if (t < 0) break;
+        const TileInfo ti = tile_info(p, t, mtiles, ntiles);
+        if (ti.nkb == 0) continue;
+        const uint32_t as = acc_iter & 1u;
+        mbar_wait(accum_empty + as, ((acc_iter >> 1) & 1u) ^ 1u);       // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t sb = sa + 2 * A_BYTES;
+        const uint32_t tmem_d = tmem_base + as * (uint32_t)BN;
+        for (int kb = 0; kb < ti.nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1u;
+          mbar_wait(full_bar + s, ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t sb = sa + 2 * A_BYTES;
 #pragma unroll
-        for (int ks = 0; ks < BK / 8; ++ks) {
-          // K-major SW64: rows of 64 B, 8-row groups 512 B apart; one K=8 step = 32 B inside the row
-          const uint64_t a_raw = make_desc(sa + ks * 32, 16, 512, 4);
-          const uint64_t a_lo = make_desc(sa + A_BYTES + ks * 32, 16, 512, 4);
-          uint64_t b_raw, b_lo;
-          if (B_KMAJOR) {
-            b_raw = make_desc(sb + ks * 32, 16, 512, 4);
-            b_lo = make_desc(sb + B_BYTES + ks * 32, 16, 512, 4);
-          } else {
-            // MN-major tf32 must use SWIZZLE_128B_BASE32B (layout type 1; 32 B chunks swizzled inside a 4-row x 128 B
-            // atom): chunks of 32 columns (128 B rows) 2 KB apart (= LBO), 4-row k groups 512 B apart (= SBO);
-            // one K=8 step = two k groups = 1 KB
-            b_raw = make_desc(sb + ks * 1024, 2048, 512, 1);
-            b_lo = make_desc(sb + B_BYTES + ks * 1024, 2048, 512, 1);
+          for (int ks = 0; ks < BK / 8; ++ks) {
+            // K-major SW64: rows of 64 B, 8-row groups 512 B apart; one K=8 step = 32 B inside the row
+            const uint64_t a_raw = make_desc(sa + ks * 32, 16, 512, 4);
+            const uint64_t a_lo = make_desc(sa + A_BYTES + ks * 32, 16, 512, 4);
+            uint64_t b_raw, b_lo;
+            if (B_KMAJOR) {
+              b_raw = make_desc(sb + ks * 32, 16, 512, 4);
+              b_lo = make_desc(sb + B_BYTES + ks * 32, 16, 512, 4);
+            } else {
+              // MN-major tf32 must use SWIZZLE_128B_BASE32B (layout type 1; 32 B chunks swizzled inside a 4-row x 128 B
+              // atom): chunks of 32 columns (128 B rows) 2 KB apart (= LBO), 4-row k groups 512 B apart (= SBO);
+              // one K=8 step = two k groups = 1 KB
+              b_raw = make_desc(sb + ks * 1024, 2048, 512, 1);
+              b_lo = make_desc(sb + B_BYTES + ks * 1024, 2048, 512, 1);
+            }
+            const uint32_t acc0 = (kb > 0 || ks > 0) ? 1u : 0u;
+            if (p.n_terms == 3) {
+              umma_tf32(tmem_d, a_raw, b_lo, idesc, acc0);
+              umma_tf32(tmem_d, a_lo, b_raw, idesc, 1u);
+              umma_tf32(tmem_d, a_raw, b_raw, idesc, 1u);
+            } else {
+              umma_tf32(tmem_d, a_raw, b_raw, idesc, acc0);
+            }
           }
-          const uint32_t acc0 = (it > 0 || ks > 0) ? 1u : 0u;
-          if (p.n_terms == 3) {
-            umma_tf32(tmem_base, a_raw, b_lo, idesc, acc0);
-            umma_tf32(tmem_base, a_lo, b_raw, idesc, 1u);
-            umma_tf32(tmem_base, a_raw, b_raw, idesc, 1u);
-          } else {
-            umma_tf32(tmem_base, a_raw, b_raw, idesc, acc0);
-          }
+          umma_commit(empty_bar + s);               // frees the smem stage once these MMAs have read it
         }
-        umma_commit(empty_bar + s);                 // frees the smem stage once these MMAs have read it
+        umma_commit(accum_full + as);               // accumulator complete
+        ++acc_iter;
       }
-      umma_commit(accum_bar);                       // accumulator complete
     }
   } else {
     // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
     const int q = warp & 3;
-    mbar_wait(accum_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int gi = i0 + q * 32 + lane;
-    float* Drow = p.D + (int64_t)b * p.sD + (int64_t)gi * p.ldd;
-    float* Lrow = p.Dlo ? p.Dlo + (int64_t)b * p.sD + (int64_t)gi * p.ldd : nullptr;
-    const float* Crow = p.Cin ? p.Cin + (int64_t)b * p.sD + (int64_t)gi * p.ldd : nullptr;
     const bool vec_ok = (p.ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) &&
                         (!p.Dlo || (reinterpret_cast<uintptr_t>(p.Dlo) & 15) == 0) &&
                         (!p.Cin || (reinterpret_cast<uintptr_t>(p.Cin) & 15) == 0) && ((p.sD % 4) == 0);
+    uint32_t acc_iter = 0;
+    for (uint32_t iter = 0;; ++iter) {
+      const int slot = iter & 1;
+      mbar_wait(sched_full + slot, (iter >> 1) & 1u);
+      const int t = sched_tile[slot];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sched_empty + slot);
+      if (t < 0) break;
+      const TileInfo ti = tile_info(p, t, mtiles, ntiles);
+      if (ti.nkb == 0) continue;
+      const uint32_t as = acc_iter & 1u;
+      mbar_wait(accum_full + as, (acc_iter >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int gi = ti.i0 + q * 32 + lane;
+      float* Drow = p.D + (int64_t)ti.b * p.sD + (int64_t)gi * p.ldd;
+      float* Lrow = p.Dlo ? p.Dlo + (int64_t)ti.b * p.sD + (int64_t)gi * p.ldd : nullptr;
+      const float* Crow = p.Cin ? p.Cin + (int64_t)ti.b * p.sD + (int64_t)gi * p.ldd : nullptr;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), r);
-      const int gj0 = j0 + c * 32;
-      if (gi >= p.m || gj0 >= p.n) continue;
-      const bool full = (gj0 + 32 <= p.n) && !((p.d_tri == 1 && gj0 + 31 > gi) || (p.d_tri == 2 && gj0 < gi));
-      if (p.splitk > 1) {
-        for (int t = 0; t < 32; ++t) {
-          const int gj = gj0 + t;
-          if (gj >= p.n) break;
-          if ((p.d_tri == 1 && gj > gi) || (p.d_tri == 2 && gj < gi)) continue;
-          atomicAdd(Drow + gj, p.alpha * __uint_as_float(r[t]));
-        }
-      } else if (full && vec_ok) {
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)BN + (uint32_t)(c * 32), r);
+        const int gj0 = ti.j0 + c * 32;
+        if (gi >= p.m || gj0 >= p.n) continue;
+        const bool full = (gj0 + 32 <= p.n) && !((p.d_tri == 1 && gj0 + 31 > gi) || (p.d_tri == 2 && gj0 < gi));
+        if (p.splitk > 1) {
+          for (int u = 0; u < 32; ++u) {
+            const int gj = gj0 + u;
+            if (gj >= p.n) break;
+            if ((p.d_tri == 1 && gj > gi) || (p.d_tri == 2 && gj < gi)) continue;
+            atomicAdd(Drow + gj, p.alpha * __uint_as_float(r[u]));
+          }
+        } else if (full && vec_ok) {
 #pragma unroll
-        for (int t = 0; t < 32; t += 4) {
-          float4 v = make_float4(p.alpha * __uint_as_float(r[t]), p.alpha * __uint_as_float(r[t + 1]),
-                                 p.alpha * __uint_as_float(r[t + 2]), p.alpha * __uint_as_float(r[t + 3]));
-          if (Crow) {
-            const float4 cc = *reinterpret_cast<const float4*>(Crow + gj0 + t);
-            v.x += cc.x; v.y += cc.y; v.z += cc.z; v.w += cc.w;
+          for (int u = 0; u < 32; u += 4) {
+            float4 v = make_float4(p.alpha * __uint_as_float(r[u]), p.alpha * __uint_as_float(r[u + 1]),
+                                   p.alpha * __uint_as_float(r[u + 2]), p.alpha * __uint_as_float(r[u + 3]));
+            if (Crow) {
+              const float4 cc = *reinterpret_cast<const float4*>(Crow + gj0 + u);
+              v.x += cc.x; v.y += cc.y; v.z += cc.z; v.w += cc.w;
+            }
+            *reinterpret_cast<float4*>(Drow + gj0 + u) = v;
+            if (Lrow) {
+              float4 lo;
+              lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+              lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+              lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+              lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+              *reinterpret_cast<float4*>(Lrow + gj0 + u) = lo;
+            }
           }
-          *reinterpret_cast<float4*>(Drow + gj0 + t) = v;
-          if (Lrow) {
-            float4 lo;
-            lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-            lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-            lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-            lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-            *reinterpret_cast<float4*>(Lrow + gj0 + t) = lo;
+        } else {
+          for (int u = 0; u < 32; ++u) {
+            const int gj = gj0 + u;
+            if (gj >= p.n) break;
+            if ((p.d_tri == 1 && gj > gi) || (p.d_tri == 2 && gj < gi)) continue;
+            float v = p.alpha * __uint_as_float(r[u]);
+            if (Crow) v += Crow[gj];
+            Drow[gj] = v;
+            if (Lrow) Lrow[gj] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
           }
-        }
-      } else {
-        for (int t = 0; t < 32; ++t) {
-          const int gj = gj0 + t;
-          if (gj >= p.n) break;
-          if ((p.d_tri == 1 && gj > gi) || (p.d_tri == 2 && gj < gi)) continue;
-          float v = p.alpha * __uint_as_float(r[t]);
-          if (Crow) v += Crow[gj];
-          Drow[gj] = v;
-          if (Lrow) Lrow[gj] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
         }
       }
+      // this warp is done reading the accumulator stage: hand it back to the MMA thread
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(accum_empty + as);
+      ++acc_iter;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -340,6 +416,9 @@ static int make_map_mnmajor(CUtensorMap* map, const float* base, int k, int n, i
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+constexpr int NUM_COUNTERS = 256;
+__device__ unsigned int g_tile_counters[NUM_COUNTERS];
+
 }  // namespace umma
 }  // namespace gpz
 
@@ -383,15 +462,32 @@ extern "C" int gpz_umma_gemm_f32(int b_kmajor, int m, int n, int k, float alpha,
   Params p;
   p.D = D; p.Dlo = Dlo; p.Cin = Cin; p.m = m; p.n = n; p.k = k; p.ldd = ldd; p.sD = sD; p.batch = batch; p.splitk = splitk;
   p.a_tri = a_tri; p.b_tri = b_tri; p.d_tri = d_tri; p.n_terms = n_terms; p.alpha = alpha;
-  dim3 grid((unsigned)cdiv(m, BM), (unsigned)cdiv(n, BN), (unsigned)(batch * splitk));
-  if (grid.y > 65535u || grid.z > 65535u) return GPZ_ERR_UNSUPPORTED;
+  const int mtiles = (int)cdiv(m, BM), ntiles = (int)cdiv(n, BN);
+  const int64_t total64 = (int64_t)mtiles * ntiles * batch * splitk;
+  if (total64 > 0x7fffffff) return GPZ_ERR_UNSUPPORTED;
+  const int total = (int)total64;
   cudaStream_t st = (cudaStream_t)stream;
+  // dynamic tile scheduler: one counter per in-flight launch, taken round-robin from a small device array
+  static unsigned int* counters = nullptr;
+  static std::atomic<unsigned int> next_slot{0};
+  static int num_sms = 0;
+  if (!counters) {
+    unsigned int* ptr = nullptr;
+    GPZ_CUDA(cudaGetSymbolAddress((void**)&ptr, g_tile_counters));
+    counters = ptr;
+    int dev = 0;
+    GPZ_CUDA(cudaGetDevice(&dev));
+    GPZ_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  unsigned int* counter = counters + (next_slot.fetch_add(1) % NUM_COUNTERS);
+  GPZ_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+  const int grid = total < num_sms ? total : num_sms;
   if (b_kmajor) {
     GPZ_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    umma_gemm_kernel<true><<<grid, NTHREADS, SMEM_BYTES, st>>>(mA, mAlo, mB, mBlo, p);
+    umma_gemm_kernel<true><<<grid, NTHREADS, SMEM_BYTES, st>>>(mA, mAlo, mB, mBlo, p, counter, total, mtiles, ntiles);
   } else {
     GPZ_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    umma_gemm_kernel<false><<<grid, NTHREADS, SMEM_BYTES, st>>>(mA, mAlo, mB, mBlo, p);
+    umma_gemm_kernel<false><<<grid, NTHREADS, SMEM_BYTES, st>>>(mA, mAlo, mB, mBlo, p, counter, total, mtiles, ntiles);
   }
   GPZ_CHECK_LAUNCH();
   return GPZ_OK;

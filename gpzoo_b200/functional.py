@@ -142,17 +142,13 @@ class CholeskyInverse(Function):
     def forward(ctx, Kzz):
         dt = Kzz.dtype
         L, M, _ = Kzz.shape
-        Lc = Kzz.detach().clone(memory_format=torch.contiguous_format)
+        W = Kzz.detach().clone(memory_format=torch.contiguous_format)
         info = torch.empty(L, dtype=torch.int32, device=Kzz.device)
-        call("potrf", dt, ptr(Lc), c_i(M), c_i(L), ptr(info))
+        Lc, Linv, tmp = torch.empty_like(W), torch.empty_like(W), torch.empty_like(W)
+        call("chol_inv", dt, ptr(W), ptr(Lc), ptr(Linv), ptr(tmp), c_i(M), c_i(L), ptr(info))
+        _pending_info.append(info)
         if SYNC_CHECKS:
-            _pending_info.append(info)
             check_cholesky_info()
-        else:
-            _pending_info.append(info)
-        Linv = torch.empty_like(Lc)
-        tmp = torch.empty((L, 64, M), dtype=dt, device=Kzz.device)
-        call("trtri", dt, ptr(Lc), ptr(Linv), ptr(tmp), c_i(M), c_i(L))
         ctx.save_for_backward(Lc, Linv)
         return Lc, Linv
 
@@ -390,7 +386,8 @@ class MvnKL(Function):
         T, q, Lc, Lu = _c(T), _c(q), _c(Lc), _c(Lu)
         L, M, _ = T.shape
         kl = torch.empty(L, dtype=T.dtype, device=T.device)
-        call("mvn_kl_fwd", T.dtype, ptr(T), ptr(q), ptr(Lc), ptr(Lu), ptr(kl), c_i(M), c_i(L))
+        ws = torch.empty(L, dtype=torch.float64, device=T.device)
+        call("mvn_kl_fwd", T.dtype, ptr(T), ptr(q), ptr(Lc), ptr(Lu), ptr(kl), ptr(ws), c_i(M), c_i(L))
         ctx.save_for_backward(T, q, Lc, Lu)
         return kl
 

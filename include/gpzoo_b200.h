@@ -62,6 +62,10 @@ int gpz_potrf_f64(double* A, int M, int L, int* info, void* stream);
  * inside kl_divergence(qU,pU) (torch kl.py) become triangular products.  tmp: L x 64 x M scratch. */
 int gpz_trtri_f32(const float* Lc, float* X, float* tmp, int M, int L, void* stream);
 int gpz_trtri_f64(const double* Lc, double* X, double* tmp, int M, int L, void* stream);
+/* fused recursive Cholesky + inverse (the path the GP modules use): W = copy of Kzz (destroyed), outputs Lc and X = Lc^-1
+ * (both lower, upper triangle zero), tmp = L x M x M scratch, info as gpz_potrf.  All O(M^3) work is GEMMs. */
+int gpz_chol_inv_f32(float* W, float* Lc, float* X, float* tmp, int M, int L, int* info, void* stream);
+int gpz_chol_inv_f64(double* W, double* Lc, double* X, double* tmp, int M, int L, int* info, void* stream);
 /* strided-batched D = alpha op(A) op(B) + beta D with triangular-structure skipping (see csrc/gemm_simt.cuh):
  * S = Lu Lu^T (gp.py:221), W@(S-Kzz) (utilities.py:395) and the O(M^3) backward products are built from it. */
 int gpz_gemm_f32(int ta, int tb, int m, int n, int k, float alpha, const float* A, int64_t lda, int64_t sA, const float* B,
@@ -106,10 +110,12 @@ int gpz_svgp_predict_bwd_tc_f32(const float* Kzx, const float* Kzx_lo, const flo
                                 float* gA_lo, float* gKzx, float* gLinv, float* gT, float* gq, float* ws, int M, int N, int L,
                                 void* stream);
 
-/* ---- K5 KL(qU || pU): utilities.py:481,616 -> torch kl.py MVN||MVN, from the whitened T, q */
-int gpz_mvn_kl_fwd_f32(const float* T, const float* q, const float* Lc, const float* Lu, float* kl, int M, int L, void* stream);
-int gpz_mvn_kl_fwd_f64(const double* T, const double* q, const double* Lc, const double* Lu, double* kl, int M, int L,
+/* ---- K5 KL(qU || pU): utilities.py:481,616 -> torch kl.py MVN||MVN, from the whitened T, q (T lower triangular);
+ *      ws: L doubles of scratch */
+int gpz_mvn_kl_fwd_f32(const float* T, const float* q, const float* Lc, const float* Lu, float* kl, double* ws, int M, int L,
                        void* stream);
+int gpz_mvn_kl_fwd_f64(const double* T, const double* q, const double* Lc, const double* Lu, double* kl, double* ws, int M,
+                       int L, void* stream);
 int gpz_mvn_kl_bwd_f32(const float* g, const float* T, const float* q, const float* Lc, const float* Lu, float* gT, float* gq,
                        float* gLc, float* gLu, int M, int L, void* stream);
 int gpz_mvn_kl_bwd_f64(const double* g, const double* T, const double* q, const double* Lc, const double* Lu, double* gT,

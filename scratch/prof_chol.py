@@ -1,0 +1,11 @@
+import sys, torch
+sys.path.insert(0, '.')
+from gpzoo_b200 import functional as F
+F.set_sync_checks(False)
+torch.manual_seed(0)
+L, M = 10, 1024
+Q = torch.randn(L, M, M, device='cuda')
+K = Q @ Q.transpose(1, 2) / M + torch.eye(M, device='cuda')
+for _ in range(3):
+    Lc, Linv = F.CholeskyInverse.apply(K)
+torch.cuda.synchronize()
