@@ -189,45 +189,59 @@ __global__ void __launch_bounds__(256) chol_inv_leaf_kernel(const T* __restrict_
   // ---- Cholesky ----
   for (int j0 = 0; j0 < n; j0 += SB) {
     const int jn = min(SB, n - j0);
-    if (warp == 0) {                                   // (a) diagonal 16 x 16 block, lane = row
-      const int row = j0 + lane;
-      for (int j = j0; j < j0 + jn; ++j) {
-        const T d = a[j][j];
-        if (!(d > T(0)) && lane == 0 && info[blockIdx.x] == 0) info[blockIdx.x] = r0 + j + 1;
-        const T sd = Num<T>::sqrt(d);
-        __syncwarp();
-        if (lane < jn && row > j) {
-          const T v = a[row][j] / sd;
-          a[row][j] = v;
+    if (warp == 0) {
+      // (a) diagonal 16 x 16 block in registers: lane r holds row r, columns are exchanged with shuffles
+      T row[SB];
+#pragma unroll
+      for (int k = 0; k < SB; ++k) row[k] = (lane < jn && k <= lane) ? a[j0 + lane][j0 + k] : T(0);
+#pragma unroll
+      for (int j = 0; j < SB; ++j) {
+        const T d = __shfl_sync(0xffffffffu, row[j], j);
+        if (j < jn) {
+          if (!(d > T(0)) && lane == 0 && info[blockIdx.x] == 0) info[blockIdx.x] = r0 + j0 + j + 1;
+          const T sd = Num<T>::sqrt(d);
+          if (lane == j) row[j] = sd;
+          else if (lane > j) row[j] = row[j] / sd;
         }
-        if (lane == 0) a[j][j] = sd;
-        __syncwarp();
-        if (lane < jn && row > j) {
-          const T v = a[row][j];
-          for (int k = j + 1; k <= row; ++k) a[row][k] -= v * a[k][j];
+        const T mine = row[j];
+#pragma unroll
+        for (int k = j + 1; k < SB; ++k) {
+          const T other = __shfl_sync(0xffffffffu, mine, k);       // a[k][j] lives in lane k
+          if (j < jn && lane >= k) row[k] -= mine * other;
         }
-        __syncwarp();
+      }
+      if (lane < jn) {
+#pragma unroll
+        for (int k = 0; k < SB; ++k) if (k <= lane) a[j0 + lane][j0 + k] = row[k];
       }
     }
     __syncthreads();
     const int rest0 = j0 + jn;
     if (rest0 < n) {
-      // (b) panel rows below: one thread per row
+      // (b) panel rows below: one thread per row, the 16-wide row segment lives in registers
       if (tid < n - rest0) {
         const int i = rest0 + tid;
-        for (int c = 0; c < jn; ++c) {
-          T v = a[i][j0 + c];
-          for (int t = 0; t < c; ++t) v -= a[i][j0 + t] * a[j0 + c][j0 + t];
-          a[i][j0 + c] = v / a[j0 + c][j0 + c];
+        T seg[SB];
+#pragma unroll
+        for (int c = 0; c < SB; ++c) seg[c] = c < jn ? a[i][j0 + c] : T(0);
+#pragma unroll
+        for (int c = 0; c < SB; ++c) {
+          if (c < jn) {
+            T v = seg[c];
+#pragma unroll
+            for (int t = 0; t < c; ++t) v -= seg[t] * a[j0 + c][j0 + t];
+            seg[c] = v / a[j0 + c][j0 + c];
+          }
         }
+#pragma unroll
+        for (int c = 0; c < SB; ++c) if (c < jn) a[i][j0 + c] = seg[c];
       }
       __syncthreads();
       // (c) trailing update of the lower triangle
-      const int nr = n - rest0;
-      for (int e = tid; e < nr * nr; e += 256) {
-        const int i = rest0 + e / nr, k = rest0 + e % nr;
-        if (k <= i) {
+      for (int i = rest0 + (tid >> 4); i < n; i += 16) {
+        for (int k = rest0 + (tid & 15); k <= i; k += 16) {
           T v = a[i][k];
+#pragma unroll 4
           for (int t = 0; t < jn; ++t) v -= a[i][j0 + t] * a[k][j0 + t];
           a[i][k] = v;
         }
@@ -235,14 +249,23 @@ __global__ void __launch_bounds__(256) chol_inv_leaf_kernel(const T* __restrict_
       __syncthreads();
     }
   }
-  // ---- inverse, 16-blocked:  diagonal blocks by substitution (thread = column), then block diagonals d = 1, 2, 3 ----
+  // ---- inverse, 16-blocked:  diagonal blocks by substitution (thread = column, column kept in registers), then the
+  //      block diagonals d = 1, 2, 3 ----
   if (tid < n) {
     const int c = tid, b0 = (c / SB) * SB, b1 = min(b0 + SB, n);
-    x[c][c] = T(1) / a[c][c];
-    for (int r = c + 1; r < b1; ++r) {
-      T v = T(0);
-      for (int t = c; t < r; ++t) v -= a[r][t] * x[t][c];
-      x[r][c] = v / a[r][r];
+    T xc[SB];
+#pragma unroll
+    for (int u = 0; u < SB; ++u) xc[u] = T(0);
+#pragma unroll
+    for (int u = 0; u < SB; ++u) {
+      const int r = b0 + u;
+      if (r < b1 && r >= c) {
+        T v = (r == c) ? T(1) : T(0);
+#pragma unroll
+        for (int w = 0; w < u; ++w) v -= a[r][b0 + w] * xc[w];       // xc[w] = 0 for rows above c
+        xc[u] = v / a[r][r];
+        x[r][c] = xc[u];
+      }
     }
   }
   __syncthreads();
@@ -271,10 +294,12 @@ __global__ void __launch_bounds__(256) chol_inv_leaf_kernel(const T* __restrict_
   }
   T* Lm = Lall + off;
   T* X = Xall + off;
-  for (int e = tid; e < n * n; e += 256) {
-    const int i = e / n, j = e % n;
-    Lm[(int64_t)(r0 + i) * M + r0 + j] = j <= i ? a[i][j] : T(0);
-    X[(int64_t)(r0 + i) * M + r0 + j] = j <= i ? x[i][j] : T(0);
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int i = e / NB, j = e % NB;
+    if (i < n && j < n) {
+      Lm[(int64_t)(r0 + i) * M + r0 + j] = j <= i ? a[i][j] : T(0);
+      X[(int64_t)(r0 + i) * M + r0 + j] = j <= i ? x[i][j] : T(0);
+    }
   }
 }
 

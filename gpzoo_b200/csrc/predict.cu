@@ -68,16 +68,24 @@ __global__ void __launch_bounds__(256) predict_bwd_prep_kernel(const T* __restri
   }
 }
 
-// out[l,m] = sum_n A[l,m,n] v[l,n]      (gq = A gm)
+// out[l,m] = sum_n A[l,m,n] v[l,n]      (gq = A gm); one CTA per row, 4 independent accumulators per thread
 template <typename T>
 __global__ void __launch_bounds__(256) rowdot_kernel(const T* __restrict__ A, const T* __restrict__ v, T* __restrict__ out, int M, int N) {
   __shared__ T red[32];
   const int m = blockIdx.x, l = blockIdx.y;
   const T* a = A + ((int64_t)l * M + m) * N;
   const T* vv = v + (int64_t)l * N;
-  T acc = T(0);
-  for (int n = threadIdx.x; n < N; n += blockDim.x) acc = fma(a[n], vv[n], acc);
-  acc = block_sum<T>(acc, red);
+  T acc0 = T(0), acc1 = T(0), acc2 = T(0), acc3 = T(0);
+  int n = threadIdx.x;
+  for (; n + 3 * 256 < N; n += 4 * 256) {
+    const T a0 = a[n], a1 = a[n + 256], a2 = a[n + 512], a3 = a[n + 768];
+    acc0 = fma(a0, vv[n], acc0);
+    acc1 = fma(a1, vv[n + 256], acc1);
+    acc2 = fma(a2, vv[n + 512], acc2);
+    acc3 = fma(a3, vv[n + 768], acc3);
+  }
+  for (; n < N; n += 256) acc0 = fma(a[n], vv[n], acc0);
+  T acc = block_sum<T>((acc0 + acc1) + (acc2 + acc3), red);
   if (threadIdx.x == 0) out[(int64_t)l * M + m] = acc;
 }
 

@@ -19,6 +19,7 @@
 #include <cuda.h>
 
 #include <atomic>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "gpzoo_b200.h"
@@ -30,7 +31,9 @@ constexpr int BM = 128, BN = 256, BK = 16, STAGES = 4;
 constexpr int A_BYTES = BM * BK * 4;          // 8 KB   (128 rows x 64 B, SWIZZLE_64B)
 constexpr int B_BYTES = BN * BK * 4;          // 16 KB  (MN-major: 8 chunks x 16 rows x 128 B; K-major: 256 rows x 64 B)
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // raw + lo of both operands = 48 KB
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EPI_LD = 36;                    // padded row length (floats) of the per-warp 32 x 32 epilogue staging tile
+constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;  // 4 epilogue warps
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
 constexpr int NTHREADS = 192;
 constexpr uint32_t TMEM_COLS = 512;      // two 128 x 256 fp32 accumulators
 
@@ -41,6 +44,7 @@ struct Params {
   int batch, splitk;
   int a_tri, b_tri, d_tri;
   int n_terms;            // 3: split-TF32, 1: plain TF32
+  int b_map4d;            // MN-major B loaded with one 4-D box per stage (needs n % 32 == 0)
   float alpha;
 };
 
@@ -72,6 +76,13 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* ba
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
           smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -108,7 +119,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 
 struct TileInfo {
-  int b, i0, j0, kb0, nkb;     // batch entry, tile origin, first k-block, number of k-blocks (0 = nothing to do)
+  int b, i0, j0, kb0, nkb;     // batch entry, tile origin, first k-block, number of k-blocks (0 = no MMA work)
+  int zero;                    // nkb == 0 but the tile is part of the output: the epilogue writes alpha*0 (+Cin)
 };
 
 // tile index -> coordinates.  mt (row tile) is the fastest index so that consecutively scheduled tiles share the same
@@ -126,6 +138,7 @@ __device__ __forceinline__ TileInfo tile_info(const Params& p, int t, int mtiles
   const int i1 = min(ti.i0 + BM, p.m), j1 = min(ti.j0 + BN, p.n);
   ti.kb0 = 0;
   ti.nkb = 0;
+  ti.zero = 0;
   if ((p.d_tri == 1 && ti.j0 >= i1) || (p.d_tri == 2 && ti.i0 >= j1)) return ti;
   int k_lo = 0, k_hi = p.k;
   if (p.a_tri == 1) k_hi = min(k_hi, i1);
@@ -142,6 +155,7 @@ __device__ __forceinline__ TileInfo tile_info(const Params& p, int t, int mtiles
   }
   ti.kb0 = kb0 + kb_begin;
   ti.nkb = max(0, kb_end - kb_begin);
+  ti.zero = (ti.nkb == 0 && p.splitk == 1) ? 1 : 0;      // empty k-range of triangular operands: the product is 0
   return ti;
 }
 
@@ -211,6 +225,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           tma_load_3d(&mapA, full_bar + s, st, kc, ti.i0, ti.b);
           if (B_KMAJOR) {
             tma_load_3d(&mapB, full_bar + s, st + 2 * A_BYTES, kc, ti.j0, ti.b);
+          } else if (p.b_map4d) {                  // one box {32 cols, 16 k-rows, 8 column chunks}: chunk-major in smem
+            tma_load_4d(&mapB, full_bar + s, st + 2 * A_BYTES, 0, kc, ti.j0 / 32, ti.b);
           } else {
 #pragma unroll
             for (int c = 0; c < BN / 32; ++c)        // 32-column chunks: 16 k-rows x 128 B each, 2 KB apart
@@ -220,6 +236,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             tma_load_3d(&mapAlo, full_bar + s, st + A_BYTES, kc, ti.i0, ti.b);
             if (B_KMAJOR) {
               tma_load_3d(&mapBlo, full_bar + s, st + 2 * A_BYTES + B_BYTES, kc, ti.j0, ti.b);
+            } else if (p.b_map4d) {
+              tma_load_4d(&mapBlo, full_bar + s, st + 2 * A_BYTES + B_BYTES, 0, kc, ti.j0 / 32, ti.b);
             } else {
 #pragma unroll
               for (int c = 0; c < BN / 32; ++c)
@@ -293,6 +311,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const bool vec_ok = (p.ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) &&
                         (!p.Dlo || (reinterpret_cast<uintptr_t>(p.Dlo) & 15) == 0) &&
                         (!p.Cin || (reinterpret_cast<uintptr_t>(p.Cin) & 15) == 0) && ((p.sD % 4) == 0);
+    float* epi = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 2) * 32 * EPI_LD;
     uint32_t acc_iter = 0;
     for (uint32_t iter = 0;; ++iter) {
       const int slot = iter & 1;
@@ -302,10 +321,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       if (lane == 0) mbar_arrive(sched_empty + slot);
       if (t < 0) break;
       const TileInfo ti = tile_info(p, t, mtiles, ntiles);
-      if (ti.nkb == 0) continue;
+      const bool has_acc = ti.nkb > 0;
+      if (!has_acc && !ti.zero) continue;
       const uint32_t as = acc_iter & 1u;
-      mbar_wait(accum_full + as, (acc_iter >> 1) & 1u);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (has_acc) {
+        mbar_wait(accum_full + as, (acc_iter >> 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
       const int gi = ti.i0 + q * 32 + lane;
       float* Drow = p.D + (int64_t)ti.b * p.sD + (int64_t)gi * p.ldd;
       float* Lrow = p.Dlo ? p.Dlo + (int64_t)ti.b * p.sD + (int64_t)gi * p.ldd : nullptr;
@@ -313,10 +335,18 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)BN + (uint32_t)(c * 32), r);
+        if (has_acc) {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)BN + (uint32_t)(c * 32), r);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 32; ++u) r[u] = 0u;
+        }
         const int gj0 = ti.j0 + c * 32;
-        if (gi >= p.m || gj0 >= p.n) continue;
-        const bool full = (gj0 + 32 <= p.n) && !((p.d_tri == 1 && gj0 + 31 > gi) || (p.d_tri == 2 && gj0 < gi));
+        // warp-uniform: the whole 32 x 32 block of this warp lies inside the matrix and inside the stored triangle
+        const int wi0 = ti.i0 + q * 32;
+        const bool warp_full = (wi0 + 32 <= p.m) && (gj0 + 32 <= p.n) &&
+                               !((p.d_tri == 1 && gj0 + 31 > wi0) || (p.d_tri == 2 && gj0 < wi0 + 31));
+        if (!warp_full && (gi >= p.m || gj0 >= p.n)) continue;
         if (p.splitk > 1) {
           for (int u = 0; u < 32; ++u) {
             const int gj = gj0 + u;
@@ -324,25 +354,36 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             if ((p.d_tri == 1 && gj > gi) || (p.d_tri == 2 && gj < gi)) continue;
             atomicAdd(Drow + gj, p.alpha * __uint_as_float(r[u]));
           }
-        } else if (full && vec_ok) {
+        } else if (warp_full && vec_ok) {
+          // transpose the 32 x 32 block through shared memory so that every store instruction writes whole 128-byte
+          // lines: lane -> (row = 4*it + lane/8, 4 columns at (lane%8)*4)
 #pragma unroll
-          for (int u = 0; u < 32; u += 4) {
-            float4 v = make_float4(p.alpha * __uint_as_float(r[u]), p.alpha * __uint_as_float(r[u + 1]),
-                                   p.alpha * __uint_as_float(r[u + 2]), p.alpha * __uint_as_float(r[u + 3]));
-            if (Crow) {
-              const float4 cc = *reinterpret_cast<const float4*>(Crow + gj0 + u);
+          for (int u = 0; u < 32; u += 4)
+            *reinterpret_cast<float4*>(epi + lane * EPI_LD + u) =
+                make_float4(__uint_as_float(r[u]), __uint_as_float(r[u + 1]), __uint_as_float(r[u + 2]), __uint_as_float(r[u + 3]));
+          __syncwarp();
+          const int cq = (lane & 7) * 4;
+#pragma unroll
+          for (int itr = 0; itr < 8; ++itr) {
+            const int rr = itr * 4 + (lane >> 3);
+            float4 v = *reinterpret_cast<const float4*>(epi + rr * EPI_LD + cq);
+            v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha;
+            const int64_t o = (int64_t)ti.b * p.sD + (int64_t)(ti.i0 + q * 32 + rr) * p.ldd + gj0 + cq;
+            if (p.Cin) {
+              const float4 cc = *reinterpret_cast<const float4*>(p.Cin + o);
               v.x += cc.x; v.y += cc.y; v.z += cc.z; v.w += cc.w;
             }
-            *reinterpret_cast<float4*>(Drow + gj0 + u) = v;
-            if (Lrow) {
+            *reinterpret_cast<float4*>(p.D + o) = v;
+            if (p.Dlo) {
               float4 lo;
               lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
               lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
               lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
               lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-              *reinterpret_cast<float4*>(Lrow + gj0 + u) = lo;
+              *reinterpret_cast<float4*>(p.Dlo + o) = lo;
             }
           }
+          __syncwarp();
         } else {
           for (int u = 0; u < 32; ++u) {
             const int gj = gj0 + u;
@@ -355,11 +396,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           }
         }
       }
-      // this warp is done reading the accumulator stage: hand it back to the MMA thread
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(accum_empty + as);
-      ++acc_iter;
+      if (has_acc) {
+        // this warp is done reading the accumulator stage: hand it back to the MMA thread
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(accum_empty + as);
+        ++acc_iter;
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -414,6 +457,21 @@ static int make_map_mnmajor(CUtensorMap* map, const float* base, int k, int n, i
   return r == CUDA_SUCCESS ? GPZ_OK : GPZ_ERR_BADARG;
 }
 
+// MN-major operand with n % 32 == 0: 4-D view {32, k, n/32, batch} (strides 4 B, ld, 128 B, sB) so that ONE box {32, 16, 8, 1}
+// lands chunk-major in shared memory (8 chunks x 16 rows x 128 B) - 1 TMA instruction per stage instead of 8.
+static int make_map_mnmajor4d(CUtensorMap* map, const float* base, int k, int n, int64_t ld, int64_t sB, int batch) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return GPZ_ERR_UNSUPPORTED;
+  cuuint64_t gdim[4] = {32, (cuuint64_t)k, (cuuint64_t)(n / 32), (cuuint64_t)batch};
+  cuuint64_t gstr[3] = {(cuuint64_t)ld * 4, 128, (cuuint64_t)(batch > 1 ? sB : (int64_t)k * ld) * 4};
+  cuuint32_t box[4] = {32, (cuuint32_t)BK, (cuuint32_t)(BN / 32), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? GPZ_OK : GPZ_ERR_BADARG;
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 constexpr int NUM_COUNTERS = 256;
@@ -445,6 +503,7 @@ extern "C" int gpz_umma_gemm_f32(int b_kmajor, int m, int n, int k, float alpha,
   if (splitk < 1) splitk = 1;
   if (splitk > 1 && (Cin || Dlo)) return GPZ_ERR_BADARG;
   CUtensorMap mA, mAlo, mB, mBlo;
+  int b_map4d = 0;
   int rc = make_map_kmajor(&mA, A, m, k, lda, sA, batch, BM);
   if (rc) return rc;
   rc = make_map_kmajor(&mAlo, Alo ? Alo : A, m, k, lda, sA, batch, BM);
@@ -454,12 +513,23 @@ extern "C" int gpz_umma_gemm_f32(int b_kmajor, int m, int n, int k, float alpha,
     if (rc) return rc;
     rc = make_map_kmajor(&mBlo, Blo ? Blo : B, n, k, ldb, sB, batch, BN);
   } else {
-    rc = make_map_mnmajor(&mB, B, k, n, ldb, sB, batch);
-    if (rc) return rc;
-    rc = make_map_mnmajor(&mBlo, Blo ? Blo : B, k, n, ldb, sB, batch);
+    static int use4d = -1;
+    if (use4d < 0) { const char* e = getenv("GPZ_UMMA_MAP4D"); use4d = e ? atoi(e) : 1; }
+    b_map4d = (use4d && n % 32 == 0) ? 1 : 0;
+    if (b_map4d) {
+      rc = make_map_mnmajor4d(&mB, B, k, n, ldb, sB, batch);
+      if (rc == GPZ_OK) rc = make_map_mnmajor4d(&mBlo, Blo ? Blo : B, k, n, ldb, sB, batch);
+      if (rc != GPZ_OK) b_map4d = 0;          // driver refused the 4-D view: fall back to 8 plain boxes
+    }
+    if (!b_map4d) {
+      rc = make_map_mnmajor(&mB, B, k, n, ldb, sB, batch);
+      if (rc) return rc;
+      rc = make_map_mnmajor(&mBlo, Blo ? Blo : B, k, n, ldb, sB, batch);
+    }
   }
   if (rc) return rc;
   Params p;
+  p.b_map4d = b_map4d;
   p.D = D; p.Dlo = Dlo; p.Cin = Cin; p.m = m; p.n = n; p.k = k; p.ldd = ldd; p.sD = sD; p.batch = batch; p.splitk = splitk;
   p.a_tri = a_tri; p.b_tri = b_tri; p.d_tri = d_tri; p.n_terms = n_terms; p.alpha = alpha;
   const int mtiles = (int)cdiv(m, BM), ntiles = (int)cdiv(n, BN);

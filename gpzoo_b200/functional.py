@@ -18,6 +18,7 @@ from ._cabi import c_f, c_i, c_i64, c_p, call, ptr, scalar
 # reference's torch.linalg.cholesky (one device sync).  Throughput runs may turn it off and call
 # `check_cholesky_info()` when they read the loss.
 SYNC_CHECKS = True
+USE_TENSOR_CORES = True      # fp32: route large contractions through the tcgen05 split-TF32 kernels
 _pending_info = []
 
 
@@ -43,7 +44,10 @@ def _c(t):
 
 
 def gemm(A, B, ta=False, tb=False, alpha=1.0, beta=0.0, out=None, a_tri=0, b_tri=0, d_tri=0, splitk=1):
-    """out[b] = alpha op(A[b]) op(B[b]) + beta out[b]; A, B, out are (batch, rows, cols) contiguous."""
+    """out[b] = alpha op(A[b]) op(B[b]) + beta out[b]; A, B, out are (batch, rows, cols) contiguous.
+
+    fp32 products with all dimensions >= 128 go to the tcgen05 split-TF32 kernel (the M x M operand is split into
+    (x, lo) / transposed on the fly); everything else, and all of fp64, runs on the exact CUDA-core GEMM."""
     bsz = A.shape[0]
     m, k = (A.shape[2], A.shape[1]) if ta else (A.shape[1], A.shape[2])
     n = B.shape[1] if tb else B.shape[2]
@@ -52,12 +56,30 @@ def gemm(A, B, ta=False, tb=False, alpha=1.0, beta=0.0, out=None, a_tri=0, b_tri
     if out is None:
         out = (torch.zeros if (d_tri or splitk > 1) else torch.empty)((bsz, m, n), dtype=A.dtype, device=A.device)
     dt = A.dtype
+    if (USE_TENSOR_CORES and dt == torch.float32 and min(m, n, k) >= 128 and splitk == 1 and beta in (0.0, 1.0)
+            and m % 4 == 0 and n % 4 == 0 and k % 4 == 0):
+        if ta:
+            Ae, Ae_lo = transpose_lo(A)
+        else:
+            Ae, Ae_lo = A, tf32_lo(A)
+        call("umma_gemm", dt, c_i(int(tb)), c_i(m), c_i(n), c_i(k), c_f(alpha), ptr(Ae), ptr(Ae_lo), c_i64(k), c_i64(m * k),
+             ptr(B), ptr(tf32_lo(B)), c_i64(B.shape[2]), c_i64(B.shape[1] * B.shape[2]), ptr(out if beta == 1.0 else None),
+             ptr(out), ptr(None), c_i64(n), c_i64(m * n), c_i(bsz), c_i(a_tri), c_i(b_tri), c_i(d_tri), c_i(1), c_i(3))
+        return out
     call("gemm", dt, c_i(int(ta)), c_i(int(tb)), c_i(m), c_i(n), c_i(k), scalar(dt, alpha),
          ptr(A), c_i64(A.shape[2]), c_i64(A.shape[1] * A.shape[2]),
          ptr(B), c_i64(B.shape[2]), c_i64(B.shape[1] * B.shape[2]),
          scalar(dt, beta), ptr(out), c_i64(out.shape[2]), c_i64(out.shape[1] * out.shape[2]),
          c_i(bsz), c_i(a_tri), c_i(b_tri), c_i(d_tri), c_i(splitk))
     return out
+
+
+def transpose_lo(x):
+    """(x^T, lo(x^T)) per matrix of a batch of square fp32 matrices."""
+    x = _c(x)
+    xt, xt_lo = torch.empty_like(x), torch.empty_like(x)
+    call("transpose_lo", torch.float32, ptr(x), ptr(xt), ptr(xt_lo), c_i(x.shape[-1]), c_i(x.shape[0]))
+    return xt, xt_lo
 
 
 def tri_op(X, mode, out=None):
@@ -222,9 +244,6 @@ class Whiten(Function):
 # ------------------------------------------------------------------------------------------------
 # K3 / K4
 # ------------------------------------------------------------------------------------------------
-USE_TENSOR_CORES = True      # fp32: route the N-proportional contractions through the tcgen05 split-TF32 kernels
-
-
 def tensor_core_predict_ok(dtype, M, N):
     return (USE_TENSOR_CORES and dtype == torch.float32
             and bool(_cabi.lib().gpz_svgp_predict_tc_supported(c_i(int(M)), c_i(int(N)))))
