@@ -14,7 +14,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -34,36 +33,40 @@ def peaks():
 
 
 class ClockSampler:
-    def __init__(self, index):
-        self.index, self.rows, self.stop_flag, self.t = index, [], False, None
+    """nvidia-smi streaming sampler (one long-lived process, 20 ms period) for the clocks line of the timing rules."""
 
-    def _run(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.1)
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
 
     def start(self):
-        self.t = threading.Thread(target=self._run, daemon=True)
-        self.t.start()
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.15)          # let it emit its first samples before the timed region starts
+        except Exception:
+            self.proc = None
 
     def stop(self):
-        self.stop_flag = True
-        if self.t:
-            self.t.join(timeout=6)
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        rows = []
+        if self.proc is not None:
+            time.sleep(0.05)
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
+                out = ""
+            rows = [[c.strip() for c in l.split(",")] for l in out.splitlines() if l.strip()]
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows)]
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
-        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
-                    samples=len(self.rows))
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in rows)]
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_min_mhz=sm[0] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=reasons, samples=len(rows))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -275,7 +278,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

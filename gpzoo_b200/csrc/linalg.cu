@@ -332,13 +332,66 @@ static int chol_inv_rec(T* W, T* Lc, T* X, T* tmp, int M, int L, int r0, int n, 
   return gemm<T>(st, false, false, n2, n1, n2, T(-1), X + o22, M, sL, tmp, M, sL, T(0), X + o21, M, sL, L, 1, 0, 0);
 }
 
+// batched (outer = factor, inner = block pair) GEMM on sub-blocks of L x M x M matrices
+template <typename T>
+static int gemm_pairs(cudaStream_t st, int m, int n, int k, T alpha, const T* A, const T* B, T beta, T* D, int M, int L, int npairs,
+                      int64_t pair_stride, int a_tri, int b_tri) {
+  GemmParams<T> p;
+  p.A = A; p.B = B; p.D = D; p.m = m; p.n = n; p.k = k; p.lda = p.ldb = p.ldd = M;
+  p.sAo = p.sBo = p.sDo = (int64_t)M * M;
+  p.sAi = p.sBi = p.sDi = pair_stride;
+  p.batch = L * npairs; p.batch_inner = npairs;
+  p.alpha = alpha; p.beta = beta; p.a_tri = a_tri; p.b_tri = b_tri; p.d_tri = 0; p.splitk = 1;
+  return gemm_launch(p, false, false, st);
+}
+
 // W: L x M x M copy of the (jittered) Kzz, destroyed; Lc, X: outputs; tmp: L x M x M scratch.
+// Right-looking blocked factorisation (NB = 64): leaf (factor + invert the diagonal block) -> panel L21 = A21 X11^T (GEMM,
+// all row blocks in parallel) -> trailing SYRK (GEMM); then X = Lc^-1 by recursive doubling from the 64 x 64 diagonal
+// inverses:  X21 = -X22 (L21 X11) for all block pairs of a level at once (log2(M/64) levels, 2 batched GEMMs each).
 template <typename T> int chol_inv(T* W, T* Lc, T* X, T* tmp, int M, int L, int* info, cudaStream_t st) {
   const int64_t sL = (int64_t)M * M;
   GPZ_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * L, st));
   GPZ_CUDA(cudaMemsetAsync(Lc, 0, sizeof(T) * sL * L, st));
   GPZ_CUDA(cudaMemsetAsync(X, 0, sizeof(T) * sL * L, st));
-  return chol_inv_rec<T>(W, Lc, X, tmp, M, L, 0, M, info, st);
+  constexpr int smem = (int)(2 * NB * (NB + 1) * sizeof(T));
+  GPZ_CUDA(cudaFuncSetAttribute(chol_inv_leaf_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  for (int k0 = 0; k0 < M; k0 += NB) {
+    const int nb = min(NB, M - k0);
+    chol_inv_leaf_kernel<T><<<L, 256, smem, st>>>(W, Lc, X, M, k0, nb, info);
+    GPZ_CHECK_LAUNCH();
+    const int rem = M - k0 - nb;
+    if (rem > 0) {
+      const int64_t o11 = (int64_t)k0 * M + k0, o21 = (int64_t)(k0 + nb) * M + k0, o22 = (int64_t)(k0 + nb) * M + k0 + nb;
+      int rc = gemm<T>(st, false, true, rem, nb, nb, T(1), W + o21, M, sL, X + o11, M, sL, T(0), Lc + o21, M, sL, L, 0, 2, 0);
+      if (rc) return rc;
+      rc = gemm<T>(st, false, true, rem, rem, nb, T(-1), Lc + o21, M, sL, Lc + o21, M, sL, T(1), W + o22, M, sL, L, 0, 0, 1);
+      if (rc) return rc;
+    }
+  }
+  for (int b = NB; b < M; b *= 2) {
+    // pairs of blocks [2pb, 2pb+b) (done) and [2pb+b, 2pb+2b) (done): fill the off-diagonal block X21 of the pair
+    const int nfull = M / (2 * b);                       // pairs whose second block is complete
+    const int64_t pstride = (int64_t)2 * b * M + 2 * b;   // diagonal step from one pair to the next
+    if (nfull > 0) {
+      // tmp21 = L21 X11 ; X21 = -X22 tmp21      (block offsets inside the first pair)
+      int rc = gemm_pairs<T>(st, b, b, b, T(1), Lc + (int64_t)b * M, X, T(0), tmp + (int64_t)b * M, M, L, nfull, pstride, 0, 1);
+      if (rc) return rc;
+      rc = gemm_pairs<T>(st, b, b, b, T(-1), X + (int64_t)b * M + b, tmp + (int64_t)b * M, T(0), X + (int64_t)b * M, M, L, nfull,
+                         pstride, 1, 0);
+      if (rc) return rc;
+    }
+    const int r0 = nfull * 2 * b;                         // a trailing, incomplete pair
+    const int m2 = M - r0 - b;
+    if (m2 > 0) {
+      const int64_t o11 = (int64_t)r0 * M + r0, o21 = (int64_t)(r0 + b) * M + r0, o22 = (int64_t)(r0 + b) * M + r0 + b;
+      int rc = gemm<T>(st, false, false, m2, b, b, T(1), Lc + o21, M, sL, X + o11, M, sL, T(0), tmp + o21, M, sL, L, 0, 1, 0);
+      if (rc) return rc;
+      rc = gemm<T>(st, false, false, m2, b, m2, T(-1), X + o22, M, sL, tmp + o21, M, sL, T(0), X + o21, M, sL, L, 1, 0, 0);
+      if (rc) return rc;
+    }
+  }
+  return GPZ_OK;
 }
 
 // ---- element-wise O(M^2) helpers -------------------------------------------------------------------

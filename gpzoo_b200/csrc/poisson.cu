@@ -12,6 +12,8 @@
 // parks t in shared memory.  Phase B (lane = gene, warp = quarter of the spots): the gW[g,f] partial
 // sum_n t[g,n] exp(F)[f,n] from shared memory.  Per-CTA gW partials go to a workspace slice and are
 // summed by a second tiny kernel (deterministic, no atomics on the G x F output).
+#include <type_traits>
+
 #include "common.cuh"
 #include "gpzoo_b200.h"
 
@@ -40,7 +42,7 @@ template <typename T> struct PoissonArgs {
 };
 
 template <typename T, int FMAX>
-__global__ void __launch_bounds__(PZ_SPOTS) poisson_kernel(const PoissonArgs<T> a) {
+__global__ void __launch_bounds__(PZ_SPOTS, sizeof(T) == 4 ? 3 : 1) poisson_kernel(const PoissonArgs<T> a) {
   extern __shared__ __align__(16) unsigned char pz_smem[];
   typedef T RowT[PZ_SPOTS + 1];
   typedef T RowE[FMAX];
@@ -55,6 +57,7 @@ __global__ void __launch_bounds__(PZ_SPOTS) poisson_kernel(const PoissonArgs<T> 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = blockIdx.x * PZ_SPOTS + tid;
   const bool active = n < a.B;
+  const bool block_full = (blockIdx.x + 1) * PZ_SPOTS <= a.B;      // uniform: every thread of the CTA has a spot
   const int64_t col = active ? (a.idx ? a.idx[n] : (int64_t)n) : 0;
   const T invE = T(1) / T(a.E);
 
@@ -75,6 +78,12 @@ __global__ void __launch_bounds__(PZ_SPOTS) poisson_kernel(const PoissonArgs<T> 
 
   const int g_begin = blockIdx.y * a.genes_per_cta;
   const int g_end = min(a.G, g_begin + a.genes_per_cta);
+  // software pipeline over groups of 8 genes: the y values of the NEXT group are in flight while the current group is
+  // being processed (the sequence of groups is chunk -> sample e -> group, so with E > 1 a chunk is re-read E times)
+  T ynext[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u)
+    ynext[u] = (active && g_begin + u < g_end) ? __ldcs(a.y + (int64_t)(g_begin + u) * a.y_ld + col) : T(0);
   for (int g0 = g_begin; g0 < g_end; g0 += PZ_GCH) {
     T acc[FMAX];
 #pragma unroll
@@ -105,29 +114,45 @@ __global__ void __launch_bounds__(PZ_SPOTS) poisson_kernel(const PoissonArgs<T> 
       T llc = T(0);
 #pragma unroll 1
       for (int gb = 0; gb < PZ_GCH; gb += 8) {
-        T yv[8];                      // 8 independent coalesced loads in flight per thread
+        T yv[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-          yv[u] = (active && g0 + gb + u < g_end) ? __ldcs(a.y + (int64_t)(g0 + gb + u) * a.y_ld + col) : T(0);
+        for (int u = 0; u < 8; ++u) yv[u] = ynext[u];
+        {
+          // first gene of the group after this one
+          int gn = g0 + gb + 8;
+          if (gb + 8 == PZ_GCH) gn = (e + 1 < a.E) ? g0 : g0 + PZ_GCH;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+          for (int u = 0; u < 8; ++u)
+            ynext[u] = (active && gn + u < g_end) ? __ldcs(a.y + (int64_t)(gn + u) * a.y_ld + col) : T(0);
+        }
+        // per-gene body; GUARD=false is the interior case (all 128 spots and all 32 genes of the chunk valid): no branches
+        auto body = [&](auto guard, int u) {
+          constexpr bool GUARD = decltype(guard)::value;
           const int gi = gb + u;
           T t = T(0);
-          if (active && g0 + gi < g_end) {
+          if (!GUARD || (active && g0 + gi < g_end)) {
             const T y = yv[u];
             T zr = T(0);
 #pragma unroll
             for (int f = 0; f < FMAX; ++f) zr = fma(sW[gi][f], ef[f], zr);
             const T r = spV * zr;
-            T lp = (y == T(0) ? T(0) : y * Num<T>::log(r)) - r;
+            const T ylog = y * fast_log(r);
+            T lp = (y == T(0) ? T(0) : ylog) - r;
             if (a.with_lgamma && y > T(1.5)) lp -= Num<T>::lgamma(y + T(1));   // lgamma(1) = lgamma(2) = 0
             llc += lp;
-            t = (y / zr - spV) * invE;
-            gVacc += (y - r) * invE;
+            t = (fast_div(y, zr) - spV) * invE;
+            gVacc += y - r;
 #pragma unroll
             for (int f = 0; f < FMAX; ++f) pg[f] = fma(sW[gi][f], t, pg[f]);
           }
           tS[gi][tid] = t;
+        };
+        if (block_full && g0 + PZ_GCH <= g_end) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) body(std::false_type{}, u);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) body(std::true_type{}, u);
         }
       }
       ll += (double)(llc * invE);
@@ -161,7 +186,7 @@ __global__ void __launch_bounds__(PZ_SPOTS) poisson_kernel(const PoissonArgs<T> 
   }
 
   if (active) {
-    const T gv = softplus_grad(vraw) * gVacc / spV;
+    const T gv = softplus_grad(vraw) * gVacc * invE / spV;
     if (a.atomic_out) atomicAdd(a.gV + n, gv); else a.gV[n] = gv;
 #pragma unroll
     for (int f = 0; f < FMAX; ++f) {
