@@ -92,7 +92,7 @@ def _cpu_step_time(n_sample, steps, warmup):
     return sum(times) / len(times), torch.get_num_threads()
 
 
-def cpu_reference_full_step(steps, warmup, n1=256, n2=1024):
+def cpu_reference_full_step(steps, warmup, n1=128, n2=768):
     """Time the oracle port (the reference's op sequence on CPU torch, fp32, all host threads) on a bounded sample and
     extrapolate to the full N: the step costs t(N) = a + b N (a: the O(M^3) Cholesky / KL work, b: everything per spot),
     fitted from `steps` timed steps at N=n1 and one at N=n2."""

@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(256) chol_inv_leaf_kernel(const T* __restrict_
   Row* a = reinterpret_cast<Row*>(leaf_smem);
   Row* x = a + NB;
   __shared__ T sbuf[SB][SB + 1];
+  __shared__ T rsd[SB];
   const int64_t off = (int64_t)blockIdx.x * M * M;
   const T* W = Wall + off;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -189,30 +190,23 @@ __global__ void __launch_bounds__(256) chol_inv_leaf_kernel(const T* __restrict_
   // ---- Cholesky ----
   for (int j0 = 0; j0 < n; j0 += SB) {
     const int jn = min(SB, n - j0);
-    if (warp == 0) {
-      // (a) diagonal 16 x 16 block in registers: lane r holds row r, columns are exchanged with shuffles
-      T row[SB];
-#pragma unroll
-      for (int k = 0; k < SB; ++k) row[k] = (lane < jn && k <= lane) ? a[j0 + lane][j0 + k] : T(0);
-#pragma unroll
-      for (int j = 0; j < SB; ++j) {
-        const T d = __shfl_sync(0xffffffffu, row[j], j);
-        if (j < jn) {
-          if (!(d > T(0)) && lane == 0 && info[blockIdx.x] == 0) info[blockIdx.x] = r0 + j0 + j + 1;
-          const T sd = Num<T>::sqrt(d);
-          if (lane == j) row[j] = sd;
-          else if (lane > j) row[j] = row[j] / sd;
+    {
+      // (a) diagonal 16 x 16 block: thread (ti, tk) owns entry (ti, tk); one barrier per column.  Column j is left
+      //     un-scaled while it is used (the update divides by the pivot instead) and scaled once at the end.
+      const int ti = tid >> 4, tk = tid & 15;
+      for (int j = 0; j < jn; ++j) {
+        const T d = a[j0 + j][j0 + j];
+        if (tid == 0) {
+          if (!(d > T(0)) && info[blockIdx.x] == 0) info[blockIdx.x] = r0 + j0 + j + 1;
+          rsd[j] = Num<T>::rsqrt(d);
         }
-        const T mine = row[j];
-#pragma unroll
-        for (int k = j + 1; k < SB; ++k) {
-          const T other = __shfl_sync(0xffffffffu, mine, k);       // a[k][j] lives in lane k
-          if (j < jn && lane >= k) row[k] -= mine * other;
-        }
+        if (ti < jn && tk > j && tk <= ti)
+          a[j0 + ti][j0 + tk] -= a[j0 + ti][j0 + j] * a[j0 + tk][j0 + j] / d;
+        __syncthreads();
       }
-      if (lane < jn) {
-#pragma unroll
-        for (int k = 0; k < SB; ++k) if (k <= lane) a[j0 + lane][j0 + k] = row[k];
+      if (ti < jn && tk <= ti) {
+        const T v = a[j0 + ti][j0 + tk] * rsd[tk];          // diagonal: d * rsqrt(d) = sqrt(d)
+        a[j0 + ti][j0 + tk] = v;
       }
     }
     __syncthreads();

@@ -15,6 +15,7 @@
 //     gKxx = gv
 #include "gemm_simt.cuh"
 #include "gpzoo_b200.h"
+#include "umma_gemm.h"
 
 namespace gpz {
 
@@ -133,29 +134,64 @@ int predict_bwd(const T* Kzx, const T* Linv, const T* Tm, const T* q, const T* A
 }
 
 // ---- tensor-core (tcgen05, split-TF32) variant of the same two entry points, fp32 only ----------------------------
-// ws layout (floats): [Linv_lo | TT | TT_lo | T_lo | LinvT | LinvT_lo], each L*M*M.
+// ws layout (floats): [Linv_lo | TT | TT_lo | T_lo | LinvT | LinvT_lo] (each L*M*M) then [sumA2 | sumC2] (each L*N).
+// The column reductions of the predictive mean / variance and the row reduction gq = A gm are fused into the GEMM
+// epilogues (umma_gemm.cu epi_mode 1..3), so A and C are never re-read for them.
 static int tc_gemm(cudaStream_t st, int bk, int m, int n, int k, const float* A, const float* Alo, int64_t lda, int64_t sA,
-                   const float* B, const float* Blo, int64_t ldb, int64_t sB, const float* Cin, float* D, float* Dlo, int64_t ldd,
-                   int64_t sD, int batch, int a_tri, int d_tri, int splitk) {
-  return gpz_umma_gemm_f32(bk, m, n, k, 1.0f, A, Alo, lda, sA, B, Blo, ldb, sB, Cin, D, Dlo, ldd, sD, batch, a_tri, 0, d_tri, splitk,
-                           3, (void*)st);
+                   const float* B, const float* Blo, int64_t ldb, int64_t sB, float* D, float* Dlo, int64_t ldd, int64_t sD,
+                   int batch, int a_tri, int d_tri, int splitk, const UmmaEpilogue* epi = nullptr) {
+  return umma_gemm_ex(bk, m, n, k, 1.0f, A, Alo, lda, sA, B, Blo, ldb, sB, nullptr, D, Dlo, ldd, sD, batch, a_tri, 0, d_tri, splitk,
+                      3, epi, (void*)st);
+}
+
+__global__ void predict_var_kernel(const float* __restrict__ kxx, const float* __restrict__ sA2, const float* __restrict__ sC2,
+                                   float* __restrict__ var, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) var[i] = kxx[i] - sA2[i] + sC2[i];
+}
+
+// C <- gC = 2 C gv  and its lo part
+__global__ void __launch_bounds__(256) predict_scale_kernel(float* __restrict__ C, float* __restrict__ Clo, const float* __restrict__ gv,
+                                                             int M, int N) {
+  const int l = blockIdx.z;
+  const int n4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (n4 >= N) return;
+  const float4 g = *reinterpret_cast<const float4*>(gv + (int64_t)l * N + n4);
+  const int m0 = blockIdx.y * 16, m1 = min(m0 + 16, M);
+  for (int m = m0; m < m1; ++m) {
+    const int64_t e = ((int64_t)l * M + m) * N + n4;
+    float4 c = *reinterpret_cast<const float4*>(C + e);
+    c.x *= 2.f * g.x; c.y *= 2.f * g.y; c.z *= 2.f * g.z; c.w *= 2.f * g.w;
+    *reinterpret_cast<float4*>(C + e) = c;
+    float4 lo;
+    lo.x = c.x - __uint_as_float(__float_as_uint(c.x) & 0xFFFFE000u);
+    lo.y = c.y - __uint_as_float(__float_as_uint(c.y) & 0xFFFFE000u);
+    lo.z = c.z - __uint_as_float(__float_as_uint(c.z) & 0xFFFFE000u);
+    lo.w = c.w - __uint_as_float(__float_as_uint(c.w) & 0xFFFFE000u);
+    *reinterpret_cast<float4*>(Clo + e) = lo;
+  }
 }
 
 static int predict_fwd_tc(const float* Kzx, const float* Kzx_lo, const float* Linv, const float* Tm, const float* q, const float* kxx,
                           float* A, float* A_lo, float* C, float* mean, float* var, float* ws, int M, int N, int L, cudaStream_t st) {
-  const int64_t sMM = (int64_t)M * M, sMN = (int64_t)M * N, W = sMM * L;
+  const int64_t sMM = (int64_t)M * M, sMN = (int64_t)M * N, W = sMM * L, LN = (int64_t)L * N;
   float* Linv_lo = ws; float* TT = ws + W; float* TT_lo = ws + 2 * W;
+  float* sA2 = ws + 6 * W; float* sC2 = sA2 + LN;
   int rc = gpz_tf32_lo_f32(Linv, Linv_lo, W, (void*)st);
   if (rc) return rc;
   rc = gpz_transpose_lo_f32(Tm, TT, TT_lo, M, L, (void*)st);
   if (rc) return rc;
-  // A = Linv Kzx  (lower-triangular product == TRSM Lc A = Kzx)
-  rc = tc_gemm(st, 0, M, N, M, Linv, Linv_lo, M, sMM, Kzx, Kzx_lo, N, sMN, nullptr, A, A_lo, N, sMN, L, 1, 0, 1);
+  GPZ_CUDA(cudaMemsetAsync(sA2, 0, sizeof(float) * 2 * LN, st));
+  GPZ_CUDA(cudaMemsetAsync(mean, 0, sizeof(float) * LN, st));
+  // A = Linv Kzx  (lower-triangular product == TRSM Lc A = Kzx); epilogue: sum_m A^2 and mean = sum_m q_m A
+  UmmaEpilogue e1{1, nullptr, q, nullptr, nullptr, sA2, mean, nullptr};
+  rc = tc_gemm(st, 0, M, N, M, Linv, Linv_lo, M, sMM, Kzx, Kzx_lo, N, sMN, A, A_lo, N, sMN, L, 1, 0, 1, &e1);
   if (rc) return rc;
-  // C = T^T A     (upper-triangular product)
-  rc = tc_gemm(st, 0, M, N, M, TT, TT_lo, M, sMM, A, A_lo, N, sMN, nullptr, C, nullptr, N, sMN, L, 2, 0, 1);
+  // C = T^T A     (upper-triangular product); epilogue: sum_m C^2
+  UmmaEpilogue e2{2, nullptr, nullptr, nullptr, nullptr, sC2, nullptr, nullptr};
+  rc = tc_gemm(st, 0, M, N, M, TT, TT_lo, M, sMM, A, A_lo, N, sMN, C, nullptr, N, sMN, L, 2, 0, 1, &e2);
   if (rc) return rc;
-  predict_reduce_kernel<float><<<dim3((unsigned)cdiv(N, 256), L), 256, sizeof(float) * M, st>>>(A, C, q, kxx, mean, var, M, N);
+  predict_var_kernel<<<(unsigned)cdiv(LN, 256), 256, 0, st>>>(kxx, sA2, sC2, var, LN);
   GPZ_CHECK_LAUNCH();
   return GPZ_OK;
 }
@@ -169,29 +205,27 @@ static int predict_bwd_tc(const float* Kzx, const float* Kzx_lo, const float* Li
   if (rc) return rc;
   rc = gpz_transpose_lo_f32(Linv, LinvT, LinvT_lo, M, L, (void*)st);
   if (rc) return rc;
-  const int rows = 64;
-  // C <- gC = 2 C gv (+ lo part);  gA <- -2 A gv + q gm^T
-  predict_bwd_prep_kernel<float><<<dim3((unsigned)cdiv(N, 256), (unsigned)cdiv(M, rows), L), 256, 0, st>>>(A, C, q, gm, gv, gA, C_lo,
-                                                                                                        M, N, rows);
+  // C <- gC = 2 C gv (+ lo part)
+  predict_scale_kernel<<<dim3((unsigned)cdiv(N, 1024), (unsigned)cdiv(M, 16), L), 256, 0, st>>>(C, C_lo, gv, M, N);
   GPZ_CHECK_LAUNCH();
-  rowdot_kernel<float><<<dim3(M, L), 256, 0, st>>>(A, gm, gq, M, N);
-  GPZ_CHECK_LAUNCH();
+  GPZ_CUDA(cudaMemsetAsync(gq, 0, sizeof(float) * (size_t)L * M, st));
   int splitk = 1;
   {
     const int64_t tiles = cdiv(M, 128) * cdiv(M, 256) * L / 2 + 1;
     while (splitk < 32 && tiles * splitk < 148 * 2 && N / (splitk * 2) >= 1024) splitk *= 2;
   }
   // gT = tril(A gC^T)   (reduction over the N spots, both operands K-major)
-  rc = tc_gemm(st, 1, M, M, N, A, A_lo, N, sMN, C, C_lo, N, sMN, nullptr, gT, nullptr, M, sMM, L, 0, 1, splitk);
+  rc = tc_gemm(st, 1, M, M, N, A, A_lo, N, sMN, C, C_lo, N, sMN, gT, nullptr, M, sMM, L, 0, 1, splitk);
   if (rc) return rc;
-  // gA = T gC + gA
-  rc = tc_gemm(st, 0, M, N, M, Tm, T_lo, M, sMM, C, C_lo, N, sMN, gA, gA, gA_lo, N, sMN, L, 1, 0, 1);
+  // gA = T gC - 2 A gv + q gm^T ;  gq = A gm     (both in the epilogue, which reads the A tile once)
+  UmmaEpilogue e3{3, A, q, gv, gm, nullptr, nullptr, gq};
+  rc = tc_gemm(st, 0, M, N, M, Tm, T_lo, M, sMM, C, C_lo, N, sMN, gA, gA_lo, N, sMN, L, 1, 0, 1, &e3);
   if (rc) return rc;
   // gKzx = Linv^T gA
-  rc = tc_gemm(st, 0, M, N, M, LinvT, LinvT_lo, M, sMM, gA, gA_lo, N, sMN, nullptr, gKzx, nullptr, N, sMN, L, 2, 0, 1);
+  rc = tc_gemm(st, 0, M, N, M, LinvT, LinvT_lo, M, sMM, gA, gA_lo, N, sMN, gKzx, nullptr, N, sMN, L, 2, 0, 1);
   if (rc) return rc;
   // gLinv = tril(gA Kzx^T)
-  return tc_gemm(st, 1, M, M, N, gA, gA_lo, N, sMN, Kzx, Kzx_lo, N, sMN, nullptr, gLinv, nullptr, M, sMM, L, 0, 1, splitk);
+  return tc_gemm(st, 1, M, M, N, gA, gA_lo, N, sMN, Kzx, Kzx_lo, N, sMN, gLinv, nullptr, M, sMM, L, 0, 1, splitk);
 }
 
 }  // namespace gpz

@@ -23,6 +23,7 @@
 
 #include "common.cuh"
 #include "gpzoo_b200.h"
+#include "umma_gemm.h"
 
 namespace gpz {
 namespace umma {
@@ -45,6 +46,13 @@ struct Params {
   int a_tri, b_tri, d_tri;
   int n_terms;            // 3: split-TF32, 1: plain TF32
   int b_map4d;            // MN-major B loaded with one 4-D box per stage (needs n % 32 == 0)
+  // fused epilogues of the SVGP predictive op (csrc/predict.cu); vectors are per batch entry
+  //   1: col1[n] += sum_i D[i,n]^2 ; col2[n] += sum_i rowv[i] D[i,n]                     (A = Linv Kzx: sum A^2 and mean)
+  //   2: col1[n] += sum_i D[i,n]^2                                                        (C = T^T A: sum C^2)
+  //   3: D = acc - 2 Aux[i,n] colv1[n] + rowv[i] colv2[n] ; rowacc[i] += sum_n Aux[i,n] colv2[n]   (gA and gq = A gm)
+  int epi_mode;
+  const float* Aux; const float* rowv; const float* colv1; const float* colv2;
+  float* col1; float* col2; float* rowacc;
   float alpha;
 };
 
@@ -329,6 +337,17 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       }
       const int gi = ti.i0 + q * 32 + lane;
+      const int wrow0 = ti.i0 + q * 32;
+      float racc[8];                          // mode 3: per-row partial sums of this lane's 8 rows (coalesced path)
+      float qreg[8];                          // rowv of this lane's 8 rows (coalesced path)
+      float racc_s = 0.f;                     // mode 3, scalar path: row gi
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        racc[u] = 0.f;
+        const int rr = wrow0 + u * 4 + (lane >> 3);
+        qreg[u] = (p.epi_mode != 0 && p.epi_mode != 2 && rr < p.m) ? p.rowv[(int64_t)ti.b * p.m + rr] : 0.f;
+      }
+      const float q_s = (p.epi_mode != 0 && p.epi_mode != 2 && gi < p.m) ? p.rowv[(int64_t)ti.b * p.m + gi] : 0.f;
       float* Drow = p.D + (int64_t)ti.b * p.sD + (int64_t)gi * p.ldd;
       float* Lrow = p.Dlo ? p.Dlo + (int64_t)ti.b * p.sD + (int64_t)gi * p.ldd : nullptr;
       const float* Crow = p.Cin ? p.Cin + (int64_t)ti.b * p.sD + (int64_t)gi * p.ldd : nullptr;
@@ -363,6 +382,12 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 make_float4(__uint_as_float(r[u]), __uint_as_float(r[u + 1]), __uint_as_float(r[u + 2]), __uint_as_float(r[u + 3]));
           __syncwarp();
           const int cq = (lane & 7) * 4;
+          float4 cs1 = make_float4(0.f, 0.f, 0.f, 0.f), cs2 = make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 cv1 = cs1, cv2 = cs1;
+          if (p.epi_mode == 3) {
+            cv1 = *reinterpret_cast<const float4*>(p.colv1 + (int64_t)ti.b * p.n + gj0 + cq);
+            cv2 = *reinterpret_cast<const float4*>(p.colv2 + (int64_t)ti.b * p.n + gj0 + cq);
+          }
 #pragma unroll
           for (int itr = 0; itr < 8; ++itr) {
             const int rr = itr * 4 + (lane >> 3);
@@ -372,6 +397,25 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             if (p.Cin) {
               const float4 cc = *reinterpret_cast<const float4*>(p.Cin + o);
               v.x += cc.x; v.y += cc.y; v.z += cc.z; v.w += cc.w;
+            }
+            if (p.epi_mode == 3) {
+              const float4 ax = *reinterpret_cast<const float4*>(p.Aux + o);
+              const float qv = qreg[itr];
+              v.x += fmaf(qv, cv2.x, -2.f * ax.x * cv1.x);
+              v.y += fmaf(qv, cv2.y, -2.f * ax.y * cv1.y);
+              v.z += fmaf(qv, cv2.z, -2.f * ax.z * cv1.z);
+              v.w += fmaf(qv, cv2.w, -2.f * ax.w * cv1.w);
+              float rp = ax.x * cv2.x + ax.y * cv2.y + ax.z * cv2.z + ax.w * cv2.w;
+              rp += __shfl_xor_sync(0xffffffffu, rp, 1);
+              rp += __shfl_xor_sync(0xffffffffu, rp, 2);
+              rp += __shfl_xor_sync(0xffffffffu, rp, 4);
+              racc[itr] += rp;
+            } else if (p.epi_mode != 0) {
+              cs1.x = fmaf(v.x, v.x, cs1.x); cs1.y = fmaf(v.y, v.y, cs1.y); cs1.z = fmaf(v.z, v.z, cs1.z); cs1.w = fmaf(v.w, v.w, cs1.w);
+              if (p.epi_mode == 1) {
+                const float qv = qreg[itr];
+                cs2.x = fmaf(qv, v.x, cs2.x); cs2.y = fmaf(qv, v.y, cs2.y); cs2.z = fmaf(qv, v.z, cs2.z); cs2.w = fmaf(qv, v.w, cs2.w);
+              }
             }
             *reinterpret_cast<float4*>(p.D + o) = v;
             if (p.Dlo) {
@@ -383,6 +427,26 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
               *reinterpret_cast<float4*>(p.Dlo + o) = lo;
             }
           }
+          if (p.epi_mode == 1 || p.epi_mode == 2) {
+            // column sums over the warp's 32 rows: combine the four row groups (lane/8), then lanes 0..7 own 4 columns each
+#pragma unroll
+            for (int sh = 8; sh <= 16; sh <<= 1) {
+              cs1.x += __shfl_xor_sync(0xffffffffu, cs1.x, sh); cs1.y += __shfl_xor_sync(0xffffffffu, cs1.y, sh);
+              cs1.z += __shfl_xor_sync(0xffffffffu, cs1.z, sh); cs1.w += __shfl_xor_sync(0xffffffffu, cs1.w, sh);
+              if (p.epi_mode == 1) {
+                cs2.x += __shfl_xor_sync(0xffffffffu, cs2.x, sh); cs2.y += __shfl_xor_sync(0xffffffffu, cs2.y, sh);
+                cs2.z += __shfl_xor_sync(0xffffffffu, cs2.z, sh); cs2.w += __shfl_xor_sync(0xffffffffu, cs2.w, sh);
+              }
+            }
+            if (lane < 8) {
+              float* c1 = p.col1 + (int64_t)ti.b * p.n + gj0 + cq;
+              atomicAdd(c1, cs1.x); atomicAdd(c1 + 1, cs1.y); atomicAdd(c1 + 2, cs1.z); atomicAdd(c1 + 3, cs1.w);
+              if (p.epi_mode == 1) {
+                float* c2 = p.col2 + (int64_t)ti.b * p.n + gj0 + cq;
+                atomicAdd(c2, cs2.x); atomicAdd(c2 + 1, cs2.y); atomicAdd(c2 + 2, cs2.z); atomicAdd(c2 + 3, cs2.w);
+              }
+            }
+          }
           __syncwarp();
         } else {
           for (int u = 0; u < 32; ++u) {
@@ -391,10 +455,29 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             if ((p.d_tri == 1 && gj > gi) || (p.d_tri == 2 && gj < gi)) continue;
             float v = p.alpha * __uint_as_float(r[u]);
             if (Crow) v += Crow[gj];
+            if (p.epi_mode == 3) {
+              const float ax = p.Aux[(int64_t)ti.b * p.sD + (int64_t)gi * p.ldd + gj];
+              const float g2 = p.colv2[(int64_t)ti.b * p.n + gj];
+              v += fmaf(q_s, g2, -2.f * ax * p.colv1[(int64_t)ti.b * p.n + gj]);
+              racc_s = fmaf(ax, g2, racc_s);
+            } else if (p.epi_mode != 0) {
+              atomicAdd(p.col1 + (int64_t)ti.b * p.n + gj, v * v);
+              if (p.epi_mode == 1) atomicAdd(p.col2 + (int64_t)ti.b * p.n + gj, q_s * v);
+            }
             Drow[gj] = v;
             if (Lrow) Lrow[gj] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
           }
         }
+      }
+      if (p.epi_mode == 3) {
+        if ((lane & 7) == 0) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int rr = wrow0 + u * 4 + (lane >> 3);
+            if (rr < p.m && racc[u] != 0.f) atomicAdd(p.rowacc + (int64_t)ti.b * p.m + rr, racc[u]);
+          }
+        }
+        if (gi < p.m && racc_s != 0.f) atomicAdd(p.rowacc + (int64_t)ti.b * p.m + gi, racc_s);
       }
       if (has_acc) {
         // this warp is done reading the accumulator stage: hand it back to the MMA thread
@@ -495,6 +578,14 @@ extern "C" int gpz_umma_gemm_f32(int b_kmajor, int m, int n, int k, float alpha,
                                  int64_t sA, const float* B, const float* Blo, int64_t ldb, int64_t sB, const float* Cin, float* D,
                                  float* Dlo, int64_t ldd, int64_t sD, int batch, int a_tri, int b_tri, int d_tri, int splitk,
                                  int n_terms, void* stream) {
+  return umma_gemm_ex(b_kmajor, m, n, k, alpha, A, Alo, lda, sA, B, Blo, ldb, sB, Cin, D, Dlo, ldd, sD, batch, a_tri, b_tri, d_tri,
+                      splitk, n_terms, nullptr, stream);
+}
+
+int umma_gemm_ex(int b_kmajor, int m, int n, int k, float alpha, const float* A, const float* Alo, int64_t lda, int64_t sA,
+                 const float* B, const float* Blo, int64_t ldb, int64_t sB, const float* Cin, float* D, float* Dlo, int64_t ldd,
+                 int64_t sD, int batch, int a_tri, int b_tri, int d_tri, int splitk, int n_terms, const UmmaEpilogue* epi,
+                 void* stream) {
   if (!gpz_umma_gemm_supported(b_kmajor, m, n, k, lda, ldb, ldd)) return GPZ_ERR_UNSUPPORTED;
   if (n_terms != 1 && n_terms != 3) return GPZ_ERR_BADARG;
   if (n_terms == 3 && (!Alo || !Blo)) return GPZ_ERR_BADARG;
@@ -530,6 +621,11 @@ extern "C" int gpz_umma_gemm_f32(int b_kmajor, int m, int n, int k, float alpha,
   if (rc) return rc;
   Params p;
   p.b_map4d = b_map4d;
+  p.epi_mode = epi ? epi->mode : 0;
+  p.Aux = epi ? epi->Aux : nullptr; p.rowv = epi ? epi->rowv : nullptr; p.colv1 = epi ? epi->colv1 : nullptr;
+  p.colv2 = epi ? epi->colv2 : nullptr; p.col1 = epi ? epi->col1 : nullptr; p.col2 = epi ? epi->col2 : nullptr;
+  p.rowacc = epi ? epi->rowacc : nullptr;
+  if (p.epi_mode != 0 && (splitk > 1 || d_tri != 0)) return GPZ_ERR_BADARG;
   p.D = D; p.Dlo = Dlo; p.Cin = Cin; p.m = m; p.n = n; p.k = k; p.ldd = ldd; p.sD = sD; p.batch = batch; p.splitk = splitk;
   p.a_tri = a_tri; p.b_tri = b_tri; p.d_tri = d_tri; p.n_terms = n_terms; p.alpha = alpha;
   const int mtiles = (int)cdiv(m, BM), ntiles = (int)cdiv(n, BN);

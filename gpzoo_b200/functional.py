@@ -267,7 +267,7 @@ class Predict(Function):
         if tc:
             Kzx_lo = _c(Kzx_lo)
             A_lo = torch.empty_like(Kzx)
-            ws = torch.empty(6 * L * M * M, dtype=dt, device=Kzx.device)
+            ws = torch.empty(6 * L * M * M + 2 * L * N, dtype=dt, device=Kzx.device)
             call("svgp_predict_fwd_tc", dt, ptr(Kzx), ptr(Kzx_lo), ptr(Linv), ptr(T), ptr(q), ptr(Kxx), ptr(A), ptr(A_lo), ptr(C),
                  ptr(mean), ptr(var), ptr(ws), c_i(M), c_i(N), c_i(L))
             ctx.save_for_backward(Kzx, Linv, T, q, A, C, Kzx_lo, A_lo, ws)

@@ -228,7 +228,7 @@ class Hybrid_NSF2(nn.Module):
         qF2, pF2 = self.cf.prior.forward_batched(idx)
         return self._combine(qF1, qF2, idx, E, eps, eps2), qF1, qU, pU, qF2, pF2
 
-    def elbo(self, X, y, idx=None, E=1, eps=None, eps2=None, with_lgamma=True, **kwargs):
+    def elbo(self, X, y, idx=None, E=1, eps=None, eps2=None, with_lgamma=True, kl_weight=1.0, **kwargs):
         """Fused hybrid ELBO: ll - sum KL(qU||pU) - sum KL(qF2||pF2)   (utilities.py:509-516).
         The L spatial factors enter the likelihood kernel as (mean, variance), the T non-spatial ones as
         (mean, sd); both loading blocks are contracted in the same pass over y."""
@@ -251,7 +251,7 @@ class Hybrid_NSF2(nn.Module):
         ll = F.PoissonLL.apply(y, idx, W, self.V.to(dt), mean, spread, torch.cat((eps, eps2), 1), L, gp.clamp_min,
                                True, with_lgamma)
         kl = F.MvnKL.apply(m["T"], m["q"], m["Lc"], m["Lu"])
-        return ll - kl.sum() - distributions.kl_divergence(qF2, pF2).sum()
+        return ll - kl_weight * kl.sum() - distributions.kl_divergence(qF2, pF2).sum()
 
 
 class Hybrid_NSF_Exact(Hybrid_NSF2):
@@ -298,3 +298,22 @@ class Hybrid_NSF(NSF):
 
     def forward_batched(self, X, idx, E=10, verbose=False, eps=None, eps2=None, **kwargs):
         return self._run(X, idx, E, verbose, eps, eps2, kwargs)
+
+    def elbo(self, X, y, idx=None, E=1, eps=None, eps2=None, with_lgamma=True, kl_weight=1.0, **kwargs):
+        """Fused ELBO of the raw-loading hybrid (utilities.py:498-529): ll - sum KL(qU||pU) - sum KL(qF2||pF2)."""
+        gp = self.gp
+        Xb = X if idx is None else X[idx]
+        gX = kwargs.get("groupsX")
+        m = gp.moments(Xb, gX) if gX is not None else gp.moments(Xb)
+        qF2, pF2 = self._q2(idx)
+        mean1, var1 = m["mean"], m["var"]
+        dt, dev = mean1.dtype, mean1.device
+        L, T2, B = mean1.shape[0], qF2.loc.shape[0], mean1.shape[1]
+        eps = torch.randn((E, L, B), dtype=dt, device=dev) if eps is None else eps
+        eps2 = torch.randn((E, T2, B), dtype=dt, device=dev) if eps2 is None else eps2
+        W = torch.cat((self.W, self.W2), dim=1).to(dt)
+        ll = F.PoissonLL.apply(y, idx, W, self.V.to(dt), torch.cat((mean1, qF2.loc.to(dt)), 0),
+                               torch.cat((var1, qF2.scale.to(dt)), 0), torch.cat((eps, eps2), 1), L, gp.clamp_min, False,
+                               with_lgamma)
+        kl = F.MvnKL.apply(m["T"], m["q"], m["Lc"], m["Lu"])
+        return ll - kl_weight * kl.sum() - distributions.kl_divergence(qF2, pF2).sum()

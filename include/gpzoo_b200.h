@@ -99,7 +99,7 @@ int gpz_svgp_predict_bwd_f64(const double* Kzx, const double* Linv, const double
                              double* gT, double* gq, int M, int N, int L, void* stream);
 
 /* tensor-core (tcgen05 split-TF32) variant of the two calls above, fp32 only.  Kzx_lo: lo part of Kzx (kernel_build out_lo);
- * A_lo, C_lo, gA_lo: L x M x N scratch kept between forward and backward / inside the backward; ws: 6*L*M*M floats
+ * A_lo, C_lo, gA_lo: L x M x N scratch kept between forward and backward / inside the backward; ws: 6*L*M*M + 2*L*N floats
  * (the same buffer must be passed to forward and backward).  gLinv and gT must be zero-filled by the caller. */
 int gpz_svgp_predict_tc_supported(int M, int N);
 int gpz_svgp_predict_fwd_tc_f32(const float* Kzx, const float* Kzx_lo, const float* Linv, const float* T, const float* q,
