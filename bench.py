@@ -4,8 +4,10 @@
 Workload (BASELINE.json configs[1]): NSF2(SVGP(NSF_RBF)), N=32768 spots, M=1024 inducing points, L=10 factors,
 G=2000 genes, E=1, fp32, synthetic Slide-seq-shaped data (gpzoo_b200.synthetic.nsf_problem).
 One step = ELBO forward + backward producing every parameter gradient (+ all-reduce of the shared-parameter
-gradients when N>1); the optimiser update is excluded.  Multi-GPU: the spots are sharded across
-ranks (strong scaling, fixed global N), shared gradients summed with one NCCL all-reduce.
+gradients when N>1); the optimiser update is excluded.  Multi-GPU: data parallel over spots, shared
+gradients summed with one NCCL all-reduce.  Headline `value` is WEAK scaling (every GPU runs the 32768-spot workload,
+global minibatch = N x 32768 spots, value = 32768-spot steps/s summed over the GPUs); the `strong` block of the same
+JSON line is the fixed-global-size measurement (32768 spots split over the ranks).
 
 Prints ONE JSON line (rank 0).  `--impl reference` times the reference's CPU PyTorch path (oracle port) instead.
 """
@@ -155,19 +157,32 @@ def run_ours(args):
     functional.set_sync_checks(False)          # Cholesky info is checked once, after the timed region
     dt = torch.float32
     c = CFG
-    prob = synthetic.nsf_problem(N=c["N"], M=c["M"], L=c["L"], G=c["G"], E=c["E"], seed=c["seed"], coord_scale=c["coord_scale"],
-                                 lengthscale=c["lengthscale"], jitter=c["jitter"], dtype=dt)
-    lo, hi = shard_range(c["N"], world, rank)
-    n_loc = hi - lo
-    sl = slice(lo, hi)
-    # host (pinned) copies of this rank's shard: the e2e leg copies them in every step
-    hX = prob["X"][sl].contiguous().pin_memory()
-    hy = prob["y"][:, sl].contiguous().pin_memory()
-    prob_loc = dict(prob)
-    prob_loc["V"] = prob["V"][sl].contiguous()
-    model, shared = build_model(prob_loc, dt, dev)
-    X, y = hX.to(dev), hy.to(dev)
-    eps = prob["eps"][:, :, sl].contiguous().to(dev)
+
+    def setup(mode):
+        """weak: every rank owns a full 32768-spot shard (global minibatch = world x 32768 spots, parameters shared);
+        strong: the 32768 spots of configs[1] are split over the ranks."""
+        prob = synthetic.nsf_problem(N=c["N"], M=c["M"], L=c["L"], G=c["G"], E=c["E"], seed=c["seed"], coord_scale=c["coord_scale"],
+                                     lengthscale=c["lengthscale"], jitter=c["jitter"], dtype=dt)
+        if mode == "weak":
+            if rank > 0:      # same parameters on every rank, a different block of spots
+                data = synthetic.nsf_problem(N=c["N"], M=c["M"], L=c["L"], G=c["G"], E=c["E"], seed=c["seed"] + 1000 + rank,
+                                             coord_scale=c["coord_scale"], lengthscale=c["lengthscale"], jitter=c["jitter"], dtype=dt)
+                for k in ("X", "y", "eps", "V"):
+                    prob[k] = data[k]
+            sl = slice(0, c["N"])
+        else:
+            lo, hi = shard_range(c["N"], world, rank)
+            sl = slice(lo, hi)
+        # host (pinned) copies of this rank's shard: the e2e leg copies them in every step
+        hX_ = prob["X"][sl].contiguous().pin_memory()
+        hy_ = prob["y"][:, sl].contiguous().pin_memory()
+        prob_loc = dict(prob)
+        prob_loc["V"] = prob["V"][sl].contiguous()
+        model_, shared_ = build_model(prob_loc, dt, dev)
+        return model_, shared_, hX_, hy_, hX_.to(dev), hy_.to(dev), prob["eps"][:, :, sl].contiguous().to(dev)
+
+    model, shared, hX, hy, X, y, eps = setup("weak")
+    n_loc = X.shape[0]
     reducer = FlatGradReducer(shared, device=dev, dtype=dt)
 
     def step(Xd, yd, epsd):
@@ -215,12 +230,24 @@ def run_ours(args):
         yd = hy.to(dev, non_blocking=True)
         return float(step(Xd, yd, None))          # eps drawn on the device, loss D2H
 
+    hX_keep = None
     ms_e2e = None
     if not args.no_e2e:
         for _ in range(2):
             e2e_step()
         ms_e2e = timed(e2e_step, max(2, args.steps // 2))
 
+    strong = None
+    if world > 1:
+        # second leg: strong scaling, the 32768 spots of configs[1] split over the ranks (device-resident timing only)
+        del model, shared, X, y, eps, hX_keep
+        torch.cuda.empty_cache()
+        model, shared, _, _, X, y, eps = setup("strong")
+        reducer = FlatGradReducer(shared, device=dev, dtype=dt)
+        for _ in range(3):
+            step(X, y, eps)
+        ms_s = timed(lambda: step(X, y, eps), args.steps)
+        strong = dict(value=1e3 / ms_s, unit="steps/s", ms_per_step=ms_s, spots_per_gpu=int(X.shape[0]), global_spots=c["N"])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -259,14 +286,18 @@ def run_ours(args):
         roofline = dict(kernel=dom["kernel"], bound=dom["bound"], achieved=dom["achieved"], peak=dom["peak"], unit=dom["unit"],
                         frac=dom["frac"], traffic=None, peak_source=pk["src"] + (" (bf16 dense, sustained)" if dom["bound"] == "tensor" else ""))
     h2d = hX.numel() * 4 + hy.numel() * 4
-    line = dict(metric=METRIC, value=1e3 / ms, unit="steps/s", n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
-                ms_per_step=ms, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload="NSF2(SVGP(NSF_RBF)) N=32768 M=1024 L=10 G=2000 E=1 (BASELINE.json configs[1])",
-                            spots_per_gpu=n_loc, parallelism=f"dp{world} over spots", l2="inputs larger than L2 (y 262 MB, Kzx 1.3 GB)",
-                            inducing="jittered 32x32 grid"),
+    # value: 32768-spot ELBO steps per second summed over the ranks (weak scaling: every GPU runs configs[1]'s 32768 spots per step
+    # and the shared gradients are all-reduced, i.e. the global minibatch is world x 32768 spots)
+    line = dict(metric=METRIC, value=world * 1e3 / ms, unit="steps/s", n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
+                ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload="NSF2(SVGP(NSF_RBF)) N=32768 M=1024 L=10 G=2000 E=1 (BASELINE.json configs[1]) per GPU",
+                            spots_per_gpu=n_loc, global_spots=n_loc * world, parallelism=f"dp{world} over spots, 1 NCCL all-reduce/step",
+                            l2="inputs larger than L2 (y 262 MB, Kzx 1.3 GB)", inducing="jittered 32x32 grid"),
                 clocks=clocks, gpu_launches=int(launches),
-                e2e=(dict(value=1e3 / ms_e2e, unit="steps/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4) if ms_e2e else None),
+                e2e=(dict(value=world * 1e3 / ms_e2e, unit="steps/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4) if ms_e2e else None),
                 roofline=roofline, kernels=kernels, per_call_ms=per_call)
+    if strong is not None:
+        line["strong"] = strong
     if world == 1 and not args.no_cpu_baseline:
         full, cores, note = cpu_reference_full_step(1, 1)
         line["cpu_baseline"] = dict(value=1.0 / full, unit="steps/s", cores=cores, kind="port", sample=note)

@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(KB_THREADS) kbuild_fwd_kernel(const KBArgs<T> 
 //   g_x1[i,:]  -= sum_{l,j} G K0 (x1_i - x2_j)/(ls^2 den) ;  g_x2[j,:] += same
 // One CTA covers KB_ROWS rows x (KB_THREADS*4) columns; the L accumulators live in registers.
 template <typename T, bool MG, bool ALIGNED, int LMAX>
-__global__ void __launch_bounds__(KB_THREADS) kbuild_bwd_kernel(const KBArgs<T> a, const T* __restrict__ G, int l0, int Lc,
+__global__ void __launch_bounds__(KB_THREADS, (sizeof(T) == 4 && LMAX <= 12) ? 2 : 1) kbuild_bwd_kernel(const KBArgs<T> a, const T* __restrict__ G, int l0, int Lc,
                                                                  double* __restrict__ g_x1, T* __restrict__ g_x2,
                                                                  double* __restrict__ g_sigma, double* __restrict__ g_ls,
                                                                  double* __restrict__ g_a) {
@@ -326,7 +326,7 @@ int kbuild_bwd(const KBArgs<T>& a, const T* G, T* g_x1, T* g_x2, T* g_sigma, T* 
   if (a.n1 > 0 && a.n2 > 0) {
     const bool al = (a.n2 % KB_VEC == 0) && ((reinterpret_cast<uintptr_t>(G) & 31) == 0);
     dim3 grid((unsigned)cdiv(a.n2, (int64_t)KB_THREADS * KB_VEC), (unsigned)cdiv(a.n1, KB_ROWS));
-    const int lmax = a.L <= 4 ? 4 : (a.L <= 8 ? 8 : (a.L <= 16 ? 16 : KB_LMAX));
+    const int lmax = a.L <= 4 ? 4 : (a.L <= 8 ? 8 : (a.L <= 12 ? 12 : (a.L <= 16 ? 16 : KB_LMAX)));
     for (int l0 = 0; l0 < a.L; l0 += lmax) {
       const int Lc = min(lmax, a.L - l0);
       // g_x1/g_x2 accumulate over all l-chunks (atomics), so every chunk launch adds its share
@@ -339,6 +339,7 @@ int kbuild_bwd(const KBArgs<T>& a, const T* G, T* g_x1, T* g_x2, T* g_sigma, T* 
   } while (0)
       if (lmax == 4) GPZ_KB_DISPATCH(4);
       else if (lmax == 8) GPZ_KB_DISPATCH(8);
+      else if (lmax == 12) GPZ_KB_DISPATCH(12);
       else if (lmax == 16) GPZ_KB_DISPATCH(16);
       else GPZ_KB_DISPATCH(KB_LMAX);
 #undef GPZ_KB_DISPATCH

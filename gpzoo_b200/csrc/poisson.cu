@@ -41,6 +41,22 @@ template <typename T> struct PoissonArgs {
   int atomic_out;                      // gridDim.y > 1
 };
 
+// 16-byte vector loads of an FMAX-long shared-memory row (FMAX is a multiple of 4, rows are 16-byte aligned)
+template <int FMAX> __device__ __forceinline__ void load_row(const float* p, float (&o)[FMAX]) {
+#pragma unroll
+  for (int i = 0; i < FMAX / 4; ++i) {
+    const float4 v = reinterpret_cast<const float4*>(p)[i];
+    o[4 * i] = v.x; o[4 * i + 1] = v.y; o[4 * i + 2] = v.z; o[4 * i + 3] = v.w;
+  }
+}
+template <int FMAX> __device__ __forceinline__ void load_row(const double* p, double (&o)[FMAX]) {
+#pragma unroll
+  for (int i = 0; i < FMAX / 2; ++i) {
+    const double2 v = reinterpret_cast<const double2*>(p)[i];
+    o[2 * i] = v.x; o[2 * i + 1] = v.y;
+  }
+}
+
 template <typename T, int FMAX>
 __global__ void __launch_bounds__(PZ_SPOTS, sizeof(T) == 4 ? 3 : 1) poisson_kernel(const PoissonArgs<T> a) {
   extern __shared__ __align__(16) unsigned char pz_smem[];
@@ -132,9 +148,11 @@ __global__ void __launch_bounds__(PZ_SPOTS, sizeof(T) == 4 ? 3 : 1) poisson_kern
           T t = T(0);
           if (!GUARD || (active && g0 + gi < g_end)) {
             const T y = yv[u];
+            T wrow[FMAX];
+            load_row<FMAX>(&sW[gi][0], wrow);
             T zr = T(0);
 #pragma unroll
-            for (int f = 0; f < FMAX; ++f) zr = fma(sW[gi][f], ef[f], zr);
+            for (int f = 0; f < FMAX; ++f) zr = fma(wrow[f], ef[f], zr);
             const T r = spV * zr;
             const T ylog = y * fast_log(r);
             T lp = (y == T(0) ? T(0) : ylog) - r;
@@ -143,7 +161,7 @@ __global__ void __launch_bounds__(PZ_SPOTS, sizeof(T) == 4 ? 3 : 1) poisson_kern
             t = (fast_div(y, zr) - spV) * invE;
             gVacc += y - r;
 #pragma unroll
-            for (int f = 0; f < FMAX; ++f) pg[f] = fma(sW[gi][f], t, pg[f]);
+            for (int f = 0; f < FMAX; ++f) pg[f] = fma(wrow[f], t, pg[f]);
           }
           tS[gi][tid] = t;
         };
@@ -170,8 +188,10 @@ __global__ void __launch_bounds__(PZ_SPOTS, sizeof(T) == 4 ? 3 : 1) poisson_kern
 #pragma unroll 4
       for (int k = 0; k < 32; ++k) {
         const T t = tS[lane][nb + k];
+        T erow[FMAX];
+        load_row<FMAX>(&efS[nb + k][0], erow);
 #pragma unroll
-        for (int f = 0; f < FMAX; ++f) acc[f] = fma(t, efS[nb + k][f], acc[f]);
+        for (int f = 0; f < FMAX; ++f) acc[f] = fma(t, erow[f], acc[f]);
       }
     }
 #pragma unroll
