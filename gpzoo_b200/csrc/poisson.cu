@@ -269,7 +269,11 @@ static void poisson_grid(int G, int B, int* nbx, int* nby, int* gpc) {
 template <typename T>
 int poisson_fwdbwd(PoissonArgs<T> a, T* gW, double* ll_out, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (a.F < 1 || a.F > 32 || a.E < 1 || a.G < 1) return GPZ_ERR_UNSUPPORTED;
-  if (a.B == 0) return GPZ_OK;
+  if (a.B == 0) {                       // empty minibatch: ll = 0, no gradient
+    GPZ_CUDA(cudaMemsetAsync(ll_out, 0, sizeof(double), st));
+    GPZ_CUDA(cudaMemsetAsync(gW, 0, sizeof(T) * (size_t)a.G * a.F, st));
+    return GPZ_OK;
+  }
   int nbx, nby, gpc;
   poisson_grid(a.G, a.B, &nbx, &nby, &gpc);
   const size_t need = sizeof(double) * ((size_t)nbx * nby + 2) + sizeof(T) * (size_t)nbx * a.G * a.F;

@@ -270,3 +270,37 @@ def test_hybrid_raw_loadings_elbo_matches_dropin():
     pY, qF, qU, pU, qF2, pF2 = model(prob["X"], E=2, eps=prob["eps"], eps2=eps2)
     ref = pY.log_prob(prob["y"]).mean(0).sum() - distributions.kl_divergence(qU, pU).sum() - distributions.kl_divergence(qF2, pF2).sum()
     assert relerr(fused, ref) < 1e-10
+
+
+def test_tensor_core_step_matches_fp64_midsize():
+    """The fp32 tensor-core (tcgen05 split-TF32) step against the fp64 CUDA-core step of the same model at a size the CPU
+    oracle would need minutes for (N=4096, M=256, L=4, G=256): ELBO and every gradient within the fp32 tolerance."""
+    from gpzoo_b200 import synthetic
+    prob = synthetic.nsf_problem(N=4096, M=256, L=4, G=256, E=1, seed=6, coord_scale=100.0, lengthscale=9.0, jitter=1e-1)
+    res = {}
+    for dt in (torch.float64, torch.float32):
+        model, named = build_nsf(prob, dt)
+        elbo = model.elbo(prob["X"].to(DEV, dt), prob["y"].to(DEV, dt), E=1, eps=prob["eps"].to(DEV, dt))
+        elbo.backward()
+        res[dt] = dict(elbo=elbo.detach(), **{k: v.grad.clone() for k, v in named.items()})
+    for k in res[torch.float64]:
+        assert relerr(res[torch.float32][k], res[torch.float64][k]) < 1e-4, k
+
+
+def test_ragged_and_degenerate_sizes():
+    """Edge cases: N not a multiple of any tile (ragged), a single spot, an empty minibatch, M below every block size."""
+    import gpzoo_b200 as gz
+    from gpzoo_b200 import synthetic
+    dt = torch.float64
+    prob = synthetic.nsf_problem(N=131, M=7, L=2, G=5, E=2, seed=8, coord_scale=2.0, jitter=1e-2, dtype=dt, device=DEV)
+    model, named = build_nsf(prob, dt)
+    full = model.elbo(prob["X"], prob["y"], E=2, eps=prob["eps"], return_parts=True)[1]
+    # sum over single-spot minibatches of the likelihood term == full likelihood term
+    idx1 = torch.tensor([17], device=DEV)
+    one = model.elbo(prob["X"], prob["y"], idx=idx1, E=2, eps=prob["eps"][:, :, idx1], return_parts=True)[1]
+    rest = torch.tensor([i for i in range(131) if i != 17], device=DEV)
+    oth = model.elbo(prob["X"], prob["y"], idx=rest, E=2, eps=prob["eps"][:, :, rest], return_parts=True)[1]
+    assert relerr(one["ll"] + oth["ll"], full["ll"]) < 1e-11
+    empty = torch.zeros(0, dtype=torch.int64, device=DEV)
+    e0 = model.elbo(prob["X"], prob["y"], idx=empty, E=2, eps=prob["eps"][:, :, empty], return_parts=True)[1]
+    assert float(e0["ll"]) == 0.0 and relerr(e0["kl"], full["kl"]) < 1e-12
