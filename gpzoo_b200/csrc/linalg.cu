@@ -7,6 +7,10 @@
 //   (1) potf2: factor the NB x NB diagonal block in shared memory (one CTA per factor l)
 //   (2) trsm : L21 = A21 L11^-T, one thread per row, panel staged through shared memory
 //   (3) syrk : A22 -= L21 L21^T  -- the only O(M^3) part; a GEMM (gemm_simt.cuh / tcgen05 path)
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+
 #include "gemm_simt.cuh"
 #include "gpzoo_b200.h"
 
@@ -168,19 +172,15 @@ template <typename T> int trtri(const T* Lc, T* X, T* tmp, int M, int L, cudaStr
 //     (L11, X11) = rec(A11);  L21 = A21 X11^T;  A22 -= L21 L21^T;  (L22, X22) = rec(A22);  X21 = -X22 (L21 X11)
 // so all O(M^3) work is GEMMs (4 per internal node) and the only sequential kernel is the 64 x 64 leaf below, which
 // factors AND inverts its block in shared memory with 16-wide sub-blocking (a dozen block barriers instead of 128).
+// Factor and invert the n x n (n <= 64) diagonal block at (r0, r0) of one factor: W (input, lower), Lm and X (outputs).
+// `a`, `x`: two [NB][NB+1] shared-memory tiles.  256 threads; contains block barriers.
 template <typename T>
-__global__ void __launch_bounds__(256) chol_inv_leaf_kernel(const T* __restrict__ Wall, T* __restrict__ Lall, T* __restrict__ Xall,
-                                                             int M, int r0, int n, int* __restrict__ info) {
+__device__ void leaf_body(T (*a)[NB + 1], T (*x)[NB + 1], const T* __restrict__ W, T* __restrict__ Lm, T* __restrict__ X, int M,
+                          int r0, int n, int* __restrict__ info_l) {
   constexpr int SB = 16;
-  extern __shared__ __align__(16) unsigned char leaf_smem[];
-  typedef T Row[NB + 1];
-  Row* a = reinterpret_cast<Row*>(leaf_smem);
-  Row* x = a + NB;
   __shared__ T sbuf[SB][SB + 1];
   __shared__ T rsd[SB];
-  const int64_t off = (int64_t)blockIdx.x * M * M;
-  const T* W = Wall + off;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   for (int e = tid; e < NB * NB; e += 256) {
     const int i = e / NB, j = e % NB;
     a[i][j] = (i < n && j <= i) ? W[(int64_t)(r0 + i) * M + r0 + j] : T(0);
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(256) chol_inv_leaf_kernel(const T* __restrict_
       for (int j = 0; j < jn; ++j) {
         const T d = a[j0 + j][j0 + j];
         if (tid == 0) {
-          if (!(d > T(0)) && info[blockIdx.x] == 0) info[blockIdx.x] = r0 + j0 + j + 1;
+          if (!(d > T(0)) && *info_l == 0) *info_l = r0 + j0 + j + 1;
           rsd[j] = Num<T>::rsqrt(d);
         }
         if (ti < jn && tk > j && tk <= ti)
@@ -286,8 +286,6 @@ __global__ void __launch_bounds__(256) chol_inv_leaf_kernel(const T* __restrict_
       __syncthreads();
     }
   }
-  T* Lm = Lall + off;
-  T* X = Xall + off;
   for (int e = tid; e < NB * NB; e += 256) {
     const int i = e / NB, j = e % NB;
     if (i < n && j < n) {
@@ -296,6 +294,234 @@ __global__ void __launch_bounds__(256) chol_inv_leaf_kernel(const T* __restrict_
     }
   }
 }
+
+template <typename T>
+__global__ void __launch_bounds__(256) chol_inv_leaf_kernel(const T* __restrict__ Wall, T* __restrict__ Lall, T* __restrict__ Xall,
+                                                             int M, int r0, int n, int* __restrict__ info) {
+  extern __shared__ __align__(16) unsigned char leaf_smem[];
+  typedef T Row[NB + 1];
+  Row* a = reinterpret_cast<Row*>(leaf_smem);
+  Row* x = a + NB;
+  const int64_t off = (int64_t)blockIdx.x * M * M;
+  leaf_body<T>(a, x, Wall + off, Lall + off, Xall + off, M, r0, n, info + blockIdx.x);
+}
+
+// ---- the whole Cholesky + inverse of one factor in ONE kernel: a thread-block cluster of 8 CTAs per factor --------
+// Same right-looking algorithm as chol_inv() below, but the ~60 dependent launches become phases separated by
+// hardware cluster barriers (barrier.cluster, ~0.2 us): leaf on CTA 0 -> panel row blocks over the 8 CTAs -> trailing
+// 64 x 64 tiles over the 8 CTAs; then the doubling inverse tile by tile.  All tile products are 64 x 64 x 64 from
+// shared memory; matrices stay in global memory (L2-resident: 3 x 4 MB per factor).
+constexpr int CL = 8;     // CTAs per cluster
+
+constexpr int TLD = NB + 4;     // padded row length of the k-major operand tiles (keeps 16-byte alignment for vector loads)
+
+// k-major operand tile: dst[t][i] = src[(r0+i)*ld + c0+t]  (transpose == false: rows i of a row-major block, reduction index
+// t along its columns) or dst[t][i] = src[(r0+t)*ld + c0+i] (transpose == true: reduction index along the rows).
+// nr, nc: valid rows / columns of the source block, zero outside.
+template <typename T>
+__device__ __forceinline__ void load_tile(T (*dst)[TLD], const T* __restrict__ src, int64_t ld, int r0, int c0, int nr, int nc,
+                                          bool transpose) {
+#pragma unroll 4
+  for (int e = threadIdx.x; e < NB * NB; e += 256) {
+    const int r = e >> 6, c = e & (NB - 1);           // source row / column inside the block (coalesced along c)
+    const T v = (r < nr && c < nc) ? src[(int64_t)(r0 + r) * ld + c0 + c] : T(0);
+    if (transpose) dst[r][c] = v; else dst[c][r] = v;
+  }
+}
+__device__ __forceinline__ void ld4(const float* p, float (&o)[4]) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+__device__ __forceinline__ void ld4(const double* p, double (&o)[4]) {
+  const double2 v0 = reinterpret_cast<const double2*>(p)[0], v1 = reinterpret_cast<const double2*>(p)[1];
+  o[0] = v0.x; o[1] = v0.y; o[2] = v1.x; o[3] = v1.y;
+}
+// acc[u][v] += sum_t A[t][ty*4+u] * B[t][tx*4+v]   (both operands k-major in shared memory, two vector loads per 16 FMAs)
+template <typename T>
+__device__ __forceinline__ void tile_abt(const T (*A)[TLD], const T (*B)[TLD], T (&acc)[4][4]) {
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+#pragma unroll 8
+  for (int t = 0; t < NB; ++t) {
+    T av[4], bv[4];
+    ld4(&A[t][ty * 4], av);
+    ld4(&B[t][tx * 4], bv);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) acc[u][v] = fma(av[u], bv[v], acc[u][v]);
+  }
+}
+// dst[(r0+i)*ld + c0+j] = alpha*acc + beta*dst  for i < nr, j < nc
+template <typename T>
+__device__ __forceinline__ void store_tile(T* __restrict__ dst, int64_t ld, int r0, int c0, int nr, int nc, const T (&acc)[4][4],
+                                           T alpha, T beta) {
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int i = ty * 4 + u, j = tx * 4 + v;
+      if (i < nr && j < nc) {
+        T* d = dst + (int64_t)(r0 + i) * ld + c0 + j;
+        *d = beta == T(0) ? alpha * acc[u][v] : alpha * acc[u][v] + beta * (*d);
+      }
+    }
+}
+
+// One phase of the cluster kernel = a list of tile-product steps (block coordinates gi, gj, gk + first/last flags of the
+// output tile), built by thread 0 in shared memory.  run_steps() executes the list with a register-staged pipeline: the 32
+// global loads of step s+1 are in flight while step s is multiplied out of shared memory.
+//   A operand: MA[gi][gk];  B operand: MB[gj][gk] (b_tr = false) or MB[gk][gj] (b_tr = true);  out: MO[gi][gj] = alpha*acc + beta*MO
+constexpr int MAX_STEPS = 192;
+
+template <typename T>
+__device__ void run_steps(T (*tA)[TLD], T (*tB)[TLD], const int4* __restrict__ steps, int nsteps, const T* __restrict__ MA,
+                          const T* __restrict__ MB, T* __restrict__ MO, bool b_tr, T alpha, T beta, int M) {
+  const int tid = threadIdx.x;
+  auto bsz = [&](int b) { return min(NB, M - b * NB); };
+  T ra[16], rb[16];
+  auto fetch = [&](int sidx) {
+    const int4 st = steps[sidx];
+    const int ar0 = st.x * NB, ac0 = st.z * NB, anr = bsz(st.x), anc = bsz(st.z);
+    const int br0 = (b_tr ? st.z : st.y) * NB, bc0 = (b_tr ? st.y : st.z) * NB;
+    const int bnr = bsz(b_tr ? st.z : st.y), bnc = bsz(b_tr ? st.y : st.z);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int e = tid + u * 256, r = e >> 6, c = e & (NB - 1);
+      ra[u] = (r < anr && c < anc) ? MA[(int64_t)(ar0 + r) * M + ac0 + c] : T(0);
+      rb[u] = (r < bnr && c < bnc) ? MB[(int64_t)(br0 + r) * M + bc0 + c] : T(0);
+    }
+  };
+  if (nsteps <= 0) return;
+  fetch(0);
+  T acc[4][4];
+  for (int sidx = 0; sidx < nsteps; ++sidx) {
+    const int4 st = steps[sidx];
+    __syncthreads();                                   // previous product finished reading the tiles
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int e = tid + u * 256, r = e >> 6, c = e & (NB - 1);
+      tA[c][r] = ra[u];                               // k-major: [t][i]
+      if (b_tr) tB[r][c] = rb[u]; else tB[c][r] = rb[u];
+    }
+    __syncthreads();
+    if (sidx + 1 < nsteps) fetch(sidx + 1);            // next step's loads overlap this step's FMAs
+    if (st.w & 1) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = T(0);
+    }
+    tile_abt<T>(tA, tB, acc);
+    if (st.w & 2) store_tile<T>(MO, M, st.x * NB, st.y * NB, bsz(st.x), bsz(st.y), acc, alpha, beta);
+  }
+}
+
+template <typename T>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256)
+chol_inv_cluster_kernel(T* __restrict__ Wall, T* __restrict__ Lall, T* __restrict__ Xall, T* __restrict__ Tall, int M,
+                        int* __restrict__ info, long long* __restrict__ dbg) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) unsigned char cl_smem[];
+  typedef T Row[TLD];
+  typedef T LeafRow[NB + 1];
+  Row* tA = reinterpret_cast<Row*>(cl_smem);
+  Row* tB = tA + NB;
+  LeafRow* la = reinterpret_cast<LeafRow*>(cl_smem);            // the leaf uses the same memory with its own row length
+  LeafRow* lx = la + NB;
+  __shared__ int4 steps[MAX_STEPS];
+  __shared__ int nsteps_s, q_next_s;
+  const int l = blockIdx.x / CL, rank = (int)cluster.block_rank();
+  const int64_t off = (int64_t)l * M * M;
+  T* W = Wall + off; T* Lm = Lall + off; T* X = Xall + off; T* Tm = Tall + off;
+  const int nblk = (M + NB - 1) / NB;
+  auto bsz = [&](int b) { return min(NB, M - b * NB); };
+
+  long long t_leaf = 0, t_panel = 0, t_trail = 0, t_inv = 0, t0 = clock64(), t1;
+  // ---- factorisation ----
+  for (int k = 0; k < nblk; ++k) {
+    const int k0 = k * NB, nb = bsz(k);
+    if (rank == 0) leaf_body<T>(la, lx, W, Lm, X, M, k0, nb, info + l);
+    cluster.sync();
+    t1 = clock64(); t_leaf += t1 - t0; t0 = t1;
+    const int nrb = nblk - k - 1;                       // row blocks below the diagonal block
+    if (nrb > 0) {
+      // panel: L21 = W21 X11^T      (A = W[gi][k], B = X[k][k], out = Lc[gi][k])
+      if (threadIdx.x == 0) {
+        int ns = 0;
+        for (int rb = rank; rb < nrb; rb += CL) steps[ns++] = make_int4(k + 1 + rb, k, k, 3);
+        nsteps_s = ns;
+      }
+      __syncthreads();
+      run_steps<T>(tA, tB, steps, nsteps_s, W, X, Lm, false, T(1), T(0), M);
+      cluster.sync();
+      t1 = clock64(); t_panel += t1 - t0; t0 = t1;
+      // trailing update of the lower triangle: W[gi][gj] -= Lc[gi][k] Lc[gj][k]^T   (in rounds of at most MAX_STEPS tiles)
+      for (int q_start = 0; q_start >= 0;) {
+        if (threadIdx.x == 0) {
+          int ns = 0, q = 0, q_next = -1;
+          for (int bi = 0; bi < nrb && q_next < 0; ++bi)
+            for (int bj = 0; bj <= bi; ++bj, ++q) {
+              if (q < q_start || q % CL != rank) continue;
+              if (ns == MAX_STEPS) { q_next = q; break; }
+              steps[ns++] = make_int4(k + 1 + bi, k + 1 + bj, k, 3);
+            }
+          nsteps_s = ns;
+          q_next_s = q_next;
+        }
+        __syncthreads();
+        const int ns = nsteps_s, qn = q_next_s;
+        run_steps<T>(tA, tB, steps, ns, Lm, Lm, W, false, T(-1), T(1), M);
+        __syncthreads();
+        q_start = qn;
+      }
+      cluster.sync();
+      t1 = clock64(); t_trail += t1 - t0; t0 = t1;
+    }
+  }
+  // ---- inverse by recursive doubling, tile by tile:  tmp21 = L21 X11 ;  X21 = -X22 tmp21 ----
+  for (int b = 1; b < nblk; b *= 2) {                      // b = blocks per half
+    const int npair = (nblk + 2 * b - 1) / (2 * b);
+    for (int stage = 0; stage < 2; ++stage) {
+      // the per-CTA step list can exceed MAX_STEPS at large M: process it in rounds
+      for (int q_start = 0; q_start >= 0;) {
+        if (threadIdx.x == 0) {
+          int ns = 0, q = 0, q_next = -1;
+          for (int p = 0; p < npair && q_next < 0; ++p) {
+            const int f0 = p * 2 * b;
+            const int n2 = min(b, nblk - f0 - b);
+            if (n2 <= 0) continue;
+            for (int ti = 0; ti < n2 && q_next < 0; ++ti)
+              for (int tj = 0; tj < b; ++tj, ++q) {
+                if (q < q_start || q % CL != rank) continue;
+                // stage 0: sum_{tk=tj}^{b-1} L[gi][f0+tk] X[f0+tk][gj];  stage 1: sum_{tk=0}^{ti} X[gi][f0+b+tk] tmp[f0+b+tk][gj]
+                const int t_lo = stage == 0 ? tj : 0, t_hi = stage == 0 ? b - 1 : ti;
+                if (ns + (t_hi - t_lo + 1) > MAX_STEPS) { q_next = q; break; }
+                for (int tk = t_lo; tk <= t_hi; ++tk)
+                  steps[ns++] = make_int4(f0 + b + ti, f0 + tj, stage == 0 ? f0 + tk : f0 + b + tk,
+                                          (tk == t_lo ? 1 : 0) | (tk == t_hi ? 2 : 0));
+              }
+          }
+          nsteps_s = ns;
+          q_next_s = q_next;
+        }
+        __syncthreads();
+        const int ns = nsteps_s, qn = q_next_s;
+        if (stage == 0) run_steps<T>(tA, tB, steps, ns, Lm, X, Tm, true, T(1), T(0), M);
+        else run_steps<T>(tA, tB, steps, ns, X, Tm, X, true, T(-1), T(0), M);
+        __syncthreads();
+        q_start = qn;
+      }
+      cluster.sync();
+    }
+  }
+  t1 = clock64(); t_inv = t1 - t0;
+  if (dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0) { dbg[0] = t_leaf; dbg[1] = t_panel; dbg[2] = t_trail; dbg[3] = t_inv; }
+}
+
+long long* g_chol_dbg = nullptr;
+extern "C" void gpz_chol_debug_(long long* p) { g_chol_dbg = p; }
 
 template <typename T>
 static int chol_inv_rec(T* W, T* Lc, T* X, T* tmp, int M, int L, int r0, int n, int* info, cudaStream_t st) {
@@ -349,6 +575,17 @@ template <typename T> int chol_inv(T* W, T* Lc, T* X, T* tmp, int M, int L, int*
   GPZ_CUDA(cudaMemsetAsync(Lc, 0, sizeof(T) * sL * L, st));
   GPZ_CUDA(cudaMemsetAsync(X, 0, sizeof(T) * sL * L, st));
   constexpr int smem = (int)(2 * NB * (NB + 1) * sizeof(T));
+  static int use_cluster = -1;
+  if (use_cluster < 0) { const char* e = getenv("GPZ_CHOL_CLUSTER"); use_cluster = e ? atoi(e) : 1; }
+  // one cluster kernel while the chain is latency-bound (M <= 1536); beyond that the O(M^3) trailing updates dominate and
+  // the multi-launch path below, whose GEMMs use the whole GPU, is faster (measured: M = 2048 23.8 vs 26.7 ms/step)
+  if (use_cluster && M <= 1536) {
+    constexpr int csmem = (int)(2 * NB * TLD * sizeof(T));
+    GPZ_CUDA(cudaFuncSetAttribute(chol_inv_cluster_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, csmem));
+    chol_inv_cluster_kernel<T><<<L * CL, 256, csmem, st>>>(W, Lc, X, tmp, M, info, g_chol_dbg);
+    GPZ_CHECK_LAUNCH();
+    return GPZ_OK;
+  }
   GPZ_CUDA(cudaFuncSetAttribute(chol_inv_leaf_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   for (int k0 = 0; k0 < M; k0 += NB) {
     const int nb = min(NB, M - k0);

@@ -46,7 +46,7 @@ def test_gemm_triangular_flags(dt):
 
 
 @pytest.mark.parametrize("dt", [torch.float64, torch.float32])
-@pytest.mark.parametrize("M", [25, 64, 200, 515])
+@pytest.mark.parametrize("M", [25, 64, 200, 515, 1100])
 def test_cholesky_and_inverse(dt, M):
     from gpzoo_b200 import functional as F
     g = torch.Generator().manual_seed(M)
