@@ -90,6 +90,23 @@ __global__ void __launch_bounds__(256) rowdot_kernel(const T* __restrict__ A, co
   if (threadIdx.x == 0) out[(int64_t)l * M + m] = acc;
 }
 
+// out[l,j] = sum_k A[l,k,j] v[l,k]      (A^T v for row-major A: one thread per column, rows streamed coalesced)
+template <typename T>
+__global__ void __launch_bounds__(256) coldot_kernel(const T* __restrict__ A, const T* __restrict__ v, T* __restrict__ out, int K, int N) {
+  const int l = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  const T* a = A + (int64_t)l * K * N + j;
+  const T* vv = v + (int64_t)l * K;
+  T acc0 = T(0), acc1 = T(0);
+  int k = 0;
+  for (; k + 1 < K; k += 2) {
+    acc0 = fma(a[(int64_t)k * N], vv[k], acc0);
+    acc1 = fma(a[(int64_t)(k + 1) * N], vv[k + 1], acc1);
+  }
+  if (k < K) acc0 = fma(a[(int64_t)k * N], vv[k], acc0);
+  out[(int64_t)l * N + j] = acc0 + acc1;
+}
+
 template <typename T>
 int predict_fwd(const T* Kzx, const T* Linv, const T* Tm, const T* q, const T* kxx, T* A, T* C, T* mean, T* var,
                 int M, int N, int L, cudaStream_t st) {
@@ -266,3 +283,16 @@ extern "C" int gpz_svgp_predict_bwd_tc_f32(const float* Kzx, const float* Kzx_lo
 
 GPZ_PREDICT_IMPL(f32, float)
 GPZ_PREDICT_IMPL(f64, double)
+
+// batched matrix-vector products: trans == 0: out[l,i] = sum_k A[l,i,k] v[l,k] (A: rows x cols);  trans != 0: out[l,j] = sum_k A[l,k,j] v[l,k]
+#define GPZ_GEMV_IMPL(SUF, T)                                                                                         \
+  extern "C" int gpz_gemv_##SUF(int trans, const T* A, const T* v, T* out, int rows, int cols, int L, void* stream) { \
+    if (rows <= 0 || cols <= 0 || L <= 0) return GPZ_OK;                                                              \
+    cudaStream_t st = (cudaStream_t)stream;                                                                           \
+    if (!trans) rowdot_kernel<T><<<dim3(rows, L), 256, 0, st>>>(A, v, out, rows, cols);                               \
+    else coldot_kernel<T><<<dim3((unsigned)cdiv(cols, 256), L), 256, 0, st>>>(A, v, out, rows, cols);                 \
+    GPZ_CHECK_LAUNCH();                                                                                               \
+    return GPZ_OK;                                                                                                    \
+  }
+GPZ_GEMV_IMPL(f32, float)
+GPZ_GEMV_IMPL(f64, double)

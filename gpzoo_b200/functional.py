@@ -77,9 +77,21 @@ def gemm(A, B, ta=False, tb=False, alpha=1.0, beta=0.0, out=None, a_tri=0, b_tri
 def transpose_lo(x):
     """(x^T, lo(x^T)) per matrix of a batch of square fp32 matrices."""
     x = _c(x)
-    xt, xt_lo = torch.empty_like(x), torch.empty_like(x)
-    call("transpose_lo", torch.float32, ptr(x), ptr(xt), ptr(xt_lo), c_i(x.shape[-1]), c_i(x.shape[0]))
-    return xt, xt_lo
+
+    def make():
+        xt, xt_lo = torch.empty_like(x), torch.empty_like(x)
+        call("transpose_lo", torch.float32, ptr(x), ptr(xt), ptr(xt_lo), c_i(x.shape[-1]), c_i(x.shape[0]))
+        return xt, xt_lo
+    return _cached("T", x, make)
+
+
+def gemv(A, v, trans=False):
+    """out[l] = A[l] v[l] (trans=False) or A[l]^T v[l]; A: (L, rows, cols), v: (L, cols) or (L, rows)."""
+    A, v = _c(A), _c(v)
+    L, rows, cols = A.shape
+    out = torch.empty((L, cols if trans else rows), dtype=A.dtype, device=A.device)
+    call("gemv", A.dtype, c_i(int(trans)), ptr(A), ptr(v), ptr(out), c_i(rows), c_i(cols), c_i(L))
+    return out
 
 
 def tri_op(X, mode, out=None):
@@ -220,7 +232,7 @@ class Whiten(Function):
     def forward(ctx, Linv, Lu, mu):
         Linv, Lu, mu = _c(Linv), _c(Lu), _c(mu)
         T = gemm(Linv, Lu, a_tri=1, b_tri=1, d_tri=1)
-        q = gemm(Linv, mu.unsqueeze(-1), a_tri=1).squeeze(-1)
+        q = gemv(Linv, mu)
         ctx.save_for_backward(Linv, Lu, mu)
         return T, q
 
@@ -237,7 +249,7 @@ class Whiten(Function):
         if gq is not None:
             gq = _c(gq).unsqueeze(-1)
             gemm(gq, mu.unsqueeze(-1), tb=True, beta=1.0, out=gLinv, d_tri=1)
-            gmu = gemm(Linv, gq, ta=True, a_tri=2).squeeze(-1)
+            gmu = gemv(Linv, gq.squeeze(-1), trans=True)
         return gLinv, gLu, gmu
 
 
@@ -321,11 +333,35 @@ def umma_gemm(A, B, b_kmajor, Alo=None, Blo=None, Cin=None, alpha=1.0, want_lo=F
     return (D, Dlo) if want_lo else D
 
 
+# (x, lo) planes and transposes of the M x M operands are needed by several GEMMs of one step (Linv: whitening, predict,
+# Cholesky backward ...).  They are cached per source tensor for the duration of a step; the cache holds a reference to the
+# source so its memory cannot be recycled under the same key, and `clear_step_cache()` runs at the start of every step.
+_step_cache = {}
+
+
+def clear_step_cache():
+    _step_cache.clear()
+
+
+def _cached(kind, x, make):
+    key = (kind, x.data_ptr(), x._version, tuple(x.shape))
+    hit = _step_cache.get(key)
+    if hit is None:
+        if len(_step_cache) > 64:
+            _step_cache.clear()
+        hit = (make(), x)
+        _step_cache[key] = hit
+    return hit[0]
+
+
 def tf32_lo(x):
     x = _c(x)
-    lo = torch.empty_like(x)
-    call("tf32_lo", torch.float32, ptr(x), ptr(lo), c_i64(x.numel()))
-    return lo
+
+    def make():
+        lo = torch.empty_like(x)
+        call("tf32_lo", torch.float32, ptr(x), ptr(lo), c_i64(x.numel()))
+        return lo
+    return _cached("lo", x, make) if x.dim() == 3 and x.shape[-1] == x.shape[-2] else make()
 
 
 # ------------------------------------------------------------------------------------------------

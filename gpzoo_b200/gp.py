@@ -91,6 +91,7 @@ class _SparseGPBase(nn.Module):
 
     def moments(self, X, groupsX=None):
         """Fused predictive moments: returns dict(mean, var (unclamped), T, q, Lc, Lu), all L-batched."""
+        F.clear_step_cache()
         want_lo = F.tensor_core_predict_ok(X.dtype, self.Z.shape[0], X.shape[0])
         Kxx, Kzx, Kzz = self._kernel_matrices(X, groupsX, want_lo)
         Kzx_lo = None
@@ -233,6 +234,7 @@ class VNNGP(_SparseGPBase):
 
     def moments(self, X, groupsX=None):
         dt = X.dtype
+        F.clear_step_cache()
         Kzz = _as3(self.kernel(self.Z, self.Z, _jitter=self.jitter))                 # first jitter (gp.py:55)
         Kxx = self.kernel(X, X, diag=True)
         Kxx = Kxx if Kxx.dim() == 2 else Kxx.unsqueeze(0)

@@ -74,6 +74,10 @@ int gpz_gemm_f32(int ta, int tb, int m, int n, int k, float alpha, const float* 
 int gpz_gemm_f64(int ta, int tb, int m, int n, int k, double alpha, const double* A, int64_t lda, int64_t sA,
                  const double* B, int64_t ldb, int64_t sB, double beta, double* D, int64_t ldd, int64_t sD, int batch,
                  int a_tri, int b_tri, int d_tri, int splitk, void* stream);
+/* batched matrix-vector products (q = Lc^-1 mu and its backward; torch kl.py _batch_mahalanobis's solve):
+ * trans == 0: out[l,i] = sum_k A[l,i,k] v[l,k];  trans != 0: out[l,j] = sum_k A[l,k,j] v[l,k];  A is L x rows x cols */
+int gpz_gemv_f32(int trans, const float* A, const float* v, float* out, int rows, int cols, int L, void* stream);
+int gpz_gemv_f64(int trans, const double* A, const double* v, double* out, int rows, int cols, int L, void* stream);
 /* gp.py:220 transform_to(lower_cholesky): out = tril(raw,-1) + diag(exp(diag raw)), and its backward */
 int gpz_lower_cholesky_fwd_f32(const float* raw, float* out, int M, int L, void* stream);
 int gpz_lower_cholesky_fwd_f64(const double* raw, double* out, int M, int L, void* stream);
