@@ -12,6 +12,7 @@
 // parks t in shared memory.  Phase B (lane = gene, warp = quarter of the spots): the gW[g,f] partial
 // sum_n t[g,n] exp(F)[f,n] from shared memory.  Per-CTA gW partials go to a workspace slice and are
 // summed by a second tiny kernel (deterministic, no atomics on the G x F output).
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -226,6 +227,200 @@ __global__ void __launch_bounds__(PZ_SPOTS, sizeof(T) == 4 ? 3 : 1) poisson_kern
   if (tid == 0) a.ll_part[blockIdx.y * gridDim.x + blockIdx.x] = tot;
 }
 
+// ---- v2: two spots per thread (256 spots per CTA), sample loop outermost ---------------------------------------------
+// Same two-phase scheme, restructured for instruction count and occupancy (the kernel is FMA-issue bound, not HBM bound):
+// each softplus(W) row fetched from shared memory serves two spots; per-thread state is only exp(F) and the d/dF
+// accumulator of the current sample (the E samples are an outer loop; y is re-read per sample, from L2 when it fits).
+constexpr int P2_THREADS = 128, P2_SPOTS = 256;
+constexpr int PZ_GRP = 4;        // genes per prefetch group
+
+template <typename T, int FMAX>
+__global__ void __launch_bounds__(P2_THREADS, sizeof(T) == 4 ? 4 : 1) poisson_kernel2(const PoissonArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char pz_smem[];
+  typedef T RowT[P2_SPOTS + 1];
+  typedef T RowF[FMAX];
+  typedef T AccW[PZ_GCH][FMAX];
+  RowT* tS = reinterpret_cast<RowT*>(pz_smem);                         // [PZ_GCH][P2_SPOTS+1]   t = d ll / d zr
+  RowF* efS = reinterpret_cast<RowF*>(reinterpret_cast<unsigned char*>(pz_smem) +
+                                      ((sizeof(T) * PZ_GCH * (P2_SPOTS + 1) + 15) / 16) * 16);   // [P2_SPOTS][FMAX]
+  RowF* sW = efS + P2_SPOTS;                                           // [PZ_GCH][FMAX]
+  AccW* sAcc = reinterpret_cast<AccW*>(sW + PZ_GCH);                   // [4][PZ_GCH][FMAX]
+  __shared__ double red[32];
+  __shared__ T lfact[64];                     // log(y!) for integer counts y < 64 (lgamma(y+1) of torch poisson.py log_prob)
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 64) lfact[tid] = Num<T>::lgamma(T(tid + 1));
+  const int n0 = blockIdx.x * P2_SPOTS;
+  int nn[2]; bool act[2]; int64_t col[2]; T spV[2], vraw[2], gVacc[2];
+#pragma unroll
+  for (int s2 = 0; s2 < 2; ++s2) {
+    nn[s2] = n0 + s2 * P2_THREADS + tid;
+    act[s2] = nn[s2] < a.B;
+    col[s2] = act[s2] ? (a.idx ? a.idx[nn[s2]] : (int64_t)nn[s2]) : 0;
+    vraw[s2] = act[s2] ? a.V[col[s2]] : T(0);
+    spV[s2] = act[s2] ? softplus(vraw[s2]) : T(0);
+    gVacc[s2] = T(0);
+  }
+  const bool block_full = n0 + P2_SPOTS <= a.B;
+  const T invE = T(1) / T(a.E);
+  const int g_begin = blockIdx.y * a.genes_per_cta;
+  const int g_end = min(a.G, g_begin + a.genes_per_cta);
+  double ll = 0.0;
+
+  T ynext[PZ_GRP][2];
+  auto prefetch = [&](int gfirst) {
+#pragma unroll
+    for (int u = 0; u < PZ_GRP; ++u)
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2)
+        ynext[u][s2] = (act[s2] && gfirst + u < g_end) ? __ldcs(a.y + (int64_t)(gfirst + u) * a.y_ld + col[s2]) : T(0);
+  };
+  prefetch(g_begin);
+
+  for (int e = 0; e < a.E; ++e) {
+    T ef[2][FMAX], pg[2][FMAX];
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+      for (int f = 0; f < FMAX; ++f) {
+        pg[s2][f] = T(0);
+        T v = T(0);
+        if (f < a.F && act[s2]) {
+          const int64_t o = (int64_t)f * a.B + nn[s2];
+          const T sp = a.spread[o];
+          const T sd = f < a.n_var ? Num<T>::sqrt(sp > a.clamp_min ? sp : a.clamp_min) : sp;
+          v = Num<T>::exp(fma(a.eps[((int64_t)e * a.F + f) * a.B + nn[s2]], sd, a.mean[o]));
+        }
+        ef[s2][f] = v;
+      }
+    __syncthreads();                               // phase B of the previous sample finished with efS
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+      for (int f = 0; f < FMAX; ++f) efS[s2 * P2_THREADS + tid][f] = ef[s2][f];
+
+    for (int g0 = g_begin; g0 < g_end; g0 += PZ_GCH) {
+      __syncthreads();                             // previous chunk's phase B / flush finished with sW, tS, sAcc
+      for (int i = tid; i < PZ_GCH * FMAX; i += P2_THREADS) {
+        const int gi = i / FMAX, f = i % FMAX;
+        T w = T(0);
+        if (g0 + gi < g_end && f < a.F) {
+          w = a.W[(int64_t)(g0 + gi) * a.F + f];
+          if (a.w_softplus) w = softplus(w);
+        }
+        sW[gi][f] = w;
+      }
+      __syncthreads();
+      // ---- phase A: thread = two spots ----
+      T llc = T(0);
+#pragma unroll 1
+      for (int gb = 0; gb < PZ_GCH; gb += PZ_GRP) {
+        T yv[PZ_GRP][2];
+#pragma unroll
+        for (int u = 0; u < PZ_GRP; ++u) { yv[u][0] = ynext[u][0]; yv[u][1] = ynext[u][1]; }
+        {
+          int gn = g0 + gb + PZ_GRP;               // first gene of the next group in (sample, chunk, group) order
+          if (gb + PZ_GRP == PZ_GCH && g0 + PZ_GCH >= g_end) gn = (e + 1 < a.E) ? g_begin : g_end;
+          prefetch(gn);
+        }
+        auto body = [&](auto guard, int u) {
+          constexpr bool GUARD = decltype(guard)::value;
+          const int gi = gb + u;
+          T wrow[FMAX];
+          load_row<FMAX>(&sW[gi][0], wrow);
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2) {
+            T t = T(0);
+            if (!GUARD || (act[s2] && g0 + gi < g_end)) {
+              const T y = yv[u][s2];
+              T z0 = T(0), z1 = T(0);
+#pragma unroll
+              for (int f = 0; f < FMAX; f += 2) { z0 = fma(wrow[f], ef[s2][f], z0); z1 = fma(wrow[f + 1], ef[s2][f + 1], z1); }
+              const T zr = z0 + z1;
+              const T r = spV[s2] * zr;
+              const T ylog = y * fast_log(r);
+              T lp = (y == T(0) ? T(0) : ylog) - r;
+              if (a.with_lgamma) {
+                const int yi = (int)y;
+                // counts: table lookup (no divergent lgamma call); anything else: the real thing
+                lp -= (yi >= 0 && yi < 64 && T(yi) == y) ? lfact[yi] : Num<T>::lgamma(y + T(1));
+              }
+              llc += lp;
+              t = (fast_div(y, zr) - spV[s2]) * invE;
+              gVacc[s2] += y - r;
+#pragma unroll
+              for (int f = 0; f < FMAX; ++f) pg[s2][f] = fma(wrow[f], t, pg[s2][f]);
+            }
+            tS[gi][s2 * P2_THREADS + tid] = t;
+          }
+        };
+        if (block_full && g0 + PZ_GCH <= g_end) {
+#pragma unroll
+          for (int u = 0; u < PZ_GRP; ++u) body(std::false_type{}, u);
+        } else {
+#pragma unroll 1
+          for (int u = 0; u < PZ_GRP; ++u) body(std::true_type{}, u);
+        }
+      }
+      ll += (double)(llc * invE);
+      __syncthreads();
+      // ---- phase B: lane = gene, warp = a quarter (64) of the spots ----
+      T acc[FMAX];
+#pragma unroll
+      for (int f = 0; f < FMAX; ++f) acc[f] = T(0);
+      const int nb = warp * 64;
+#pragma unroll 4
+      for (int k = 0; k < 64; ++k) {
+        const T t = tS[lane][nb + k];
+        T erow[FMAX];
+        load_row<FMAX>(&efS[nb + k][0], erow);
+#pragma unroll
+        for (int f = 0; f < FMAX; ++f) acc[f] = fma(t, erow[f], acc[f]);
+      }
+#pragma unroll
+      for (int f = 0; f < FMAX; ++f) sAcc[warp][lane][f] = acc[f];
+      __syncthreads();
+      for (int i = tid; i < PZ_GCH * a.F; i += P2_THREADS) {
+        const int gi = i / a.F, f = i % a.F;
+        if (g0 + gi < g_end) {
+          T* dst = a.gW_part + ((int64_t)blockIdx.x * a.G + g0 + gi) * a.F + f;
+          const T v = sAcc[0][gi][f] + sAcc[1][gi][f] + sAcc[2][gi][f] + sAcc[3][gi][f];
+          *dst = e == 0 ? v : *dst + v;
+        }
+      }
+    }
+    // ---- per-sample epilogue: d ll / d mean, d ll / d spread ----
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2) {
+      if (!act[s2]) continue;
+#pragma unroll
+      for (int f = 0; f < FMAX; ++f) {
+        if (f < a.F) {
+          const int64_t o = (int64_t)f * a.B + nn[s2];
+          const T gF = ef[s2][f] * pg[s2][f];
+          T gsp = gF * a.eps[((int64_t)e * a.F + f) * a.B + nn[s2]];
+          if (f < a.n_var) {                       // spread is a variance: d sd / d var = 1 / (2 sd) where not clamped
+            const T sp = a.spread[o];
+            gsp = sp >= a.clamp_min ? gsp / (T(2) * Num<T>::sqrt(sp)) : T(0);
+          }
+          if (a.atomic_out) { atomicAdd(a.gmean + o, gF); atomicAdd(a.gspread + o, gsp); }
+          else if (e == 0) { a.gmean[o] = gF; a.gspread[o] = gsp; }
+          else { a.gmean[o] += gF; a.gspread[o] += gsp; }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int s2 = 0; s2 < 2; ++s2) {
+    if (act[s2]) {
+      const T gv = softplus_grad(vraw[s2]) * gVacc[s2] * invE / spV[s2];
+      if (a.atomic_out) atomicAdd(a.gV + nn[s2], gv); else a.gV[nn[s2]] = gv;
+    }
+  }
+  const double tot = block_sum<double>(ll, red);
+  if (tid == 0) a.ll_part[blockIdx.y * gridDim.x + blockIdx.x] = tot;
+}
+
 // gW[g,f] = (softplus'(W[g,f]) or 1) * sum_b gW_part[b,g,f]
 template <typename T>
 __global__ void poisson_gw_reduce_kernel(const T* __restrict__ part, const T* __restrict__ W, T* __restrict__ gW, int64_t GF, int nb,
@@ -248,16 +443,30 @@ __global__ void sum_double_kernel(const double* __restrict__ part, int n, double
 template <typename T, int FMAX> constexpr size_t poisson_smem() {
   return sizeof(T) * (PZ_GCH * (PZ_SPOTS + 1) + FMAX * PZ_SPOTS + PZ_GCH * FMAX + 4 * PZ_GCH * FMAX);
 }
+template <typename T, int FMAX> constexpr size_t poisson_smem2() {
+  return ((sizeof(T) * PZ_GCH * (P2_SPOTS + 1) + 15) / 16) * 16 + sizeof(T) * (FMAX * P2_SPOTS + PZ_GCH * FMAX + 4 * PZ_GCH * FMAX);
+}
+static int poisson_version() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GPZ_POISSON_V"); v = e ? atoi(e) : 2; }
+  return v;
+}
 template <typename T, int FMAX> int poisson_launch(const PoissonArgs<T>& a, dim3 grid, cudaStream_t st) {
-  constexpr size_t smem = poisson_smem<T, FMAX>();
-  GPZ_CUDA(cudaFuncSetAttribute(poisson_kernel<T, FMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  poisson_kernel<T, FMAX><<<grid, PZ_SPOTS, smem, st>>>(a);
+  if (poisson_version() == 2) {
+    constexpr size_t smem = poisson_smem2<T, FMAX>();
+    GPZ_CUDA(cudaFuncSetAttribute(poisson_kernel2<T, FMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    poisson_kernel2<T, FMAX><<<grid, P2_THREADS, smem, st>>>(a);
+  } else {
+    constexpr size_t smem = poisson_smem<T, FMAX>();
+    GPZ_CUDA(cudaFuncSetAttribute(poisson_kernel<T, FMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    poisson_kernel<T, FMAX><<<grid, PZ_SPOTS, smem, st>>>(a);
+  }
   GPZ_CHECK_LAUNCH();
   return GPZ_OK;
 }
 
 static void poisson_grid(int G, int B, int* nbx, int* nby, int* gpc) {
-  *nbx = (int)cdiv(B, PZ_SPOTS);
+  *nbx = (int)cdiv(B, poisson_version() == 2 ? P2_SPOTS : PZ_SPOTS);
   const int chunks = (int)cdiv(G, PZ_GCH);
   int by = 1;
   if (*nbx < 1184) by = (int)min((int64_t)chunks, cdiv(1184, *nbx > 0 ? *nbx : 1));
