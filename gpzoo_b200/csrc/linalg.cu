@@ -379,9 +379,20 @@ __device__ void run_steps(T (*tA)[TLD], T (*tB)[TLD], const int4* __restrict__ s
                           const T* __restrict__ MB, T* __restrict__ MO, bool b_tr, T alpha, T beta, int M) {
   const int tid = threadIdx.x;
   auto bsz = [&](int b) { return min(NB, M - b * NB); };
-  T ra[16], rb[16];
+  T ra[16], rb[16], rc[4][4];
+  const int ty = tid >> 4, tx = tid & 15;
   auto fetch = [&](int sidx) {
     const int4 st = steps[sidx];
+    if (beta != T(0) && (st.w & 2)) {                  // read-modify-write output tile: its old values ride along with the operands
+      const int onr = bsz(st.x), onc = bsz(st.y);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          const int i = ty * 4 + u, j = tx * 4 + v;
+          rc[u][v] = (i < onr && j < onc) ? MO[(int64_t)(st.x * NB + i) * M + st.y * NB + j] : T(0);
+        }
+    }
     const int ar0 = st.x * NB, ac0 = st.z * NB, anr = bsz(st.x), anc = bsz(st.z);
     const int br0 = (b_tr ? st.z : st.y) * NB, bc0 = (b_tr ? st.y : st.z) * NB;
     const int bnr = bsz(b_tr ? st.z : st.y), bnc = bsz(b_tr ? st.y : st.z);
@@ -405,6 +416,13 @@ __device__ void run_steps(T (*tA)[TLD], T (*tB)[TLD], const int4* __restrict__ s
       if (b_tr) tB[r][c] = rb[u]; else tB[c][r] = rb[u];
     }
     __syncthreads();
+    T oc[4][4];
+    if (beta != T(0) && (st.w & 2)) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) oc[u][v] = rc[u][v];
+    }
     if (sidx + 1 < nsteps) fetch(sidx + 1);            // next step's loads overlap this step's FMAs
     if (st.w & 1) {
 #pragma unroll
@@ -413,7 +431,20 @@ __device__ void run_steps(T (*tA)[TLD], T (*tB)[TLD], const int4* __restrict__ s
         for (int v = 0; v < 4; ++v) acc[u][v] = T(0);
     }
     tile_abt<T>(tA, tB, acc);
-    if (st.w & 2) store_tile<T>(MO, M, st.x * NB, st.y * NB, bsz(st.x), bsz(st.y), acc, alpha, beta);
+    if (st.w & 2) {
+      if (beta != T(0)) {
+        const int onr = bsz(st.x), onc = bsz(st.y);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const int i = ty * 4 + u, j = tx * 4 + v;
+            if (i < onr && j < onc) MO[(int64_t)(st.x * NB + i) * M + st.y * NB + j] = alpha * acc[u][v] + beta * oc[u][v];
+          }
+      } else {
+        store_tile<T>(MO, M, st.x * NB, st.y * NB, bsz(st.x), bsz(st.y), acc, alpha, beta);
+      }
+    }
   }
 }
 
@@ -439,46 +470,47 @@ chol_inv_cluster_kernel(T* __restrict__ Wall, T* __restrict__ Lall, T* __restric
   auto bsz = [&](int b) { return min(NB, M - b * NB); };
 
   long long t_leaf = 0, t_panel = 0, t_trail = 0, t_inv = 0, t0 = clock64(), t1;
-  // ---- factorisation ----
-  for (int k = 0; k < nblk; ++k) {
-    const int k0 = k * NB, nb = bsz(k);
-    if (rank == 0) leaf_body<T>(la, lx, W, Lm, X, M, k0, nb, info + l);
+  // ---- factorisation, with look-ahead: while CTAs 1..7 apply the trailing update of step k, CTA 0 updates the next
+  //      diagonal tile first and immediately factors / inverts it (the leaf is the serial part of the chain) ----
+  if (rank == 0) leaf_body<T>(la, lx, W, Lm, X, M, 0, bsz(0), info + l);
+  cluster.sync();
+  t1 = clock64(); t_leaf += t1 - t0; t0 = t1;
+  for (int k = 0; k < nblk - 1; ++k) {
+    const int nrb = nblk - k - 1;                       // row blocks below the diagonal block (>= 1 here)
+    // panel: L21 = W21 X11^T      (A = W[gi][k], B = X[k][k], out = Lc[gi][k])
+    if (threadIdx.x == 0) {
+      int ns = 0;
+      for (int rb = rank; rb < nrb; rb += CL) steps[ns++] = make_int4(k + 1 + rb, k, k, 3);
+      nsteps_s = ns;
+    }
+    __syncthreads();
+    run_steps<T>(tA, tB, steps, nsteps_s, W, X, Lm, false, T(1), T(0), M);
     cluster.sync();
-    t1 = clock64(); t_leaf += t1 - t0; t0 = t1;
-    const int nrb = nblk - k - 1;                       // row blocks below the diagonal block
-    if (nrb > 0) {
-      // panel: L21 = W21 X11^T      (A = W[gi][k], B = X[k][k], out = Lc[gi][k])
+    t1 = clock64(); t_panel += t1 - t0; t0 = t1;
+    // trailing update of the lower triangle: W[gi][gj] -= Lc[gi][k] Lc[gj][k]^T   (in rounds of at most MAX_STEPS tiles).
+    // Tile 0 (the next diagonal block) belongs to CTA 0, which then runs the next leaf; tiles 1.. go round-robin to CTAs 1..7.
+    for (int q_start = 0; q_start >= 0;) {
       if (threadIdx.x == 0) {
-        int ns = 0;
-        for (int rb = rank; rb < nrb; rb += CL) steps[ns++] = make_int4(k + 1 + rb, k, k, 3);
+        int ns = 0, q = 0, q_next = -1;
+        for (int bi = 0; bi < nrb && q_next < 0; ++bi)
+          for (int bj = 0; bj <= bi; ++bj, ++q) {
+            const int owner = q == 0 ? 0 : 1 + (q - 1) % (CL - 1);
+            if (q < q_start || owner != rank) continue;
+            if (ns == MAX_STEPS) { q_next = q; break; }
+            steps[ns++] = make_int4(k + 1 + bi, k + 1 + bj, k, 3);
+          }
         nsteps_s = ns;
+        q_next_s = q_next;
       }
       __syncthreads();
-      run_steps<T>(tA, tB, steps, nsteps_s, W, X, Lm, false, T(1), T(0), M);
-      cluster.sync();
-      t1 = clock64(); t_panel += t1 - t0; t0 = t1;
-      // trailing update of the lower triangle: W[gi][gj] -= Lc[gi][k] Lc[gj][k]^T   (in rounds of at most MAX_STEPS tiles)
-      for (int q_start = 0; q_start >= 0;) {
-        if (threadIdx.x == 0) {
-          int ns = 0, q = 0, q_next = -1;
-          for (int bi = 0; bi < nrb && q_next < 0; ++bi)
-            for (int bj = 0; bj <= bi; ++bj, ++q) {
-              if (q < q_start || q % CL != rank) continue;
-              if (ns == MAX_STEPS) { q_next = q; break; }
-              steps[ns++] = make_int4(k + 1 + bi, k + 1 + bj, k, 3);
-            }
-          nsteps_s = ns;
-          q_next_s = q_next;
-        }
-        __syncthreads();
-        const int ns = nsteps_s, qn = q_next_s;
-        run_steps<T>(tA, tB, steps, ns, Lm, Lm, W, false, T(-1), T(1), M);
-        __syncthreads();
-        q_start = qn;
-      }
-      cluster.sync();
-      t1 = clock64(); t_trail += t1 - t0; t0 = t1;
+      const int ns = nsteps_s, qn = q_next_s;
+      run_steps<T>(tA, tB, steps, ns, Lm, Lm, W, false, T(-1), T(1), M);
+      __syncthreads();
+      q_start = qn;
     }
+    if (rank == 0) leaf_body<T>(la, lx, W, Lm, X, M, (k + 1) * NB, bsz(k + 1), info + l);
+    cluster.sync();
+    t1 = clock64(); t_trail += t1 - t0; t0 = t1;
   }
   // ---- inverse by recursive doubling, tile by tile:  tmp21 = L21 X11 ;  X21 = -X22 tmp21 ----
   for (int b = 1; b < nblk; b *= 2) {                      // b = blocks per half
