@@ -526,7 +526,9 @@ chol_inv_cluster_kernel(T* __restrict__ Wall, T* __restrict__ Lall, T* __restric
             if (n2 <= 0) continue;
             for (int ti = 0; ti < n2 && q_next < 0; ++ti)
               for (int tj = 0; tj < b; ++tj, ++q) {
-                if (q < q_start || q % CL != rank) continue;
+                // owner rotates with (ti + tj): the cost of a tile is b - tj (stage 0) or ti + 1 (stage 1), so a plain
+                // q % CL would hand one CTA all the expensive tiles
+                if (q < q_start || (ti + tj + p) % CL != rank) continue;
                 // stage 0: sum_{tk=tj}^{b-1} L[gi][f0+tk] X[f0+tk][gj];  stage 1: sum_{tk=0}^{ti} X[gi][f0+b+tk] tmp[f0+b+tk][gj]
                 const int t_lo = stage == 0 ? tj : 0, t_hi = stage == 0 ? b - 1 : ti;
                 if (ns + (t_hi - t_lo + 1) > MAX_STEPS) { q_next = q; break; }
