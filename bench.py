@@ -259,7 +259,10 @@ def run_ours(args):
         "svgp_predict_bwd": ("tensor", 4.0 * L * M * M * N),
         "svgp_predict_fwd_tc": ("tensor", 2.0 * L * M * M * N),
         "svgp_predict_bwd_tc": ("tensor", 4.0 * L * M * M * N),
-        "kernel_build_fwd": ("hbm", 8.0 * L * M * N),      # Kzx and its tf32 lo part
+        "svgp_predict_fwd_h": ("tensor", 2.0 * L * M * M * N),
+        "svgp_predict_bwd_h": ("tensor", 4.0 * L * M * M * N),
+        "kernel_build_fwd": ("hbm", 8.0 * L * M * N),      # Kzx and its tf32 lo part (split-TF32 path)
+        "kernel_build_fwd_h": ("hbm", 4.0 * L * M * N),    # Kzx as two fp16 planes (split-FP16 path)
         "kernel_build_bwd": ("hbm", 4.0 * L * M * N),
         "poisson_fwdbwd": ("hbm", 4.0 * G * N + 4.0 * (3 * E * L * N + 2 * G * L + 2 * N)),
     }

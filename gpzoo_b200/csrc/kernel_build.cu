@@ -10,6 +10,7 @@
 // HBM-bound: one pass writes 4*L*n1*n2 bytes; each thread owns 4 consecutive j and streams float4 stores.
 #include "common.cuh"
 #include "gpzoo_b200.h"
+#include "umma_gemm.h"
 
 namespace gpz {
 
@@ -114,6 +115,92 @@ __global__ void __launch_bounds__(KB_THREADS) kbuild_fwd_kernel(const KBArgs<T> 
         if (ALIGNED && nv == KB_VEC) __stcs(reinterpret_cast<float4*>(ol), make_float4(lo[0], lo[1], lo[2], lo[3]));
         else for (int v = 0; v < nv; ++v) ol[v] = lo[v];
       }
+    }
+  }
+}
+
+// fp32 build written directly as the fp16 operand planes of the split-FP16 tensor-core GEMMs (csrc/umma_gemm.cu):
+// out_h + out_l ~= K * scale[l], scale[l] = the power of two that puts sigma_l^2 (+|jitter|), the largest possible entry,
+// in (2^14, 2^15].  4 bytes per entry leave the SM (half of K + lo plane in fp32); each thread owns 8 consecutive j and
+// streams one 16-byte store per plane, row and factor.
+constexpr int KB_VEC8 = 8;
+template <bool MG>
+__global__ void __launch_bounds__(KB_THREADS) kbuild_fwd_h_kernel(const KBArgs<float> a, __half* __restrict__ out_h,
+                                                                  __half* __restrict__ out_l, float* __restrict__ out_scale) {
+  __shared__ float s_c[KB_LMAX * 8], s_s2[KB_LMAX * 8], s_a[KB_LMAX * 8], s_sc[KB_LMAX * 8];
+  __shared__ float s_r2[MG ? KB_GMAX * KB_GMAX : 1];
+  const int tid = threadIdx.x;
+  for (int l = tid; l < a.L; l += KB_THREADS) {
+    const float ls = a.ls[l], sg = a.sigma[l];
+    s_c[l] = -0.5f / (ls * ls);
+    s_s2[l] = sg * sg;
+    s_sc[l] = gpz_pow2_scale(sg * sg + fabsf(a.jitter));
+    if (MG) s_a[l] = a.a[l];
+    if (blockIdx.x == 0 && blockIdx.y == 0) out_scale[l] = s_sc[l];
+  }
+  if (MG) for (int e = tid; e < a.ng * a.ng; e += KB_THREADS) s_r2[e] = a.r2[e];
+  __syncthreads();
+
+  const int64_t j0 = ((int64_t)blockIdx.x * KB_THREADS + tid) * KB_VEC8;
+  if (j0 >= a.n2) return;                        // n2 % 8 == 0 (checked by the host): whole vectors only
+  float xj[KB_DMAX][KB_VEC8];
+  int gj[KB_VEC8];
+#pragma unroll
+  for (int v = 0; v < KB_VEC8; ++v) {
+#pragma unroll
+    for (int d = 0; d < KB_DMAX; ++d) xj[d][v] = d < a.D ? a.x2[(j0 + v) * a.D + d] : 0.f;
+    gj[v] = MG ? (int)a.g2[j0 + v] : 0;
+  }
+  const int i0 = blockIdx.y * KB_ROWS, i1 = min(i0 + KB_ROWS, a.n1);
+  for (int i = i0; i < i1; ++i) {
+    float d2[KB_VEC8], r2[KB_VEC8];
+#pragma unroll
+    for (int v = 0; v < KB_VEC8; ++v) d2[v] = 0.f;
+#pragma unroll
+    for (int d = 0; d < KB_DMAX; ++d) {
+      if (d < a.D) {
+        const float xi = a.x1[(int64_t)i * a.D + d];
+#pragma unroll
+        for (int v = 0; v < KB_VEC8; ++v) { const float df = xi - xj[d][v]; d2[v] = fmaf(df, df, d2[v]); }
+      }
+    }
+    if (MG) {
+      const int gi = (int)a.g1[i];
+#pragma unroll
+      for (int v = 0; v < KB_VEC8; ++v) r2[v] = s_r2[gi * a.ng + gj[v]];
+    }
+    for (int l = 0; l < a.L; ++l) {
+      const float c = s_c[l], s2 = s_s2[l], sc = s_sc[l];
+      float k[KB_VEC8];
+#pragma unroll
+      for (int v = 0; v < KB_VEC8; ++v) {
+        float val;
+        if (MG) {
+          const float den = fmaf(s_a[l], r2[v], 1.f);
+          const float scd = a.p_half == 1.f ? 1.f / den : powf(den, -a.p_half);
+          val = s2 * expf(c * d2[v] / den) * scd;
+        } else {
+          val = s2 * expf(c * d2[v]);
+        }
+        if (a.jitter != 0.f && (int64_t)i == j0 + v) val += a.jitter;
+        k[v] = val * sc;
+      }
+      uint4 h, lo;
+      { const __half2 hh = __floats2half2_rn(k[0], k[1]); const float2 f = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(k[0] - f.x, k[1] - f.y);
+        h.x = *reinterpret_cast<const uint32_t*>(&hh); lo.x = *reinterpret_cast<const uint32_t*>(&ll); }
+      { const __half2 hh = __floats2half2_rn(k[2], k[3]); const float2 f = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(k[2] - f.x, k[3] - f.y);
+        h.y = *reinterpret_cast<const uint32_t*>(&hh); lo.y = *reinterpret_cast<const uint32_t*>(&ll); }
+      { const __half2 hh = __floats2half2_rn(k[4], k[5]); const float2 f = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(k[4] - f.x, k[5] - f.y);
+        h.z = *reinterpret_cast<const uint32_t*>(&hh); lo.z = *reinterpret_cast<const uint32_t*>(&ll); }
+      { const __half2 hh = __floats2half2_rn(k[6], k[7]); const float2 f = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(k[6] - f.x, k[7] - f.y);
+        h.w = *reinterpret_cast<const uint32_t*>(&hh); lo.w = *reinterpret_cast<const uint32_t*>(&ll); }
+      const int64_t o = ((int64_t)l * a.n1 + i) * a.n2 + j0;
+      __stcs(reinterpret_cast<uint4*>(out_h + o), h);
+      __stcs(reinterpret_cast<uint4*>(out_l + o), lo);
     }
   }
 }
@@ -382,3 +469,21 @@ using namespace gpz;
 
 GPZ_KB_IMPL(f32, float)
 GPZ_KB_IMPL(f64, double)
+
+// fp16-plane forward (fp32 arithmetic): see kbuild_fwd_h_kernel
+extern "C" int gpz_kernel_build_fwd_h_f32(const float* x1, const float* x2, const float* sigma, const float* ls, const float* a,
+                                          const float* r2, const int64_t* g1, const int64_t* g2, int n1, int n2, int D, int L,
+                                          int ng, float p_half, float jitter, void* out_h, void* out_l, float* out_scale,
+                                          void* stream) {
+  KBArgs<float> k{x1, x2, sigma, ls, a, r2, g1, g2, n1, n2, D, L, ng, p_half, jitter};
+  if (D < 1 || D > KB_DMAX || L < 1 || L > KB_LMAX * 8) return GPZ_ERR_UNSUPPORTED;
+  const bool mg = g1 != nullptr;
+  if (mg && (ng < 1 || ng > KB_GMAX)) return GPZ_ERR_UNSUPPORTED;
+  if (n2 % KB_VEC8 || (reinterpret_cast<uintptr_t>(out_h) & 15) || (reinterpret_cast<uintptr_t>(out_l) & 15)) return GPZ_ERR_UNSUPPORTED;
+  if (n1 == 0 || n2 == 0) return GPZ_OK;
+  dim3 grid((unsigned)cdiv(n2, (int64_t)KB_THREADS * KB_VEC8), (unsigned)cdiv(n1, KB_ROWS));
+  if (mg) kbuild_fwd_h_kernel<true><<<grid, KB_THREADS, 0, (cudaStream_t)stream>>>(k, (__half*)out_h, (__half*)out_l, out_scale);
+  else kbuild_fwd_h_kernel<false><<<grid, KB_THREADS, 0, (cudaStream_t)stream>>>(k, (__half*)out_h, (__half*)out_l, out_scale);
+  GPZ_CHECK_LAUNCH();
+  return GPZ_OK;
+}

@@ -245,6 +245,202 @@ static int predict_bwd_tc(const float* Kzx, const float* Kzx_lo, const float* Li
   return tc_gemm(st, 1, M, M, N, gA, gA_lo, N, sMN, Kzx, Kzx_lo, N, sMN, gLinv, nullptr, M, sMM, L, 0, 1, splitk);
 }
 
+
+// ---- tensor-core (tcgen05, split-FP16) variant: the default fp32 hot path ------------------------------------------------
+// Every N-proportional operand travels as a pair of fp16 planes (hi, lo) of x * s[l] (s[l] a power of two, 22 significant
+// bits, 4 bytes per entry) instead of fp32 + lo plane (8 bytes); the GEMMs run at the f16 tensor-core rate (2x tf32).
+// Scales come from upper bounds that are available BEFORE the producing kernel runs, so every epilogue can write the planes
+// of its output directly:
+//   Kzx  : |K| <= sigma^2                                   (kernel_build.cu writes the planes and sK)
+//   A    : |A[:,n]|_2^2 = k_n^T (Kzz + jitter I)^-1 k_n <= Kxx[n]   (Schur complement of a PSD kernel)  ->  bound 2 sqrt(max Kxx)
+//   gC   : 2 max|C| max|gv|                                 (max|C| is tracked exactly by the epilogue that produced C)
+//   gA   : |T|_inf bound(gC) + 2 max|A| max|gv| + max|q| max|gm|
+//   Linv, T (M x M): exact max from a reduction pass.
+// A bound that is 2^10 too loose still leaves the fp16 subnormal floor 2^-30 below the largest entry, i.e. below fp32 epsilon
+// relative to the matrix norm; a violated bound produces inf/NaN (never a silently saturated value).
+// ws_h (halfs): [Linv_h | Linv_l | LinvT_h | LinvT_l | T_h | T_l | TT_h | TT_l], each L*M*M.
+// ws_f (floats): [sumA2 (L*N) | sumC2 (L*N) | stats (16 slots of L)], slots:
+enum { ST_S_LINV = 0, ST_S_T, ST_S_A, ST_S_GC, ST_S_GA, ST_AMAX_LINV, ST_AMAX_T, ST_AMAX_A, ST_AMAX_C, ST_TINF, ST_AMAX_GV,
+       ST_AMAX_GM, ST_AMAX_Q, ST_AMAX_KXX, ST_AMAX_GA, ST_SPARE, ST_SLOTS };
+
+__device__ __forceinline__ float block_amax(const float* __restrict__ x, int n, float* red) {
+  float m = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int sh = 16; sh > 0; sh >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, sh));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+  return m;
+}
+
+// one CTA per factor: sA[l] from max Kxx[l,:]
+__global__ void __launch_bounds__(256) predict_h_fwd_scales_kernel(const float* __restrict__ kxx, float* __restrict__ stats, int N, int L) {
+  __shared__ float red[8];
+  const int l = blockIdx.x;
+  const float mk = block_amax(kxx + (int64_t)l * N, N, red);
+  if (threadIdx.x == 0) {
+    stats[ST_AMAX_KXX * L + l] = mk;
+    stats[ST_S_A * L + l] = gpz_pow2_scale(2.f * sqrtf(mk));
+  }
+}
+
+// max_i sum_j |T[l,i,j]|: one warp per row
+__global__ void __launch_bounds__(256) rowabs_max_kernel(const float* __restrict__ T, unsigned int* __restrict__ out, int M) {
+  const int l = blockIdx.y, row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* t = T + ((int64_t)l * M + row) * M;
+  float s = 0.f;
+  for (int j = lane; j < M; j += 32) s += fabsf(t[j]);
+  s = warp_sum(s);
+  if (lane == 0 && s > 0.f) atomicMax(out + l, __float_as_uint(s));
+}
+
+// one CTA per factor: max|gv|, max|gm|, max|q| and the scales of gC and gA
+__global__ void __launch_bounds__(256) predict_h_bwd_scales_kernel(const float* __restrict__ gv, const float* __restrict__ gm,
+                                                                    const float* __restrict__ q, float* __restrict__ stats, int M,
+                                                                    int N, int L) {
+  __shared__ float red[8];
+  const int l = blockIdx.x;
+  const float a_gv = block_amax(gv + (int64_t)l * N, N, red);
+  const float a_gm = block_amax(gm + (int64_t)l * N, N, red);
+  const float a_q = block_amax(q + (int64_t)l * M, M, red);
+  if (threadIdx.x == 0) {
+    const float a_A = stats[ST_AMAX_A * L + l], a_C = stats[ST_AMAX_C * L + l], tinf = stats[ST_TINF * L + l];
+    const float b_gC = 2.f * a_C * a_gv;
+    const float b_gA = tinf * b_gC + 2.f * a_A * a_gv + a_q * a_gm;
+    stats[ST_AMAX_GV * L + l] = a_gv; stats[ST_AMAX_GM * L + l] = a_gm; stats[ST_AMAX_Q * L + l] = a_q;
+    stats[ST_S_GC * L + l] = gpz_pow2_scale(b_gC);
+    stats[ST_S_GA * L + l] = gpz_pow2_scale(b_gA);
+  }
+}
+
+// gC = 2 C gv written as fp16 planes of gC * s[l]
+__global__ void __launch_bounds__(256) predict_h_scale_kernel(const float* __restrict__ C, const float* __restrict__ gv,
+                                                               const float* __restrict__ s_gc, __half* __restrict__ gCh,
+                                                               __half* __restrict__ gCl, int M, int N) {
+  const int l = blockIdx.z;
+  const int n8 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (n8 >= N) return;
+  const float sc = 2.f * s_gc[l];
+  const float4 g0 = *reinterpret_cast<const float4*>(gv + (int64_t)l * N + n8);
+  const float4 g1 = *reinterpret_cast<const float4*>(gv + (int64_t)l * N + n8 + 4);
+  const float w[8] = {g0.x * sc, g0.y * sc, g0.z * sc, g0.w * sc, g1.x * sc, g1.y * sc, g1.z * sc, g1.w * sc};
+  const int m0 = blockIdx.y * 16, m1 = min(m0 + 16, M);
+  for (int m = m0; m < m1; ++m) {
+    const int64_t e = ((int64_t)l * M + m) * N + n8;
+    const float4 c0 = __ldcs(reinterpret_cast<const float4*>(C + e));
+    const float4 c1 = __ldcs(reinterpret_cast<const float4*>(C + e + 4));
+    const float v[8] = {c0.x * w[0], c0.y * w[1], c0.z * w[2], c0.w * w[3], c1.x * w[4], c1.y * w[5], c1.z * w[6], c1.w * w[7]};
+    uint32_t h[4], lo[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const __half2 hh = __floats2half2_rn(v[2 * u], v[2 * u + 1]);
+      const float2 f = __half22float2(hh);
+      const __half2 ll = __floats2half2_rn(v[2 * u] - f.x, v[2 * u + 1] - f.y);
+      h[u] = *reinterpret_cast<const uint32_t*>(&hh);
+      lo[u] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    *reinterpret_cast<uint4*>(gCh + e) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(gCl + e) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+static Umma16Args h_args(int bk, int m, int n, int k, const __half* Ah, const __half* Al, int64_t lda, int64_t sA, const float* sa,
+                         const __half* Bh, const __half* Bl, int64_t ldb, int64_t sB, const float* sb, int64_t ldd, int64_t sD,
+                         int batch, int a_tri, int d_tri, int splitk) {
+  Umma16Args g{};
+  g.b_kmajor = bk; g.m = m; g.n = n; g.k = k; g.alpha = 1.0f;
+  g.Ah = Ah; g.Al = Al; g.lda = lda; g.sA = sA; g.sa = sa;
+  g.Bh = Bh; g.Bl = Bl; g.ldb = ldb; g.sB = sB; g.sb = sb;
+  g.ldd = ldd; g.sD = sD; g.batch = batch; g.a_tri = a_tri; g.d_tri = d_tri; g.splitk = splitk; g.n_terms = 3;
+  return g;
+}
+
+static int predict_fwd_h(const __half* Kh, const __half* Kl, const float* sK, const float* Linv, const float* Tm, const float* q,
+                         const float* kxx, __half* Ah, __half* Al, float* C, float* mean, float* var, __half* ws_h, float* ws_f,
+                         int M, int N, int L, cudaStream_t st) {
+  const int64_t sMM = (int64_t)M * M, sMN = (int64_t)M * N, W = sMM * L, LN = (int64_t)L * N;
+  __half* Linv_h = ws_h; __half* Linv_l = ws_h + W;
+  __half* LinvT_h = ws_h + 2 * W; __half* LinvT_l = ws_h + 3 * W;
+  __half* T_h = ws_h + 4 * W; __half* T_l = ws_h + 5 * W; __half* TT_h = ws_h + 6 * W; __half* TT_l = ws_h + 7 * W;
+  float* sA2 = ws_f; float* sC2 = ws_f + LN; float* stats = ws_f + 2 * LN;
+  unsigned int* ustats = reinterpret_cast<unsigned int*>(stats);
+  GPZ_CUDA(cudaMemsetAsync(ws_f, 0, sizeof(float) * (2 * LN + (size_t)ST_SLOTS * L), st));
+  GPZ_CUDA(cudaMemsetAsync(mean, 0, sizeof(float) * LN, st));
+  int rc = split16_amax(Linv, sMM, L, ustats + ST_AMAX_LINV * L, (void*)st);
+  if (rc) return rc;
+  rc = split16_planes(Linv, M, M, L, ustats + ST_AMAX_LINV * L, stats + ST_S_LINV * L, Linv_h, Linv_l, LinvT_h, LinvT_l, (void*)st);
+  if (rc) return rc;
+  rc = split16_amax(Tm, sMM, L, ustats + ST_AMAX_T * L, (void*)st);
+  if (rc) return rc;
+  rc = split16_planes(Tm, M, M, L, ustats + ST_AMAX_T * L, stats + ST_S_T * L, T_h, T_l, TT_h, TT_l, (void*)st);
+  if (rc) return rc;
+  predict_h_fwd_scales_kernel<<<L, 256, 0, st>>>(kxx, stats, N, L);
+  GPZ_CHECK_LAUNCH();
+  // A = Linv Kzx  (lower-triangular product == TRSM Lc A = Kzx); epilogue: sum_m A^2, mean = sum_m q_m A, max |A|
+  UmmaEpilogue e1{1, nullptr, q, nullptr, nullptr, sA2, mean, nullptr};
+  Umma16Args g1 = h_args(0, M, N, M, Linv_h, Linv_l, M, sMM, stats + ST_S_LINV * L, Kh, Kl, N, sMN, sK, N, sMN, L, 1, 0, 1);
+  g1.Dh = Ah; g1.Dl = Al; g1.sd = stats + ST_S_A * L; g1.amax = ustats + ST_AMAX_A * L; g1.epi = &e1;
+  rc = umma_gemm16_ex(g1, (void*)st);
+  if (rc) return rc;
+  // C = T^T A     (upper-triangular product); epilogue: sum_m C^2, max |C|
+  UmmaEpilogue e2{2, nullptr, nullptr, nullptr, nullptr, sC2, nullptr, nullptr};
+  Umma16Args g2 = h_args(0, M, N, M, TT_h, TT_l, M, sMM, stats + ST_S_T * L, Ah, Al, N, sMN, stats + ST_S_A * L, N, sMN, L, 2, 0, 1);
+  g2.D = C; g2.amax = ustats + ST_AMAX_C * L; g2.epi = &e2;
+  rc = umma_gemm16_ex(g2, (void*)st);
+  if (rc) return rc;
+  predict_var_kernel<<<(unsigned)cdiv(LN, 256), 256, 0, st>>>(kxx, sA2, sC2, var, LN);
+  GPZ_CHECK_LAUNCH();
+  return GPZ_OK;
+}
+
+static int predict_bwd_h(const __half* Kh, const __half* Kl, const float* sK, const float* Tm, const float* q, const __half* Ah,
+                         const __half* Al, const float* C, const float* gm, const float* gv, __half* gCh, __half* gCl, __half* gAh,
+                         __half* gAl, float* gKzx, float* gLinv, float* gT, float* gq, __half* ws_h, float* ws_f, int M, int N, int L,
+                         cudaStream_t st) {
+  const int64_t sMM = (int64_t)M * M, sMN = (int64_t)M * N, W = sMM * L, LN = (int64_t)L * N;
+  __half* LinvT_h = ws_h + 2 * W; __half* LinvT_l = ws_h + 3 * W;
+  __half* T_h = ws_h + 4 * W; __half* T_l = ws_h + 5 * W;
+  float* stats = ws_f + 2 * LN;
+  unsigned int* ustats = reinterpret_cast<unsigned int*>(stats);
+  const float* sA = stats + ST_S_A * L; const float* sgC = stats + ST_S_GC * L; const float* sgA = stats + ST_S_GA * L;
+  rowabs_max_kernel<<<dim3((unsigned)cdiv(M, 8), L), 256, 0, st>>>(Tm, ustats + ST_TINF * L, M);
+  GPZ_CHECK_LAUNCH();
+  predict_h_bwd_scales_kernel<<<L, 256, 0, st>>>(gv, gm, q, stats, M, N, L);
+  GPZ_CHECK_LAUNCH();
+  predict_h_scale_kernel<<<dim3((unsigned)cdiv(N, 2048), (unsigned)cdiv(M, 16), L), 256, 0, st>>>(C, gv, sgC, gCh, gCl, M, N);
+  GPZ_CHECK_LAUNCH();
+  GPZ_CUDA(cudaMemsetAsync(gq, 0, sizeof(float) * (size_t)L * M, st));
+  int splitk = 1;
+  {
+    const int64_t tiles = cdiv(M, 128) * cdiv(M, 256) * L / 2 + 1;
+    while (splitk < 32 && tiles * splitk < 148 * 2 && N / (splitk * 2) >= 1024) splitk *= 2;
+  }
+  // gT = tril(A gC^T)   (reduction over the N spots, both operands K-major)
+  Umma16Args g4 = h_args(1, M, M, N, Ah, Al, N, sMN, sA, gCh, gCl, N, sMN, sgC, M, sMM, L, 0, 1, splitk);
+  g4.D = gT;
+  int rc = umma_gemm16_ex(g4, (void*)st);
+  if (rc) return rc;
+  // gA = T gC - 2 A gv + q gm^T ;  gq = A gm     (both in the epilogue, which reads the A planes once)
+  UmmaEpilogue e3{3, nullptr, q, gv, gm, nullptr, nullptr, gq};
+  Umma16Args g3 = h_args(0, M, N, M, T_h, T_l, M, sMM, stats + ST_S_T * L, gCh, gCl, N, sMN, sgC, N, sMN, L, 1, 0, 1);
+  g3.Dh = gAh; g3.Dl = gAl; g3.sd = sgA; g3.amax = ustats + ST_AMAX_GA * L; g3.epi = &e3; g3.AuxH = Ah; g3.AuxL = Al; g3.saux = sA;
+  rc = umma_gemm16_ex(g3, (void*)st);
+  if (rc) return rc;
+  // gKzx = Linv^T gA
+  Umma16Args g5 = h_args(0, M, N, M, LinvT_h, LinvT_l, M, sMM, stats + ST_S_LINV * L, gAh, gAl, N, sMN, sgA, N, sMN, L, 2, 0, 1);
+  g5.D = gKzx;
+  rc = umma_gemm16_ex(g5, (void*)st);
+  if (rc) return rc;
+  // gLinv = tril(gA Kzx^T)
+  Umma16Args g6 = h_args(1, M, M, N, gAh, gAl, N, sMN, sgA, Kh, Kl, N, sMN, sK, M, sMM, L, 0, 1, splitk);
+  g6.D = gLinv;
+  return umma_gemm16_ex(g6, (void*)st);
+}
+
 }  // namespace gpz
 
 using namespace gpz;
@@ -264,6 +460,25 @@ extern "C" int gpz_svgp_predict_bwd_tc_f32(const float* Kzx, const float* Kzx_lo
   if (!gpz_svgp_predict_tc_supported(M, N) || L <= 0) return GPZ_ERR_UNSUPPORTED;
   return predict_bwd_tc(Kzx, Kzx_lo, Linv, T, q, A, A_lo, C, C_lo, gm, gv, gA, gA_lo, gKzx, gLinv, gT, gq, ws, M, N, L,
                         (cudaStream_t)stream);
+}
+
+// split-FP16 tensor-core variant (see predict_fwd_h): planes are fp16, ws_h holds 8 L*M*M halfs, ws_f 2 L*N + 16 L floats
+extern "C" int gpz_svgp_predict_h_supported(int M, int N) { return (M % 8 == 0 && N % 8 == 0 && M >= 64 && N >= 256) ? 1 : 0; }
+extern "C" int gpz_svgp_predict_fwd_h_f32(const void* Kh, const void* Kl, const float* sK, const float* Linv, const float* T,
+                                          const float* q, const float* kxx, void* Ah, void* Al, float* C, float* mean, float* var,
+                                          void* ws_h, float* ws_f, int M, int N, int L, void* stream) {
+  if (!gpz_svgp_predict_h_supported(M, N) || L <= 0) return GPZ_ERR_UNSUPPORTED;
+  return predict_fwd_h((const __half*)Kh, (const __half*)Kl, sK, Linv, T, q, kxx, (__half*)Ah, (__half*)Al, C, mean, var,
+                       (__half*)ws_h, ws_f, M, N, L, (cudaStream_t)stream);
+}
+extern "C" int gpz_svgp_predict_bwd_h_f32(const void* Kh, const void* Kl, const float* sK, const float* T, const float* q,
+                                          const void* Ah, const void* Al, const float* C, const float* gm, const float* gv,
+                                          void* gCh, void* gCl, void* gAh, void* gAl, float* gKzx, float* gLinv, float* gT,
+                                          float* gq, void* ws_h, float* ws_f, int M, int N, int L, void* stream) {
+  if (!gpz_svgp_predict_h_supported(M, N) || L <= 0) return GPZ_ERR_UNSUPPORTED;
+  return predict_bwd_h((const __half*)Kh, (const __half*)Kl, sK, T, q, (const __half*)Ah, (const __half*)Al, C, gm, gv,
+                       (__half*)gCh, (__half*)gCl, (__half*)gAh, (__half*)gAl, gKzx, gLinv, gT, gq, (__half*)ws_h, ws_f, M, N, L,
+                       (cudaStream_t)stream);
 }
 
 #define GPZ_PREDICT_IMPL(SUF, T)                                                                                      \

@@ -17,6 +17,7 @@
 // epilogue, tcgen05.ld of the fp32 accumulator -> alpha/Cin/lo-split -> global (or fp32 atomics for split-K).
 // Triangular operands skip whole k-blocks; lower-triangular outputs skip whole tiles.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <atomic>
 #include <cstdlib>
@@ -28,14 +29,17 @@
 namespace gpz {
 namespace umma {
 
-constexpr int BM = 128, BN = 256, BK = 16, STAGES = 4;
+// A stage holds 64 bytes of k per row: 16 fp32 (tf32 arithmetic) or 32 fp16 (split-FP16 arithmetic) elements, so the
+// byte geometry of the K-major tiles (and the stage size) is the same in both modes.
+constexpr int BM = 128, BN = 256, BK = 16, BK16 = 32, STAGES = 4;
 constexpr int A_BYTES = BM * BK * 4;          // 8 KB   (128 rows x 64 B, SWIZZLE_64B)
-constexpr int B_BYTES = BN * BK * 4;          // 16 KB  (MN-major: 8 chunks x 16 rows x 128 B; K-major: 256 rows x 64 B)
+constexpr int B_BYTES = BN * BK * 4;          // 16 KB  (K-major: 256 rows x 64 B; MN-major tf32: 8 chunks x 16 k-rows x 128 B;
+                                              //         MN-major fp16: 4 chunks x 32 k-rows x 128 B)
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // raw + lo of both operands = 48 KB
-constexpr int EPI_LD = 36;                    // padded row length (floats) of the per-warp 32 x 32 epilogue staging tile
-constexpr int EPI_BYTES = 4 * 32 * EPI_LD * 4;  // 4 epilogue warps
+constexpr int EPI_WARPS = 8;                  // two epilogue warps per TMEM lane quadrant, each owns half of the tile's columns
+constexpr int EPI_BYTES = EPI_WARPS * 32 * 32 * 4;  // per-warp 32 x 32 fp32 staging tile, XOR-swizzled 16-byte columns
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
 constexpr uint32_t TMEM_COLS = 512;      // two 128 x 256 fp32 accumulators
 
 struct Params {
@@ -54,6 +58,12 @@ struct Params {
   const float* Aux; const float* rowv; const float* colv1; const float* colv2;
   float* col1; float* col2; float* rowacc;
   float alpha;
+  // split-FP16 mode: operands are (hi, lo) fp16 planes of x * s[b] with per-batch power-of-two scales s
+  int bk;                                 // k elements per stage (BK or BK16)
+  const float* sa; const float* sb;       // operand scales (nullptr = 1): the accumulator is multiplied by 1/(sa[b] sb[b])
+  __half* Dh; __half* Dl; const float* sd;   // optional (hi, lo) fp16 output planes of D * sd[b]  (same ldd / sD as D)
+  unsigned int* amax;                     // optional per-batch max |D| (float bits, atomicMax)
+  const __half* AuxH; const __half* AuxL; const float* saux;   // epi_mode 3: Aux given as fp16 planes instead of fp32
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -106,6 +116,35 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// x * s -> (hi, lo) fp16 pair, hi = rn(x s), lo = rn(x s - hi): 22 significant bits; an out-of-range value becomes inf
+// (and the products NaN) so that a violated scale bound is loud, never silently saturated
+__device__ __forceinline__ void split_half(float xs, __half& h, __half& l) {
+  h = __float2half_rn(xs);
+  l = __float2half_rn(xs - __half2float(h));
+}
+// two values at once with the packed conversions (cvt.rn.f16x2.f32)
+__device__ __forceinline__ void split_half2(float a, float b, uint32_t& h, uint32_t& l) {
+  const __half2 hh = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(hh);
+  const __half2 ll = __floats2half2_rn(a - hf.x, b - hf.y);
+  h = *reinterpret_cast<const uint32_t*>(&hh);
+  l = *reinterpret_cast<const uint32_t*>(&ll);
+}
+__device__ __forceinline__ float unpack_sum(uint32_t h, uint32_t l, int hi_half) {
+  const unsigned short hs = hi_half ? (unsigned short)(h >> 16) : (unsigned short)(h & 0xffffu);
+  const unsigned short ls = hi_half ? (unsigned short)(l >> 16) : (unsigned short)(l & 0xffffu);
+  return __half2float(__ushort_as_half(hs)) + __half2float(__ushort_as_half(ls));
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -153,8 +192,8 @@ __device__ __forceinline__ TileInfo tile_info(const Params& p, int t, int mtiles
   if (p.a_tri == 2) k_lo = max(k_lo, ti.i0);
   if (p.b_tri == 1) k_lo = max(k_lo, ti.j0);
   if (p.b_tri == 2) k_hi = min(k_hi, j1);
-  const int kb0 = k_lo / BK;
-  const int nkb_all = k_hi > kb0 * BK ? (k_hi - kb0 * BK + BK - 1) / BK : 0;
+  const int kb0 = k_lo / p.bk;
+  const int nkb_all = k_hi > kb0 * p.bk ? (k_hi - kb0 * p.bk + p.bk - 1) / p.bk : 0;
   int kb_begin = 0, kb_end = nkb_all;
   if (p.splitk > 1) {
     const int chunk = (nkb_all + p.splitk - 1) / p.splitk;
@@ -173,7 +212,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 // Persistent kernel: one CTA per SM, tiles handed out by an atomic counter.  The 512 TMEM columns hold two 128 x 256 fp32
 // accumulators, so the epilogue of tile i overlaps the MMAs of tile i+1.
-template <bool B_KMAJOR>
+template <bool B_KMAJOR, bool F16>
 __global__ void __launch_bounds__(NTHREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
                  const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo, const Params p,
@@ -195,9 +234,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
     for (int s = 0; s < 2; ++s) {
       mbar_init(accum_full + s, 1);
-      mbar_init(accum_empty + s, 4);             // one arrival per epilogue warp
+      mbar_init(accum_empty + s, EPI_WARPS);     // one arrival per epilogue warp
       mbar_init(sched_full + s, 1);
-      mbar_init(sched_empty + s, 5);             // MMA thread + 4 epilogue warps
+      mbar_init(sched_empty + s, 1 + EPI_WARPS); // MMA thread + epilogue warps
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -229,27 +268,29 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           mbar_wait(empty_bar + s, ph ^ 1u);
           unsigned char* st = smem + s * STAGE_BYTES;
           mbar_expect_tx(full_bar + s, tx_bytes);
-          const int kc = (ti.kb0 + kb) * BK;
+          // MN-major B: chunks of CW columns (128 B rows), CHB bytes apart (tf32: 32 cols x 16 k-rows; fp16: 64 x 32)
+          constexpr int CW = F16 ? 64 : 32, CHB = F16 ? 4096 : 2048;
+          const int kc = (ti.kb0 + kb) * (F16 ? BK16 : BK);
           tma_load_3d(&mapA, full_bar + s, st, kc, ti.i0, ti.b);
           if (B_KMAJOR) {
             tma_load_3d(&mapB, full_bar + s, st + 2 * A_BYTES, kc, ti.j0, ti.b);
-          } else if (p.b_map4d) {                  // one box {32 cols, 16 k-rows, 8 column chunks}: chunk-major in smem
-            tma_load_4d(&mapB, full_bar + s, st + 2 * A_BYTES, 0, kc, ti.j0 / 32, ti.b);
+          } else if (p.b_map4d) {                  // one box {CW cols, k-rows, BN/CW column chunks}: chunk-major in smem
+            tma_load_4d(&mapB, full_bar + s, st + 2 * A_BYTES, 0, kc, ti.j0 / CW, ti.b);
           } else {
 #pragma unroll
-            for (int c = 0; c < BN / 32; ++c)        // 32-column chunks: 16 k-rows x 128 B each, 2 KB apart
-              tma_load_3d(&mapB, full_bar + s, st + 2 * A_BYTES + c * 2048, ti.j0 + c * 32, kc, ti.b);
+            for (int c = 0; c < BN / CW; ++c)
+              tma_load_3d(&mapB, full_bar + s, st + 2 * A_BYTES + c * CHB, ti.j0 + c * CW, kc, ti.b);
           }
           if (p.n_terms == 3) {
             tma_load_3d(&mapAlo, full_bar + s, st + A_BYTES, kc, ti.i0, ti.b);
             if (B_KMAJOR) {
               tma_load_3d(&mapBlo, full_bar + s, st + 2 * A_BYTES + B_BYTES, kc, ti.j0, ti.b);
             } else if (p.b_map4d) {
-              tma_load_4d(&mapBlo, full_bar + s, st + 2 * A_BYTES + B_BYTES, 0, kc, ti.j0 / 32, ti.b);
+              tma_load_4d(&mapBlo, full_bar + s, st + 2 * A_BYTES + B_BYTES, 0, kc, ti.j0 / CW, ti.b);
             } else {
 #pragma unroll
-              for (int c = 0; c < BN / 32; ++c)
-                tma_load_3d(&mapBlo, full_bar + s, st + 2 * A_BYTES + B_BYTES + c * 2048, ti.j0 + c * 32, kc, ti.b);
+              for (int c = 0; c < BN / CW; ++c)
+                tma_load_3d(&mapBlo, full_bar + s, st + 2 * A_BYTES + B_BYTES + c * CHB, ti.j0 + c * CW, kc, ti.b);
             }
           }
         }
@@ -260,7 +301,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     if (lane == 0) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2,
       // a_major [15]=0 (K), b_major [16], N>>3 [17,23), M>>4 [24,29)
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((B_KMAJOR ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+      // operand format 2 = TF32, 0 = F16
+      const uint32_t fmt = F16 ? 0u : 2u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((B_KMAJOR ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) |
                              ((uint32_t)(BM >> 4) << 24);
       uint32_t it = 0, acc_iter = 0;
       for (uint32_t iter = 0;; ++iter) {
@@ -283,14 +326,19 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
           const uint32_t sb = sa + 2 * A_BYTES;
 #pragma unroll
-          for (int ks = 0; ks < BK / 8; ++ks) {
-            // K-major SW64: rows of 64 B, 8-row groups 512 B apart; one K=8 step = 32 B inside the row
+          for (int ks = 0; ks < 2; ++ks) {
+            // K-major SW64: rows of 64 B, 8-row groups 512 B apart; one MMA k-step (8 tf32 / 16 fp16) = 32 B inside the row
             const uint64_t a_raw = make_desc(sa + ks * 32, 16, 512, 4);
             const uint64_t a_lo = make_desc(sa + A_BYTES + ks * 32, 16, 512, 4);
             uint64_t b_raw, b_lo;
             if (B_KMAJOR) {
               b_raw = make_desc(sb + ks * 32, 16, 512, 4);
               b_lo = make_desc(sb + B_BYTES + ks * 32, 16, 512, 4);
+            } else if (F16) {
+              // MN-major fp16: plain SWIZZLE_128B (layout type 2), atoms of 64 columns (128 B) x 8 k-rows: column chunks
+              // 4 KB apart (= LBO), 8-row k groups 1 KB apart (= SBO); one K=16 step = two k groups = 2 KB
+              b_raw = make_desc(sb + ks * 2048, 4096, 1024, 2);
+              b_lo = make_desc(sb + B_BYTES + ks * 2048, 4096, 1024, 2);
             } else {
               // MN-major tf32 must use SWIZZLE_128B_BASE32B (layout type 1; 32 B chunks swizzled inside a 4-row x 128 B
               // atom): chunks of 32 columns (128 B rows) 2 KB apart (= LBO), 4-row k groups 512 B apart (= SBO);
@@ -299,7 +347,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
               b_lo = make_desc(sb + B_BYTES + ks * 1024, 2048, 512, 1);
             }
             const uint32_t acc0 = (kb > 0 || ks > 0) ? 1u : 0u;
-            if (p.n_terms == 3) {
+            if (F16) {
+              if (p.n_terms == 3) {
+                umma_f16(tmem_d, a_raw, b_lo, idesc, acc0);
+                umma_f16(tmem_d, a_lo, b_raw, idesc, 1u);
+                umma_f16(tmem_d, a_raw, b_raw, idesc, 1u);
+              } else {
+                umma_f16(tmem_d, a_raw, b_raw, idesc, acc0);
+              }
+            } else if (p.n_terms == 3) {
               umma_tf32(tmem_d, a_raw, b_lo, idesc, acc0);
               umma_tf32(tmem_d, a_lo, b_raw, idesc, 1u);
               umma_tf32(tmem_d, a_raw, b_raw, idesc, 1u);
@@ -314,12 +370,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       }
     }
   } else {
-    // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4 =====
+    // ===== epilogue: warps 2..9, TMEM lane quadrant = warp % 4; warps 2..5 take column chunks 0..3, warps 6..9 chunks 4..7 =====
     const int q = warp & 3;
+    const int c_begin = ((warp - 2) >> 2) * (BN / 64), c_end = c_begin + BN / 64;
     const bool vec_ok = (p.ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) &&
                         (!p.Dlo || (reinterpret_cast<uintptr_t>(p.Dlo) & 15) == 0) &&
-                        (!p.Cin || (reinterpret_cast<uintptr_t>(p.Cin) & 15) == 0) && ((p.sD % 4) == 0);
-    float* epi = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 2) * 32 * EPI_LD;
+                        (!p.Cin || (reinterpret_cast<uintptr_t>(p.Cin) & 15) == 0) && ((p.sD % 4) == 0) &&
+                        (!p.Dh || ((reinterpret_cast<uintptr_t>(p.Dh) & 7) == 0 && (reinterpret_cast<uintptr_t>(p.Dl) & 7) == 0)) &&
+                        (!p.AuxH || ((reinterpret_cast<uintptr_t>(p.AuxH) & 7) == 0 && (reinterpret_cast<uintptr_t>(p.AuxL) & 7) == 0));
+    float* epi = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 2) * 32 * 32;
     uint32_t acc_iter = 0;
     for (uint32_t iter = 0;; ++iter) {
       const int slot = iter & 1;
@@ -336,6 +395,13 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         mbar_wait(accum_full + as, (acc_iter >> 1) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       }
+      // per-batch scales (powers of two): accumulator -> true value, true value -> fp16 output planes
+      float alpha_b = p.alpha;
+      if (p.sa) alpha_b *= 1.0f / p.sa[ti.b];
+      if (p.sb) alpha_b *= 1.0f / p.sb[ti.b];
+      const float sd_b = (p.Dh && p.sd) ? p.sd[ti.b] : 1.0f;
+      const float inv_saux = (p.AuxH && p.saux) ? 1.0f / p.saux[ti.b] : 1.0f;
+      float amx = 0.f;
       const int gi = ti.i0 + q * 32 + lane;
       const int wrow0 = ti.i0 + q * 32;
       float racc[8];                          // mode 3: per-row partial sums of this lane's 8 rows (coalesced path)
@@ -348,11 +414,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         qreg[u] = (p.epi_mode != 0 && p.epi_mode != 2 && rr < p.m) ? p.rowv[(int64_t)ti.b * p.m + rr] : 0.f;
       }
       const float q_s = (p.epi_mode != 0 && p.epi_mode != 2 && gi < p.m) ? p.rowv[(int64_t)ti.b * p.m + gi] : 0.f;
-      float* Drow = p.D + (int64_t)ti.b * p.sD + (int64_t)gi * p.ldd;
-      float* Lrow = p.Dlo ? p.Dlo + (int64_t)ti.b * p.sD + (int64_t)gi * p.ldd : nullptr;
-      const float* Crow = p.Cin ? p.Cin + (int64_t)ti.b * p.sD + (int64_t)gi * p.ldd : nullptr;
+      const int64_t row_off = (int64_t)ti.b * p.sD + (int64_t)gi * p.ldd;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = c_begin; c < c_end; ++c) {
         uint32_t r[32];
         if (has_acc) {
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)BN + (uint32_t)(c * 32), r);
@@ -371,14 +435,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             const int gj = gj0 + u;
             if (gj >= p.n) break;
             if ((p.d_tri == 1 && gj > gi) || (p.d_tri == 2 && gj < gi)) continue;
-            atomicAdd(Drow + gj, p.alpha * __uint_as_float(r[u]));
+            atomicAdd(p.D + row_off + gj, alpha_b * __uint_as_float(r[u]));
           }
         } else if (warp_full && vec_ok) {
           // transpose the 32 x 32 block through shared memory so that every store instruction writes whole 128-byte
           // lines: lane -> (row = 4*it + lane/8, 4 columns at (lane%8)*4)
+          // (staging tile: row r keeps its 16-byte column c4 at slot c4 ^ (r & 7): conflict-free both ways without padding)
 #pragma unroll
           for (int u = 0; u < 32; u += 4)
-            *reinterpret_cast<float4*>(epi + lane * EPI_LD + u) =
+            *reinterpret_cast<float4*>(epi + lane * 32 + (((u >> 2) ^ (lane & 7)) << 2)) =
                 make_float4(__uint_as_float(r[u]), __uint_as_float(r[u + 1]), __uint_as_float(r[u + 2]), __uint_as_float(r[u + 3]));
           __syncwarp();
           const int cq = (lane & 7) * 4;
@@ -391,15 +456,23 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
           for (int itr = 0; itr < 8; ++itr) {
             const int rr = itr * 4 + (lane >> 3);
-            float4 v = *reinterpret_cast<const float4*>(epi + rr * EPI_LD + cq);
-            v.x *= p.alpha; v.y *= p.alpha; v.z *= p.alpha; v.w *= p.alpha;
+            float4 v = *reinterpret_cast<const float4*>(epi + rr * 32 + (((lane & 7) ^ (rr & 7)) << 2));
+            v.x *= alpha_b; v.y *= alpha_b; v.z *= alpha_b; v.w *= alpha_b;
             const int64_t o = (int64_t)ti.b * p.sD + (int64_t)(ti.i0 + q * 32 + rr) * p.ldd + gj0 + cq;
             if (p.Cin) {
               const float4 cc = *reinterpret_cast<const float4*>(p.Cin + o);
               v.x += cc.x; v.y += cc.y; v.z += cc.z; v.w += cc.w;
             }
             if (p.epi_mode == 3) {
-              const float4 ax = *reinterpret_cast<const float4*>(p.Aux + o);
+              float4 ax;
+              if (p.AuxH) {
+                const uint2 hh = *reinterpret_cast<const uint2*>(p.AuxH + o);
+                const uint2 ll = *reinterpret_cast<const uint2*>(p.AuxL + o);
+                ax.x = unpack_sum(hh.x, ll.x, 0) * inv_saux; ax.y = unpack_sum(hh.x, ll.x, 1) * inv_saux;
+                ax.z = unpack_sum(hh.y, ll.y, 0) * inv_saux; ax.w = unpack_sum(hh.y, ll.y, 1) * inv_saux;
+              } else {
+                ax = *reinterpret_cast<const float4*>(p.Aux + o);
+              }
               const float qv = qreg[itr];
               v.x += fmaf(qv, cv2.x, -2.f * ax.x * cv1.x);
               v.y += fmaf(qv, cv2.y, -2.f * ax.y * cv1.y);
@@ -417,7 +490,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 cs2.x = fmaf(qv, v.x, cs2.x); cs2.y = fmaf(qv, v.y, cs2.y); cs2.z = fmaf(qv, v.z, cs2.z); cs2.w = fmaf(qv, v.w, cs2.w);
               }
             }
-            *reinterpret_cast<float4*>(p.D + o) = v;
+            if (p.D) *reinterpret_cast<float4*>(p.D + o) = v;
             if (p.Dlo) {
               float4 lo;
               lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
@@ -426,6 +499,14 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
               lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
               *reinterpret_cast<float4*>(p.Dlo + o) = lo;
             }
+            if (p.Dh) {
+              uint2 ph, pl;
+              split_half2(v.x * sd_b, v.y * sd_b, ph.x, pl.x);
+              split_half2(v.z * sd_b, v.w * sd_b, ph.y, pl.y);
+              *reinterpret_cast<uint2*>(p.Dh + o) = ph;
+              *reinterpret_cast<uint2*>(p.Dl + o) = pl;
+            }
+            if (p.amax) amx = fmaxf(amx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
           }
           if (p.epi_mode == 1 || p.epi_mode == 2) {
             // column sums over the warp's 32 rows: combine the four row groups (lane/8), then lanes 0..7 own 4 columns each
@@ -453,10 +534,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             const int gj = gj0 + u;
             if (gj >= p.n) break;
             if ((p.d_tri == 1 && gj > gi) || (p.d_tri == 2 && gj < gi)) continue;
-            float v = p.alpha * __uint_as_float(r[u]);
-            if (Crow) v += Crow[gj];
+            float v = alpha_b * __uint_as_float(r[u]);
+            if (p.Cin) v += p.Cin[row_off + gj];
             if (p.epi_mode == 3) {
-              const float ax = p.Aux[(int64_t)ti.b * p.sD + (int64_t)gi * p.ldd + gj];
+              const float ax = p.AuxH ? (__half2float(p.AuxH[row_off + gj]) + __half2float(p.AuxL[row_off + gj])) * inv_saux
+                                      : p.Aux[row_off + gj];
               const float g2 = p.colv2[(int64_t)ti.b * p.n + gj];
               v += fmaf(q_s, g2, -2.f * ax * p.colv1[(int64_t)ti.b * p.n + gj]);
               racc_s = fmaf(ax, g2, racc_s);
@@ -464,8 +546,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
               atomicAdd(p.col1 + (int64_t)ti.b * p.n + gj, v * v);
               if (p.epi_mode == 1) atomicAdd(p.col2 + (int64_t)ti.b * p.n + gj, q_s * v);
             }
-            Drow[gj] = v;
-            if (Lrow) Lrow[gj] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+            if (p.D) p.D[row_off + gj] = v;
+            if (p.Dlo) p.Dlo[row_off + gj] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+            if (p.Dh) {
+              __half h, l;
+              split_half(v * sd_b, h, l);
+              p.Dh[row_off + gj] = h;
+              p.Dl[row_off + gj] = l;
+            }
+            if (p.amax) amx = fmaxf(amx, fabsf(v));
           }
         }
       }
@@ -478,6 +567,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           }
         }
         if (gi < p.m && racc_s != 0.f) atomicAdd(p.rowacc + (int64_t)ti.b * p.m + gi, racc_s);
+      }
+      if (p.amax) {
+#pragma unroll
+        for (int sh = 16; sh > 0; sh >>= 1) amx = fmaxf(amx, __shfl_xor_sync(0xffffffffu, amx, sh));
+        if (lane == 0 && amx > 0.f) atomicMax(p.amax + ti.b, __float_as_uint(amx));
       }
       if (has_acc) {
         // this warp is done reading the accumulator stage: hand it back to the MMA thread
@@ -555,6 +649,46 @@ static int make_map_mnmajor4d(CUtensorMap* map, const float* base, int k, int n,
   return r == CUDA_SUCCESS ? GPZ_OK : GPZ_ERR_BADARG;
 }
 
+// ---- fp16 planes (split-FP16 mode): same byte geometry for K-major tiles; MN-major tiles use plain SWIZZLE_128B ----
+static int make_map_kmajor16(CUtensorMap* map, const __half* base, int rows, int k, int64_t ld, int64_t sB, int batch, int box_rows) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return GPZ_ERR_UNSUPPORTED;
+  cuuint64_t gdim[3] = {(cuuint64_t)k, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(batch > 1 ? sB : (int64_t)rows * ld) * 2};
+  cuuint32_t box[3] = {(cuuint32_t)BK16, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? GPZ_OK : GPZ_ERR_BADARG;
+}
+// MN-major fp16: 3-D map {n, k, batch}, box {64, 32, 1} (128 B rows)
+static int make_map_mnmajor16(CUtensorMap* map, const __half* base, int k, int n, int64_t ld, int64_t sB, int batch) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return GPZ_ERR_UNSUPPORTED;
+  cuuint64_t gdim[3] = {(cuuint64_t)n, (cuuint64_t)k, (cuuint64_t)batch};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(batch > 1 ? sB : (int64_t)k * ld) * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)BK16, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? GPZ_OK : GPZ_ERR_BADARG;
+}
+// MN-major fp16 with n % 64 == 0: 4-D view {64, k, n/64, batch}, ONE box {64, 32, 4, 1} per stage, chunk-major in smem
+static int make_map_mnmajor16_4d(CUtensorMap* map, const __half* base, int k, int n, int64_t ld, int64_t sB, int batch) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return GPZ_ERR_UNSUPPORTED;
+  cuuint64_t gdim[4] = {64, (cuuint64_t)k, (cuuint64_t)(n / 64), (cuuint64_t)batch};
+  cuuint64_t gstr[3] = {(cuuint64_t)ld * 2, 128, (cuuint64_t)(batch > 1 ? sB : (int64_t)k * ld) * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)BK16, (cuuint32_t)(BN / 64), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? GPZ_OK : GPZ_ERR_BADARG;
+}
+
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 constexpr int NUM_COUNTERS = 256;
@@ -565,6 +699,44 @@ __device__ unsigned int g_tile_counters[NUM_COUNTERS];
 
 using namespace gpz;
 using namespace gpz::umma;
+
+// common launch: persistent grid, dynamic tile scheduler (one counter per in-flight launch, taken round-robin from a small
+// device array)
+static int launch_gemm(bool b_kmajor, bool f16, const CUtensorMap& mA, const CUtensorMap& mAlo, const CUtensorMap& mB,
+                       const CUtensorMap& mBlo, const Params& p, cudaStream_t st) {
+  const int mtiles = (int)cdiv(p.m, BM), ntiles = (int)cdiv(p.n, BN);
+  const int64_t total64 = (int64_t)mtiles * ntiles * p.batch * p.splitk;
+  if (total64 > 0x7fffffff) return GPZ_ERR_UNSUPPORTED;
+  const int total = (int)total64;
+  static unsigned int* counters = nullptr;
+  static std::atomic<unsigned int> next_slot{0};
+  static int num_sms = 0;
+  if (!counters) {
+    unsigned int* ptr = nullptr;
+    GPZ_CUDA(cudaGetSymbolAddress((void**)&ptr, g_tile_counters));
+    counters = ptr;
+    int dev = 0;
+    GPZ_CUDA(cudaGetDevice(&dev));
+    GPZ_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    GPZ_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    GPZ_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    GPZ_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    GPZ_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  }
+  unsigned int* counter = counters + (next_slot.fetch_add(1) % NUM_COUNTERS);
+  GPZ_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+  const int grid = total < num_sms ? total : num_sms;
+  if (f16) {
+    if (b_kmajor) umma_gemm_kernel<true, true><<<grid, NTHREADS, SMEM_BYTES, st>>>(mA, mAlo, mB, mBlo, p, counter, total, mtiles, ntiles);
+    else umma_gemm_kernel<false, true><<<grid, NTHREADS, SMEM_BYTES, st>>>(mA, mAlo, mB, mBlo, p, counter, total, mtiles, ntiles);
+  } else {
+    if (b_kmajor) umma_gemm_kernel<true, false><<<grid, NTHREADS, SMEM_BYTES, st>>>(mA, mAlo, mB, mBlo, p, counter, total, mtiles, ntiles);
+    else umma_gemm_kernel<false, false><<<grid, NTHREADS, SMEM_BYTES, st>>>(mA, mAlo, mB, mBlo, p, counter, total, mtiles, ntiles);
+  }
+  GPZ_CHECK_LAUNCH();
+  return GPZ_OK;
+}
+
 
 // 1 if the tcgen05 path can take this problem (alignment / divisibility), 0 otherwise (caller uses gpz_gemm_f32)
 extern "C" int gpz_umma_gemm_supported(int b_kmajor, int m, int n, int k, int64_t lda, int64_t ldb, int64_t ldd) {
@@ -628,35 +800,58 @@ int umma_gemm_ex(int b_kmajor, int m, int n, int k, float alpha, const float* A,
   if (p.epi_mode != 0 && (splitk > 1 || d_tri != 0)) return GPZ_ERR_BADARG;
   p.D = D; p.Dlo = Dlo; p.Cin = Cin; p.m = m; p.n = n; p.k = k; p.ldd = ldd; p.sD = sD; p.batch = batch; p.splitk = splitk;
   p.a_tri = a_tri; p.b_tri = b_tri; p.d_tri = d_tri; p.n_terms = n_terms; p.alpha = alpha;
-  const int mtiles = (int)cdiv(m, BM), ntiles = (int)cdiv(n, BN);
-  const int64_t total64 = (int64_t)mtiles * ntiles * batch * splitk;
-  if (total64 > 0x7fffffff) return GPZ_ERR_UNSUPPORTED;
-  const int total = (int)total64;
-  cudaStream_t st = (cudaStream_t)stream;
-  // dynamic tile scheduler: one counter per in-flight launch, taken round-robin from a small device array
-  static unsigned int* counters = nullptr;
-  static std::atomic<unsigned int> next_slot{0};
-  static int num_sms = 0;
-  if (!counters) {
-    unsigned int* ptr = nullptr;
-    GPZ_CUDA(cudaGetSymbolAddress((void**)&ptr, g_tile_counters));
-    counters = ptr;
-    int dev = 0;
-    GPZ_CUDA(cudaGetDevice(&dev));
-    GPZ_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
-  unsigned int* counter = counters + (next_slot.fetch_add(1) % NUM_COUNTERS);
-  GPZ_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
-  const int grid = total < num_sms ? total : num_sms;
-  if (b_kmajor) {
-    GPZ_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    umma_gemm_kernel<true><<<grid, NTHREADS, SMEM_BYTES, st>>>(mA, mAlo, mB, mBlo, p, counter, total, mtiles, ntiles);
+  p.bk = BK; p.sa = nullptr; p.sb = nullptr; p.Dh = nullptr; p.Dl = nullptr; p.sd = nullptr; p.amax = nullptr;
+  p.AuxH = nullptr; p.AuxL = nullptr; p.saux = nullptr;
+  return launch_gemm(b_kmajor != 0, false, mA, mAlo, mB, mBlo, p, (cudaStream_t)stream);
+}
+
+// split-FP16 GEMM: every operand is a pair of fp16 planes (hi, lo) of x * s[b]; three kind::f16 MMAs per k-step
+// (hi*lo + lo*hi + hi*hi) give ~2^-22 relative accuracy per product at twice the MMA rate of split-TF32.
+int umma_gemm16_ex(const Umma16Args& g, void* stream) {
+  if (g.m < 1 || g.n < 1 || g.k < 1 || g.batch < 1) return GPZ_ERR_BADARG;
+  if (g.lda % 8 || g.ldb % 8 || g.sA % 8 || g.sB % 8) return GPZ_ERR_UNSUPPORTED;       // 16-byte global strides for TMA
+  if (!aligned16(g.Ah) || !aligned16(g.Al) || !aligned16(g.Bh) || !aligned16(g.Bl)) return GPZ_ERR_UNSUPPORTED;
+  int splitk = g.splitk < 1 ? 1 : g.splitk;
+  if (splitk > 1 && (g.Dh || !g.D || g.amax)) return GPZ_ERR_BADARG;
+  if (!g.D && !g.Dh) return GPZ_ERR_BADARG;
+  if (g.Dh && !g.Dl) return GPZ_ERR_BADARG;
+  CUtensorMap mA, mAlo, mB, mBlo;
+  int b_map4d = 0;
+  int rc = make_map_kmajor16(&mA, g.Ah, g.m, g.k, g.lda, g.sA, g.batch, BM);
+  if (rc) return rc;
+  rc = make_map_kmajor16(&mAlo, g.Al, g.m, g.k, g.lda, g.sA, g.batch, BM);
+  if (rc) return rc;
+  if (g.b_kmajor) {
+    rc = make_map_kmajor16(&mB, g.Bh, g.n, g.k, g.ldb, g.sB, g.batch, BN);
+    if (rc) return rc;
+    rc = make_map_kmajor16(&mBlo, g.Bl, g.n, g.k, g.ldb, g.sB, g.batch, BN);
   } else {
-    GPZ_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    umma_gemm_kernel<false><<<grid, NTHREADS, SMEM_BYTES, st>>>(mA, mAlo, mB, mBlo, p, counter, total, mtiles, ntiles);
+    b_map4d = (g.n % 64 == 0) ? 1 : 0;
+    if (b_map4d) {
+      rc = make_map_mnmajor16_4d(&mB, g.Bh, g.k, g.n, g.ldb, g.sB, g.batch);
+      if (rc == GPZ_OK) rc = make_map_mnmajor16_4d(&mBlo, g.Bl, g.k, g.n, g.ldb, g.sB, g.batch);
+      if (rc != GPZ_OK) b_map4d = 0;
+    }
+    if (!b_map4d) {
+      rc = make_map_mnmajor16(&mB, g.Bh, g.k, g.n, g.ldb, g.sB, g.batch);
+      if (rc) return rc;
+      rc = make_map_mnmajor16(&mBlo, g.Bl, g.k, g.n, g.ldb, g.sB, g.batch);
+    }
   }
-  GPZ_CHECK_LAUNCH();
-  return GPZ_OK;
+  if (rc) return rc;
+  Params p;
+  const UmmaEpilogue* epi = g.epi;
+  p.b_map4d = b_map4d;
+  p.epi_mode = epi ? epi->mode : 0;
+  p.Aux = epi ? epi->Aux : nullptr; p.rowv = epi ? epi->rowv : nullptr; p.colv1 = epi ? epi->colv1 : nullptr;
+  p.colv2 = epi ? epi->colv2 : nullptr; p.col1 = epi ? epi->col1 : nullptr; p.col2 = epi ? epi->col2 : nullptr;
+  p.rowacc = epi ? epi->rowacc : nullptr;
+  if (p.epi_mode != 0 && (splitk > 1 || g.d_tri != 0)) return GPZ_ERR_BADARG;
+  p.D = g.D; p.Dlo = nullptr; p.Cin = nullptr; p.m = g.m; p.n = g.n; p.k = g.k; p.ldd = g.ldd; p.sD = g.sD; p.batch = g.batch;
+  p.splitk = splitk; p.a_tri = g.a_tri; p.b_tri = 0; p.d_tri = g.d_tri; p.n_terms = g.n_terms == 1 ? 1 : 3; p.alpha = g.alpha;
+  p.bk = BK16; p.sa = g.sa; p.sb = g.sb; p.Dh = g.Dh; p.Dl = g.Dl; p.sd = g.sd; p.amax = g.amax;
+  p.AuxH = g.AuxH; p.AuxL = g.AuxL; p.saux = g.saux;
+  return launch_gemm(g.b_kmajor != 0, true, mA, mAlo, mB, mBlo, p, (cudaStream_t)stream);
 }
 
 // lo = x - tf32_trunc(x) for a flat array, and (optionally) the batched transpose of an M x M matrix with its lo part
@@ -706,4 +901,91 @@ extern "C" int gpz_transpose_lo_f32(const float* x, float* xt, float* xt_lo, int
   transpose_lo_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, xt, xt_lo, M);
   GPZ_CHECK_LAUNCH();
   return GPZ_OK;
+}
+
+// ---- split-FP16 operand preparation -----------------------------------------------------------------
+namespace gpz {
+namespace umma {
+__global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ x, int64_t per_batch, unsigned int* __restrict__ amax) {
+  const float* xb = x + (int64_t)blockIdx.y * per_batch;
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_batch; i += (int64_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(xb[i]));
+#pragma unroll
+  for (int sh = 16; sh > 0; sh >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, sh));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax + blockIdx.y, __float_as_uint(m));
+}
+
+__global__ void split16_kernel(const float* __restrict__ x, int rows, int cols, const unsigned int* __restrict__ amax,
+                               float* __restrict__ scale, __half* __restrict__ h, __half* __restrict__ l, __half* __restrict__ hT,
+                               __half* __restrict__ lT) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const float s = gpz_pow2_scale(__uint_as_float(amax[b]));
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0) scale[b] = s;
+  const int64_t base = (int64_t)b * rows * cols;
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int i = by + r, j = bx + threadIdx.x;
+    float v = 0.f;
+    if (i < rows && j < cols) {
+      v = x[base + (int64_t)i * cols + j] * s;
+      __half hh, ll;
+      split_half(v, hh, ll);
+      if (h) { h[base + (int64_t)i * cols + j] = hh; l[base + (int64_t)i * cols + j] = ll; }
+    }
+    tile[r][threadIdx.x] = v;
+  }
+  if (!hT) return;
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int i = bx + r, j = by + threadIdx.x;          // transposed output (i, j) = input (j, i); shape cols x rows
+    if (i < cols && j < rows) {
+      __half hh, ll;
+      split_half(tile[threadIdx.x][r], hh, ll);
+      hT[base + (int64_t)i * rows + j] = hh;
+      lT[base + (int64_t)i * rows + j] = ll;
+    }
+  }
+}
+}  // namespace umma
+}  // namespace gpz
+
+int split16_amax(const float* x, int64_t per_batch, int batch, unsigned int* amax_bits, void* stream) {
+  if (per_batch <= 0 || batch <= 0) return GPZ_OK;
+  const unsigned chunks = (unsigned)std::min<int64_t>(cdiv(per_batch, 256 * 8), 1024);
+  amax_kernel<<<dim3(chunks, batch), 256, 0, (cudaStream_t)stream>>>(x, per_batch, amax_bits);
+  GPZ_CHECK_LAUNCH();
+  return GPZ_OK;
+}
+int split16_planes(const float* x, int rows, int cols, int batch, const unsigned int* amax_bits, float* scale, __half* h, __half* l,
+                   __half* hT, __half* lT, void* stream) {
+  if (rows <= 0 || cols <= 0 || batch <= 0) return GPZ_OK;
+  dim3 grid((unsigned)cdiv(cols, 32), (unsigned)cdiv(rows, 32), batch);
+  split16_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, rows, cols, amax_bits, scale, h, l, hT, lT);
+  GPZ_CHECK_LAUNCH();
+  return GPZ_OK;
+}
+
+// x (batch x rows x cols fp32) -> fp16 planes (h, l) of x * scale[b] and optionally of the transposes; amax_ws: batch uint32 scratch
+extern "C" int gpz_split16_f32(const float* x, int rows, int cols, int batch, void* h, void* l, void* hT, void* lT, float* scale,
+                               void* amax_ws, void* stream) {
+  GPZ_CUDA(cudaMemsetAsync(amax_ws, 0, sizeof(unsigned int) * (size_t)batch, (cudaStream_t)stream));
+  int rc = split16_amax(x, (int64_t)rows * cols, batch, (unsigned int*)amax_ws, stream);
+  if (rc) return rc;
+  return split16_planes(x, rows, cols, batch, (const unsigned int*)amax_ws, scale, (__half*)h, (__half*)l, (__half*)hT, (__half*)lT,
+                        stream);
+}
+
+extern "C" int gpz_umma_gemm16_f32(int b_kmajor, int m, int n, int k, float alpha, const void* Ah, const void* Al, int64_t lda,
+                                   int64_t sA, const float* sa, const void* Bh, const void* Bl, int64_t ldb, int64_t sB,
+                                   const float* sb, float* D, void* Dh, void* Dl, const float* sd, void* amax, int64_t ldd, int64_t sD,
+                                   int batch, int a_tri, int d_tri, int splitk, int n_terms, void* stream) {
+  Umma16Args g{};
+  g.b_kmajor = b_kmajor; g.m = m; g.n = n; g.k = k; g.alpha = alpha;
+  g.Ah = (const __half*)Ah; g.Al = (const __half*)Al; g.lda = lda; g.sA = sA; g.sa = sa;
+  g.Bh = (const __half*)Bh; g.Bl = (const __half*)Bl; g.ldb = ldb; g.sB = sB; g.sb = sb;
+  g.D = D; g.ldd = ldd; g.sD = sD; g.Dh = (__half*)Dh; g.Dl = (__half*)Dl; g.sd = sd; g.amax = (unsigned int*)amax;
+  g.batch = batch; g.a_tri = a_tri; g.d_tri = d_tri; g.splitk = splitk; g.n_terms = n_terms;
+  return umma_gemm16_ex(g, stream);
 }

@@ -7,6 +7,8 @@ All Functions work on L-batched, contiguous CUDA tensors in float32 or float64.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
@@ -18,7 +20,10 @@ from ._cabi import c_f, c_i, c_i64, c_p, call, ptr, scalar
 # reference's torch.linalg.cholesky (one device sync).  Throughput runs may turn it off and call
 # `check_cholesky_info()` when they read the loss.
 SYNC_CHECKS = True
-USE_TENSOR_CORES = True      # fp32: route large contractions through the tcgen05 split-TF32 kernels
+USE_TENSOR_CORES = True      # fp32: route large contractions through the tcgen05 kernels
+# arithmetic of the N-proportional tensor-core GEMMs (K3/K4 and backward): "fp16x3" = split-FP16 (fp16 operand planes, f16 MMA
+# rate), "tf32x3" = split-TF32 (fp32 + lo planes, half the rate; also used when a shape is not 8-aligned)
+TENSOR_CORE_ARITH = os.environ.get("GPZ_TC_ARITH", "fp16x3")
 _pending_info = []
 
 
@@ -155,6 +160,41 @@ class KernelBuild(Function):
              c_i(n1), c_i(n2), c_i(D), c_i(L), c_i(r2.shape[0] if mg else 0), scalar(dt, ctx.p_half), ptr(G),
              ptr(g_x1), ptr(g_x2), ptr(g_sigma), ptr(g_ls), ptr(g_a), ptr(ws))
         return g_x1, g_x2, g_sigma, g_ls, g_a, None, None, None, None, None, None
+
+
+class KernelBuildH(Function):
+    """KernelBuild for the split-FP16 tensor-core path: K is written once, as the fp16 planes (Kh, Kl) with Kh + Kl ~= K * sK[l]
+    (4 bytes per entry; csrc/kernel_build.cu kbuild_fwd_h_kernel).  The first output is a zero-storage stand-in with K's shape
+    whose only job is to carry dL/dK back to `gpz_kernel_build_bwd` (which recomputes K and never needed it stored)."""
+
+    @staticmethod
+    def forward(ctx, x1, x2, sigma, ls, a, r2, g1, g2, p_half, jitter):
+        x1, x2, sigma, ls = _c(x1), _c(x2), _c(sigma), _c(ls)
+        dt = x1.dtype
+        assert dt == torch.float32
+        n1, D = x1.shape
+        n2 = x2.shape[0]
+        L = sigma.numel()
+        mg = g1 is not None
+        if mg:
+            a, r2, g1, g2 = _c(a), _c(r2), _c(g1), _c(g2)
+        Kh = torch.empty((L, n1, n2), dtype=torch.float16, device=x1.device)
+        Kl = torch.empty_like(Kh)
+        sK = torch.empty(L, dtype=dt, device=x1.device)
+        call("kernel_build_fwd_h", dt, ptr(x1), ptr(x2), ptr(sigma), ptr(ls), ptr(a if mg else None),
+             ptr(r2 if mg else None), ptr(g1 if mg else None), ptr(g2 if mg else None), c_i(n1), c_i(n2), c_i(D), c_i(L),
+             c_i(r2.shape[0] if mg else 0), scalar(dt, p_half), scalar(dt, jitter), ptr(Kh), ptr(Kl), ptr(sK))
+        ctx.save_for_backward(x1, x2, sigma, ls, a if mg else None, r2 if mg else None, g1 if mg else None,
+                              g2 if mg else None)
+        ctx.p_half = p_half
+        handle = torch.empty(1, dtype=dt, device=x1.device).expand(L, n1, n2)
+        ctx.mark_non_differentiable(Kh, Kl, sK)
+        return handle, Kh, Kl, sK
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, G, *unused):
+        return KernelBuild.backward(ctx, G)[:10]
 
 
 def cdist(x1, x2):
@@ -316,6 +356,53 @@ class Predict(Function):
         return gv, gKzx, gLinv, gT, gq, None
 
 
+def predict_h_ok(dtype, M, N):
+    """fp32 problems large and aligned enough for the split-FP16 tcgen05 path."""
+    return (USE_TENSOR_CORES and TENSOR_CORE_ARITH == "fp16x3" and dtype == torch.float32
+            and bool(_cabi.lib().gpz_svgp_predict_h_supported(c_i(int(M)), c_i(int(N)))))
+
+
+class PredictH(Function):
+    """Predict on fp16 operand planes (split-FP16 tcgen05 GEMMs, csrc/predict.cu predict_fwd_h / predict_bwd_h).
+    `Kzx` is KernelBuildH's stand-in (it only routes dL/dKzx); (Kh, Kl, sK) are the planes it wrote."""
+
+    @staticmethod
+    def forward(ctx, Kxx, Kzx, Linv, T, q, Kh, Kl, sK):
+        Kxx, Linv, T, q, Kh, Kl, sK = _c(Kxx), _c(Linv), _c(T), _c(q), _c(Kh), _c(Kl), _c(sK)
+        dt = Linv.dtype
+        L, M, N = Kh.shape
+        dev = Kh.device
+        Ah, Al = torch.empty_like(Kh), torch.empty_like(Kh)
+        C = torch.empty((L, M, N), dtype=dt, device=dev)
+        mean = torch.empty((L, N), dtype=dt, device=dev)
+        var = torch.empty_like(mean)
+        ws_h = torch.empty(8 * L * M * M, dtype=torch.float16, device=dev)
+        ws_f = torch.empty(2 * L * N + 16 * L, dtype=dt, device=dev)
+        call("svgp_predict_fwd_h", dt, ptr(Kh), ptr(Kl), ptr(sK), ptr(Linv), ptr(T), ptr(q), ptr(Kxx), ptr(Ah), ptr(Al), ptr(C),
+             ptr(mean), ptr(var), ptr(ws_h), ptr(ws_f), c_i(M), c_i(N), c_i(L))
+        ctx.save_for_backward(Kh, Kl, sK, Linv, T, q, Ah, Al, C, ws_h, ws_f)
+        return mean, var
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gm, gv):
+        Kh, Kl, sK, Linv, T, q, Ah, Al, C, ws_h, ws_f = ctx.saved_tensors
+        dt = Linv.dtype
+        L, M, N = Kh.shape
+        dev = Kh.device
+        gm = _c(gm) if gm is not None else torch.zeros((L, N), dtype=dt, device=dev)
+        gv = _c(gv) if gv is not None else torch.zeros((L, N), dtype=dt, device=dev)
+        gCh, gCl, gAh, gAl = (torch.empty_like(Kh) for _ in range(4))
+        gKzx = torch.empty((L, M, N), dtype=dt, device=dev)
+        gLinv = torch.zeros_like(Linv)
+        gT = torch.zeros_like(T)
+        gq = torch.empty_like(q)
+        call("svgp_predict_bwd_h", dt, ptr(Kh), ptr(Kl), ptr(sK), ptr(T), ptr(q), ptr(Ah), ptr(Al), ptr(C), ptr(gm), ptr(gv),
+             ptr(gCh), ptr(gCl), ptr(gAh), ptr(gAl), ptr(gKzx), ptr(gLinv), ptr(gT), ptr(gq), ptr(ws_h), ptr(ws_f),
+             c_i(M), c_i(N), c_i(L))
+        return gv, gKzx, gLinv, gT, gq, None, None, None
+
+
 def umma_gemm(A, B, b_kmajor, Alo=None, Blo=None, Cin=None, alpha=1.0, want_lo=False, a_tri=0, b_tri=0, d_tri=0, splitk=1,
               n_terms=3):
     """Direct access to the tcgen05 split-TF32 batched GEMM (fp32).  A: (b, m, k); B: (b, k, n) or, b_kmajor, (b, n, k)."""
@@ -331,6 +418,43 @@ def umma_gemm(A, B, b_kmajor, Alo=None, Blo=None, Cin=None, alpha=1.0, want_lo=F
          c_i64(A.shape[1] * A.shape[2]), ptr(B), ptr(Blo), c_i64(B.shape[2]), c_i64(B.shape[1] * B.shape[2]), ptr(Cin), ptr(D),
          ptr(Dlo), c_i64(n), c_i64(m * n), c_i(bsz), c_i(a_tri), c_i(b_tri), c_i(d_tri), c_i(splitk), c_i(n_terms))
     return (D, Dlo) if want_lo else D
+
+
+def split16(x, transpose=False):
+    """fp16 operand planes of a batch of fp32 matrices for the split-FP16 GEMM: (hi, lo, scale) with hi + lo ~= x * scale[b]
+    (22 significant bits) and scale[b] the power of two that puts max |x[b]| in (2^14, 2^15].  transpose=True also returns the
+    planes of the per-matrix transposes: (hi, lo, hiT, loT, scale)."""
+    x = _c(x)
+    bsz, rows, cols = x.shape
+    h = torch.empty((bsz, rows, cols), dtype=torch.float16, device=x.device)
+    l = torch.empty_like(h)
+    hT = torch.empty((bsz, cols, rows), dtype=torch.float16, device=x.device) if transpose else None
+    lT = torch.empty_like(hT) if transpose else None
+    scale = torch.empty(bsz, dtype=torch.float32, device=x.device)
+    ws = torch.empty(bsz, dtype=torch.int32, device=x.device)
+    call("split16", torch.float32, ptr(x), c_i(rows), c_i(cols), c_i(bsz), ptr(h), ptr(l), ptr(hT), ptr(lT), ptr(scale), ptr(ws))
+    return (h, l, hT, lT, scale) if transpose else (h, l, scale)
+
+
+def umma_gemm16(A, B, b_kmajor, a_tri=0, d_tri=0, splitk=1, n_terms=3, alpha=1.0, out_planes=False, out_scale=None,
+                want_amax=False):
+    """Direct access to the tcgen05 split-FP16 batched GEMM.  A = (hi, lo, scale) planes of (b, m, k); B = planes of (b, k, n) or,
+    b_kmajor, (b, n, k).  Returns fp32 D, or with out_planes the fp16 planes (Dh, Dl) of D * out_scale; want_amax adds max |D|."""
+    Ah, Al, sa = A
+    Bh, Bl, sb = B
+    bsz, m, k = Ah.shape
+    n = Bh.shape[1] if b_kmajor else Bh.shape[2]
+    dev = Ah.device
+    D = None if out_planes else torch.zeros((bsz, m, n), dtype=torch.float32, device=dev)
+    Dh = torch.zeros((bsz, m, n), dtype=torch.float16, device=dev) if out_planes else None
+    Dl = torch.zeros_like(Dh) if out_planes else None
+    amax = torch.zeros(bsz, dtype=torch.int32, device=dev) if want_amax else None
+    call("umma_gemm16", torch.float32, c_i(int(b_kmajor)), c_i(m), c_i(n), c_i(k), c_f(alpha), ptr(Ah), ptr(Al), c_i64(Ah.shape[2]),
+         c_i64(Ah.shape[1] * Ah.shape[2]), ptr(sa), ptr(Bh), ptr(Bl), c_i64(Bh.shape[2]), c_i64(Bh.shape[1] * Bh.shape[2]), ptr(sb),
+         ptr(D), ptr(Dh), ptr(Dl), ptr(out_scale), ptr(amax), c_i64(n), c_i64(m * n), c_i(bsz), c_i(a_tri), c_i(d_tri), c_i(splitk),
+         c_i(n_terms))
+    res = (Dh, Dl) if out_planes else D
+    return (res, amax.view(torch.float32)) if want_amax else res
 
 
 # (x, lo) planes and transposes of the M x M operands are needed by several GEMMs of one step (Linv: whitening, predict,

@@ -58,9 +58,10 @@ class _SparseGPBase(nn.Module):
         self.constraint = constraints.lower_cholesky
 
     # -- kernel calls -------------------------------------------------------------------------------
-    def _kernel_matrices(self, X, groupsX=None, want_lo=False):
-        """Kxx (diag), Kzx, Kzz (+jitter).  want_lo: Kzx comes back as (Kzx, Kzx_lo) for the tensor-core path."""
-        kw = {"_want_lo": True} if want_lo else {}
+    def _kernel_matrices(self, X, groupsX=None, want_lo=False, want_h=False):
+        """Kxx (diag), Kzx, Kzz (+jitter).  want_lo: Kzx comes back as (Kzx, Kzx_lo) for the split-TF32 tensor-core path;
+        want_h: as (stand-in, Kh, Kl, scale) fp16 planes for the split-FP16 path."""
+        kw = {"_want_h": True} if want_h else ({"_want_lo": True} if want_lo else {})
         if groupsX is not None:
             gZ = self.groupsZ
             Kxx = self.kernel(X, X, groupsX, groupsX, diag=True)
@@ -92,18 +93,27 @@ class _SparseGPBase(nn.Module):
     def moments(self, X, groupsX=None):
         """Fused predictive moments: returns dict(mean, var (unclamped), T, q, Lc, Lu), all L-batched."""
         F.clear_step_cache()
-        want_lo = F.tensor_core_predict_ok(X.dtype, self.Z.shape[0], X.shape[0])
-        Kxx, Kzx, Kzz = self._kernel_matrices(X, groupsX, want_lo)
+        want_h = F.predict_h_ok(X.dtype, self.Z.shape[0], X.shape[0])
+        want_lo = (not want_h) and F.tensor_core_predict_ok(X.dtype, self.Z.shape[0], X.shape[0])
+        Kxx, Kzx, Kzz = self._kernel_matrices(X, groupsX, want_lo, want_h)
+        Lc, Linv, Lu, T, q, L = self._whitened(Kzz)
+        Kxx = Kxx if Kxx.dim() == 2 else Kxx.unsqueeze(0)
+        if Kxx.shape[0] != L:
+            Kxx = Kxx.expand(L, -1)
+        if want_h:
+            Kzx, Kh, Kl, sK = Kzx
+            if Kh.shape[0] != L:
+                Kzx, Kh, Kl, sK = Kzx.expand(L, -1, -1), Kh.expand(L, -1, -1), Kl.expand(L, -1, -1), sK.expand(L)
+            mean, var = F.PredictH.apply(Kxx, Kzx, Linv, T, q, Kh, Kl, sK)
+            return dict(mean=mean, var=var, T=T, q=q, Lc=Lc, Lu=Lu)
         Kzx_lo = None
         if want_lo:
             Kzx, Kzx_lo = Kzx
-        Lc, Linv, Lu, T, q, L = self._whitened(Kzz)
         Kzx = _as3(Kzx)
-        Kxx = Kxx if Kxx.dim() == 2 else Kxx.unsqueeze(0)
         if Kzx_lo is not None:
             Kzx_lo = _as3(Kzx_lo)
         if Kzx.shape[0] != L:
-            Kzx, Kxx = Kzx.expand(L, -1, -1), Kxx.expand(L, -1)
+            Kzx = Kzx.expand(L, -1, -1)
             Kzx_lo = Kzx_lo.expand(L, -1, -1) if Kzx_lo is not None else None
         mean, var = F.Predict.apply(Kxx, Kzx, Linv, T, q, Kzx_lo)
         return dict(mean=mean, var=var, T=T, q=q, Lc=Lc, Lu=Lu)

@@ -43,10 +43,15 @@ class _RBFBase(nn.Module):
     def _group_coeff(self):
         return None
 
-    def _build(self, X, Z, groupsX=None, groupsZ=None, jitter=0.0, want_lo=False):
+    def _build(self, X, Z, groupsX=None, groupsZ=None, jitter=0.0, want_lo=False, want_h=False):
         sigma, ls = self._params()
         dt = X.dtype
         sigma, ls = sigma.to(dt), ls.to(dt)
+        if want_h:      # split-FP16 planes for the tensor-core predict: (stand-in for K, Kh, Kl, scale), leading L kept
+            if groupsX is not None:
+                return F.KernelBuildH.apply(X, Z, sigma, ls, self._group_coeff().to(dt), _r2_table(self.embedding, dt).to(X.device),
+                                            groupsX, groupsZ, 0.5 * float(self.input_dim), float(jitter))
+            return F.KernelBuildH.apply(X, Z, sigma, ls, None, None, None, None, 1.0, float(jitter))
         if groupsX is not None:
             a = self._group_coeff().to(dt)
             r2 = _r2_table(self.embedding, dt).to(X.device)
@@ -79,10 +84,10 @@ class RBF(_RBFBase):
         self.lengthscale = nn.Parameter(torch.tensor(lengthscale))
         self.input_dim = 2
 
-    def forward(self, X, Z, diag=False, return_distance=False, _jitter=0.0, _want_lo=False):
+    def forward(self, X, Z, diag=False, return_distance=False, _jitter=0.0, _want_lo=False, _want_h=False):
         if diag:
             return self._diag(X)
-        K = self._build(X, Z, jitter=_jitter, want_lo=_want_lo)
+        K = self._build(X, Z, jitter=_jitter, want_lo=_want_lo, want_h=_want_h)
         if return_distance:
             return K, F.cdist(X, Z)
         return K
@@ -112,10 +117,10 @@ class MGGP_RBF(RBF):
     def _group_coeff(self):
         return _flat(self.group_diff_param)
 
-    def forward(self, X, Z, groupsX, groupsZ, diag=False, _jitter=0.0, _want_lo=False):
+    def forward(self, X, Z, groupsX, groupsZ, diag=False, _jitter=0.0, _want_lo=False, _want_h=False):
         if diag:
             return self._diag(X)
-        return self._build(X, Z, groupsX, groupsZ, jitter=_jitter, want_lo=_want_lo)
+        return self._build(X, Z, groupsX, groupsZ, jitter=_jitter, want_lo=_want_lo, want_h=_want_h)
 
 
 class MGGP_NSF_RBF(NSF_RBF):
@@ -133,10 +138,10 @@ class MGGP_NSF_RBF(NSF_RBF):
     def _group_coeff(self):
         return _flat(self.group_diff_param) ** 2
 
-    def forward(self, X, Z, groupsX, groupsZ, diag=False, _jitter=0.0, _want_lo=False):
+    def forward(self, X, Z, groupsX, groupsZ, diag=False, _jitter=0.0, _want_lo=False, _want_h=False):
         if diag:
             return self._diag(X)
-        return self._build(X, Z, groupsX, groupsZ, jitter=_jitter, want_lo=_want_lo)
+        return self._build(X, Z, groupsX, groupsZ, jitter=_jitter, want_lo=_want_lo, want_h=_want_h)
 
 
 class batched_RBF(_RBFBase):
@@ -158,10 +163,10 @@ class batched_RBF(_RBFBase):
         n = max(s.numel(), l.numel())
         return s.expand(n), l.expand(n)
 
-    def forward(self, X, Z, diag=False, _jitter=0.0, _want_lo=False):
+    def forward(self, X, Z, diag=False, _jitter=0.0, _want_lo=False, _want_h=False):
         if diag:
             return self._diag(X)
-        return self._build(X, Z, jitter=_jitter, want_lo=_want_lo)
+        return self._build(X, Z, jitter=_jitter, want_lo=_want_lo, want_h=_want_h)
 
 
 class batched_MGGP_RBF(batched_RBF):
@@ -180,8 +185,8 @@ class batched_MGGP_RBF(batched_RBF):
         n = self._params()[0].numel()
         return torch.abs(_flat(self.group_diff_param)).expand(n)
 
-    def forward(self, X, Z, groupsX, groupsZ, diag=False, _jitter=0.0, _want_lo=False):
+    def forward(self, X, Z, groupsX, groupsZ, diag=False, _jitter=0.0, _want_lo=False, _want_h=False):
         if diag:
             return self._diag(X)
         self.input_dim = X.shape[-1]
-        return self._build(X, Z, groupsX, groupsZ, jitter=_jitter, want_lo=_want_lo)
+        return self._build(X, Z, groupsX, groupsZ, jitter=_jitter, want_lo=_want_lo, want_h=_want_h)

@@ -179,6 +179,35 @@ int gpz_umma_gemm_f32(int b_kmajor, int m, int n, int k, float alpha, const floa
 int gpz_tf32_lo_f32(const float* x, float* lo, int64_t n, void* stream);
 int gpz_transpose_lo_f32(const float* x, float* xt, float* xt_lo, int M, int L, void* stream);
 
+/* ---- the same GEMM in split-FP16 arithmetic (twice the tensor-core rate of split-TF32 at the same ~2^-22 accuracy).
+ *      Operands are pairs of fp16 planes (hi, lo) of x * s[b]: hi = rn(x s), lo = rn(x s - hi), s[b] a per-batch power of two
+ *      in device memory chosen from a bound on max |x| so that nothing overflows (gpz_split16 picks it from the exact max).
+ *      The kernel issues hi*lo + lo*hi + hi*hi into one TMEM accumulator and undoes the scales in the epilogue.
+ *      Outputs (each optional): D fp32; (Dh, Dl) fp16 planes of D * sd[b]; amax[b] = max |D| as float bits (atomicMax). */
+int gpz_split16_f32(const float* x, int rows, int cols, int batch, void* h, void* l, void* hT, void* lT, float* scale,
+                    void* amax_ws, void* stream);
+int gpz_umma_gemm16_f32(int b_kmajor, int m, int n, int k, float alpha, const void* Ah, const void* Al, int64_t lda, int64_t sA,
+                        const float* sa, const void* Bh, const void* Bl, int64_t ldb, int64_t sB, const float* sb, float* D,
+                        void* Dh, void* Dl, const float* sd, void* amax, int64_t ldd, int64_t sD, int batch, int a_tri,
+                        int d_tri, int splitk, int n_terms, void* stream);
+
+/* split-FP16 K1 forward and SVGP predictive op (the default fp32 hot path; csrc/kernel_build.cu, csrc/predict.cu):
+ *      kernel_build_fwd_h writes K as fp16 planes (out_h + out_l ~= K * out_scale[l], 4 bytes per entry) instead of fp32;
+ *      predict_fwd_h / predict_bwd_h are gpz_svgp_predict_fwd/bwd (gp.py:218-225, utilities.py:382-397 and their autograd)
+ *      on those planes: A, gC, gA travel as fp16 planes as well, C, gKzx, gLinv, gT, gq, mean, var are fp32.
+ *      ws_h: 8 L M M halfs, ws_f: 2 L N + 16 L floats, both written by fwd and read by bwd; gT and gLinv zero-initialised. */
+int gpz_kernel_build_fwd_h_f32(const float* x1, const float* x2, const float* sigma, const float* ls, const float* a,
+                               const float* r2, const int64_t* g1, const int64_t* g2, int n1, int n2, int D, int L, int ng,
+                               float p_half, float jitter, void* out_h, void* out_l, float* out_scale, void* stream);
+int gpz_svgp_predict_h_supported(int M, int N);
+int gpz_svgp_predict_fwd_h_f32(const void* Kh, const void* Kl, const float* sK, const float* Linv, const float* T, const float* q,
+                               const float* kxx, void* Ah, void* Al, float* C, float* mean, float* var, void* ws_h, float* ws_f,
+                               int M, int N, int L, void* stream);
+int gpz_svgp_predict_bwd_h_f32(const void* Kh, const void* Kl, const float* sK, const float* T, const float* q, const void* Ah,
+                               const void* Al, const float* C, const float* gm, const float* gv, void* gCh, void* gCl, void* gAh,
+                               void* gAl, float* gKzx, float* gLinv, float* gT, float* gq, void* ws_h, float* ws_f, int M, int N,
+                               int L, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -272,10 +272,12 @@ def test_hybrid_raw_loadings_elbo_matches_dropin():
     assert relerr(fused, ref) < 1e-10
 
 
-def test_tensor_core_step_matches_fp64_midsize():
-    """The fp32 tensor-core (tcgen05 split-TF32) step against the fp64 CUDA-core step of the same model at a size the CPU
-    oracle would need minutes for (N=4096, M=256, L=4, G=256): ELBO and every gradient within the fp32 tolerance."""
-    from gpzoo_b200 import synthetic
+@pytest.mark.parametrize("arith", ["fp16x3", "tf32x3"])
+def test_tensor_core_step_matches_fp64_midsize(arith, monkeypatch):
+    """The fp32 tensor-core (tcgen05 split-FP16 / split-TF32) step against the fp64 CUDA-core step of the same model at a size
+    the CPU oracle would need minutes for (N=4096, M=256, L=4, G=256): ELBO and every gradient within the fp32 tolerance."""
+    from gpzoo_b200 import functional as Fn, synthetic
+    monkeypatch.setattr(Fn, "TENSOR_CORE_ARITH", arith)
     prob = synthetic.nsf_problem(N=4096, M=256, L=4, G=256, E=1, seed=6, coord_scale=100.0, lengthscale=9.0, jitter=1e-1)
     res = {}
     for dt in (torch.float64, torch.float32):

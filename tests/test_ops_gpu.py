@@ -273,14 +273,55 @@ def test_umma_gemm_split_tf32(bk):
         assert relerr(F.umma_gemm(S.to(DEV), S.to(DEV), 1, d_tri=1, splitk=2), refS) < 2e-5
 
 
-def test_predict_tensor_core_path_vs_exact():
-    """fp32 tensor-core predict (split-TF32) against the fp64 CUDA-core path on the same inputs, fwd and bwd."""
+@pytest.mark.parametrize("bk", [0, 1])
+def test_umma_gemm_split_fp16(bk):
+    """tcgen05/TMA split-FP16 GEMM vs fp64: ragged sizes, batch, badly scaled operands, triangular skipping, split-K, fp16 plane
+    output with its own scale, max |D| tracking."""
+    from gpzoo_b200 import functional as F
+    g = torch.Generator().manual_seed(12)
+    b, m, n, k = 2, 296, 520, 200
+    A = torch.randn(b, m, k, generator=g) * 1e3                      # scales are per batch entry and exact powers of two
+    B = torch.randn((b, n, k) if bk else (b, k, n), generator=g) * torch.tensor([1e-4, 30.0])[:, None, None]
+    ref = A.double() @ (B.double().transpose(1, 2) if bk else B.double())
+    Ap, Bp = F.split16(A.to(DEV)), F.split16(B.to(DEV))
+    assert relerr(Ap[0].double() + Ap[1].double(), A.double() * Ap[2].cpu().double()[:, None, None]) < 1e-6
+    assert float(Ap[0].float().abs().max()) <= 2.0 ** 15
+    out = F.umma_gemm16(Ap, Bp, bk)
+    assert relerr(out[0], ref[0]) < 5e-6 and relerr(out[1], ref[1]) < 5e-6
+    one = F.umma_gemm16(Ap, Bp, bk, n_terms=1)                        # plain fp16 operands: only ~3e-4
+    assert 1e-5 < relerr(one[0], ref[0]) < 3e-3
+    assert relerr(F.umma_gemm16(Ap, Bp, bk, splitk=3)[1], ref[1]) < 5e-6
+    sd = torch.tensor([2.0 ** 3, 2.0 ** -9], device=DEV)
+    (Dh, Dl), amax = F.umma_gemm16(Ap, Bp, bk, out_planes=True, out_scale=sd, want_amax=True)
+    rec = (Dh.double() + Dl.double()) / sd.double()[:, None, None]
+    assert relerr(rec[0], ref[0]) < 5e-6 and relerr(rec[1], ref[1]) < 5e-6
+    assert relerr(amax, ref.abs().amax((1, 2))) < 1e-5
+    m2 = 384
+    Lo = torch.tril(torch.randn(b, m2, m2, generator=g))
+    R = torch.randn((b, 640, m2) if bk else (b, m2, 640), generator=g)
+    refL = Lo.double() @ (R.double().transpose(1, 2) if bk else R.double())
+    h, l, hT, lT, sc = F.split16(Lo.to(DEV), transpose=True)
+    Rp = F.split16(R.to(DEV))
+    assert relerr(F.umma_gemm16((h, l, sc), Rp, bk, a_tri=1), refL) < 5e-6
+    refU = Lo.double().transpose(1, 2) @ (R.double().transpose(1, 2) if bk else R.double())
+    assert relerr(F.umma_gemm16((hT, lT, sc), Rp, bk, a_tri=2), refU) < 5e-6
+    if bk:
+        S = torch.randn(b, m2, 1000, generator=g)
+        Sp = F.split16(S.to(DEV))
+        refS = torch.tril(S.double() @ S.double().transpose(1, 2))
+        assert relerr(F.umma_gemm16(Sp, Sp, 1, d_tri=1, splitk=2), refS) < 2e-5
+
+
+@pytest.mark.parametrize("arith", ["fp16x3", "tf32x3"])
+def test_predict_tensor_core_path_vs_exact(arith):
+    """fp32 tensor-core predict (split-FP16 planes or split-TF32) against the fp64 CUDA-core path on the same inputs, fwd and
+    bwd, including the kernel build that writes the operand planes."""
     from gpzoo_b200 import functional as F
     g = torch.Generator().manual_seed(13)
     L, M, N = 2, 192, 768
     Z = torch.rand(M, 2, generator=g, dtype=torch.float64) * 10
     X = torch.rand(N, 2, generator=g, dtype=torch.float64) * 10
-    sg = torch.ones(L, dtype=torch.float64)
+    sg = torch.tensor([1.0, 1.1], dtype=torch.float64)
     ls = torch.tensor([0.7, 1.0], dtype=torch.float64)
     mu = torch.randn(L, M, generator=g, dtype=torch.float64)
     Lur = 0.1 * torch.randn(L, M, M, generator=g, dtype=torch.float64)
@@ -290,16 +331,20 @@ def test_predict_tensor_core_path_vs_exact():
     for dt in (torch.float64, torch.float32):
         d = lambda t: t.to(DEV, dt)
         Zd, mud, Lud = d(Z).requires_grad_(True), d(mu).requires_grad_(True), d(Lur).requires_grad_(True)
-        lsd = d(ls).requires_grad_(True)
-        out = F.KernelBuild.apply(Zd, d(X), d(sg), lsd, None, None, None, None, 1.0, 0.0, dt == torch.float32)
-        Kzx, Kzx_lo = out if isinstance(out, tuple) else (out, None)
-        Kzz = F.KernelBuild.apply(Zd, Zd, d(sg), lsd, None, None, None, None, 1.0, 0.05)
+        lsd, sgd = d(ls).requires_grad_(True), d(sg).requires_grad_(True)
+        Kzz = F.KernelBuild.apply(Zd, Zd, sgd, lsd, None, None, None, None, 1.0, 0.05)
         Lc, Linv = F.CholeskyInverse.apply(Kzz)
         Lu = F.LowerCholesky.apply(Lud)
         T, q = F.Whiten.apply(Linv, Lu, mud)
-        Kxx = d(sg)[:, None].expand(-1, N).contiguous() ** 2
-        mean, var = F.Predict.apply(Kxx, Kzx, Linv, T, q, Kzx_lo)
+        Kxx = (sgd ** 2)[:, None].expand(-1, N).contiguous()
+        if dt == torch.float32 and arith == "fp16x3":
+            Kzx, Kh, Kl, sK = F.KernelBuildH.apply(Zd, d(X), sgd, lsd, None, None, None, None, 1.0, 0.0)
+            mean, var = F.PredictH.apply(Kxx, Kzx, Linv, T, q, Kh, Kl, sK)
+        else:
+            out = F.KernelBuild.apply(Zd, d(X), sgd, lsd, None, None, None, None, 1.0, 0.0, dt == torch.float32)
+            Kzx, Kzx_lo = out if isinstance(out, tuple) else (out, None)
+            mean, var = F.Predict.apply(Kxx, Kzx, Linv, T, q, Kzx_lo)
         ((mean * d(wm)).sum() + (var * d(wv)).sum()).backward()
-        res[dt] = dict(mean=mean, var=var, gZ=Zd.grad, gmu=mud.grad, gLu=Lud.grad, gls=lsd.grad)
+        res[dt] = dict(mean=mean, var=var, gZ=Zd.grad, gmu=mud.grad, gLu=Lud.grad, gls=lsd.grad, gsg=sgd.grad)
     for k in res[torch.float64]:
         assert relerr(res[torch.float32][k], res[torch.float64][k]) < 1e-4, k
