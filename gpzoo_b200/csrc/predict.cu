@@ -90,21 +90,31 @@ __global__ void __launch_bounds__(256) rowdot_kernel(const T* __restrict__ A, co
   if (threadIdx.x == 0) out[(int64_t)l * M + m] = acc;
 }
 
-// out[l,j] = sum_k A[l,k,j] v[l,k]      (A^T v for row-major A: one thread per column, rows streamed coalesced)
+// out[l,j] = sum_k A[l,k,j] v[l,k]      (A^T v for row-major A): a CTA owns 32 columns, its 8 thread rows stride over k
 template <typename T>
 __global__ void __launch_bounds__(256) coldot_kernel(const T* __restrict__ A, const T* __restrict__ v, T* __restrict__ out, int K, int N) {
-  const int l = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= N) return;
+  __shared__ T red[8][33];
+  const int l = blockIdx.y, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
   const T* a = A + (int64_t)l * K * N + j;
   const T* vv = v + (int64_t)l * K;
   T acc0 = T(0), acc1 = T(0);
-  int k = 0;
-  for (; k + 1 < K; k += 2) {
-    acc0 = fma(a[(int64_t)k * N], vv[k], acc0);
-    acc1 = fma(a[(int64_t)(k + 1) * N], vv[k + 1], acc1);
+  if (j < N) {
+    int k = ty;
+    for (; k + 8 < K; k += 16) {
+      acc0 = fma(a[(int64_t)k * N], vv[k], acc0);
+      acc1 = fma(a[(int64_t)(k + 8) * N], vv[k + 8], acc1);
+    }
+    if (k < K) acc0 = fma(a[(int64_t)k * N], vv[k], acc0);
   }
-  if (k < K) acc0 = fma(a[(int64_t)k * N], vv[k], acc0);
-  out[(int64_t)l * N + j] = acc0 + acc1;
+  red[ty][tx] = acc0 + acc1;
+  __syncthreads();
+  if (ty == 0 && j < N) {
+    T sacc = T(0);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) sacc += red[r][tx];
+    out[(int64_t)l * N + j] = sacc;
+  }
 }
 
 template <typename T>
@@ -263,28 +273,22 @@ static int predict_bwd_tc(const float* Kzx, const float* Kzx_lo, const float* Li
 enum { ST_S_LINV = 0, ST_S_T, ST_S_A, ST_S_GC, ST_S_GA, ST_AMAX_LINV, ST_AMAX_T, ST_AMAX_A, ST_AMAX_C, ST_TINF, ST_AMAX_GV,
        ST_AMAX_GM, ST_AMAX_Q, ST_AMAX_KXX, ST_AMAX_GA, ST_SPARE, ST_SLOTS };
 
-__device__ __forceinline__ float block_amax(const float* __restrict__ x, int n, float* red) {
+// max |x[l,:]| of up to three L x n arrays in one launch: grid (chunks, L, arrays), atomicMax on the float bits
+struct Amax3 { const float* x[3]; int n[3]; unsigned int* out[3]; };
+__global__ void __launch_bounds__(256) amax3_kernel(const Amax3 a) {
+  const int l = blockIdx.y, w = blockIdx.z;
+  const float* x = a.x[w] + (int64_t)l * a.n[w];
   float m = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(x[i]));
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.n[w]; i += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
 #pragma unroll
   for (int sh = 16; sh > 0; sh >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, sh));
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-  __syncthreads();
-  m = 0.f;
-  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
-  return m;
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(a.out[w] + l, __float_as_uint(m));
 }
 
-// one CTA per factor: sA[l] from max Kxx[l,:]
-__global__ void __launch_bounds__(256) predict_h_fwd_scales_kernel(const float* __restrict__ kxx, float* __restrict__ stats, int N, int L) {
-  __shared__ float red[8];
-  const int l = blockIdx.x;
-  const float mk = block_amax(kxx + (int64_t)l * N, N, red);
-  if (threadIdx.x == 0) {
-    stats[ST_AMAX_KXX * L + l] = mk;
-    stats[ST_S_A * L + l] = gpz_pow2_scale(2.f * sqrtf(mk));
-  }
+// sA[l] from max Kxx[l,:]
+__global__ void predict_h_fwd_scales_kernel(float* __restrict__ stats, int L) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l < L) stats[ST_S_A * L + l] = gpz_pow2_scale(2.f * sqrtf(stats[ST_AMAX_KXX * L + l]));
 }
 
 // max_i sum_j |T[l,i,j]|: one warp per row
@@ -298,23 +302,16 @@ __global__ void __launch_bounds__(256) rowabs_max_kernel(const float* __restrict
   if (lane == 0 && s > 0.f) atomicMax(out + l, __float_as_uint(s));
 }
 
-// one CTA per factor: max|gv|, max|gm|, max|q| and the scales of gC and gA
-__global__ void __launch_bounds__(256) predict_h_bwd_scales_kernel(const float* __restrict__ gv, const float* __restrict__ gm,
-                                                                    const float* __restrict__ q, float* __restrict__ stats, int M,
-                                                                    int N, int L) {
-  __shared__ float red[8];
-  const int l = blockIdx.x;
-  const float a_gv = block_amax(gv + (int64_t)l * N, N, red);
-  const float a_gm = block_amax(gm + (int64_t)l * N, N, red);
-  const float a_q = block_amax(q + (int64_t)l * M, M, red);
-  if (threadIdx.x == 0) {
-    const float a_A = stats[ST_AMAX_A * L + l], a_C = stats[ST_AMAX_C * L + l], tinf = stats[ST_TINF * L + l];
-    const float b_gC = 2.f * a_C * a_gv;
-    const float b_gA = tinf * b_gC + 2.f * a_A * a_gv + a_q * a_gm;
-    stats[ST_AMAX_GV * L + l] = a_gv; stats[ST_AMAX_GM * L + l] = a_gm; stats[ST_AMAX_Q * L + l] = a_q;
-    stats[ST_S_GC * L + l] = gpz_pow2_scale(b_gC);
-    stats[ST_S_GA * L + l] = gpz_pow2_scale(b_gA);
-  }
+// the scales of gC and gA from the tracked maxima
+__global__ void predict_h_bwd_scales_kernel(float* __restrict__ stats, int L) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= L) return;
+  const float a_A = stats[ST_AMAX_A * L + l], a_C = stats[ST_AMAX_C * L + l], tinf = stats[ST_TINF * L + l];
+  const float a_gv = stats[ST_AMAX_GV * L + l], a_gm = stats[ST_AMAX_GM * L + l], a_q = stats[ST_AMAX_Q * L + l];
+  const float b_gC = 2.f * a_C * a_gv;
+  const float b_gA = tinf * b_gC + 2.f * a_A * a_gv + a_q * a_gm;
+  stats[ST_S_GC * L + l] = gpz_pow2_scale(b_gC);
+  stats[ST_S_GA * L + l] = gpz_pow2_scale(b_gA);
 }
 
 // gC = 2 C gv written as fp16 planes of gC * s[l]
@@ -378,7 +375,9 @@ static int predict_fwd_h(const __half* Kh, const __half* Kl, const float* sK, co
   if (rc) return rc;
   rc = split16_planes(Tm, M, M, L, ustats + ST_AMAX_T * L, stats + ST_S_T * L, T_h, T_l, TT_h, TT_l, (void*)st);
   if (rc) return rc;
-  predict_h_fwd_scales_kernel<<<L, 256, 0, st>>>(kxx, stats, N, L);
+  rc = split16_amax(kxx, N, L, ustats + ST_AMAX_KXX * L, (void*)st);
+  if (rc) return rc;
+  predict_h_fwd_scales_kernel<<<(unsigned)cdiv(L, 64), 64, 0, st>>>(stats, L);
   GPZ_CHECK_LAUNCH();
   // A = Linv Kzx  (lower-triangular product == TRSM Lc A = Kzx); epilogue: sum_m A^2, mean = sum_m q_m A, max |A|
   UmmaEpilogue e1{1, nullptr, q, nullptr, nullptr, sA2, mean, nullptr};
@@ -407,9 +406,15 @@ static int predict_bwd_h(const __half* Kh, const __half* Kl, const float* sK, co
   float* stats = ws_f + 2 * LN;
   unsigned int* ustats = reinterpret_cast<unsigned int*>(stats);
   const float* sA = stats + ST_S_A * L; const float* sgC = stats + ST_S_GC * L; const float* sgA = stats + ST_S_GA * L;
+  // (the backward may run more than once on the same forward state: reset the maxima it accumulates)
+  GPZ_CUDA(cudaMemsetAsync(ustats + ST_TINF * L, 0, sizeof(unsigned int) * 4 * (size_t)L, st));      // TINF, GV, GM, Q are adjacent
+  GPZ_CUDA(cudaMemsetAsync(ustats + ST_AMAX_GA * L, 0, sizeof(unsigned int) * (size_t)L, st));
   rowabs_max_kernel<<<dim3((unsigned)cdiv(M, 8), L), 256, 0, st>>>(Tm, ustats + ST_TINF * L, M);
   GPZ_CHECK_LAUNCH();
-  predict_h_bwd_scales_kernel<<<L, 256, 0, st>>>(gv, gm, q, stats, M, N, L);
+  Amax3 am{{gv, gm, q}, {N, N, M}, {ustats + ST_AMAX_GV * L, ustats + ST_AMAX_GM * L, ustats + ST_AMAX_Q * L}};
+  amax3_kernel<<<dim3(16, L, 3), 256, 0, st>>>(am);
+  GPZ_CHECK_LAUNCH();
+  predict_h_bwd_scales_kernel<<<(unsigned)cdiv(L, 64), 64, 0, st>>>(stats, L);
   GPZ_CHECK_LAUNCH();
   predict_h_scale_kernel<<<dim3((unsigned)cdiv(N, 2048), (unsigned)cdiv(M, 16), L), 256, 0, st>>>(C, gv, sgC, gCh, gCl, M, N);
   GPZ_CHECK_LAUNCH();
@@ -505,7 +510,7 @@ GPZ_PREDICT_IMPL(f64, double)
     if (rows <= 0 || cols <= 0 || L <= 0) return GPZ_OK;                                                              \
     cudaStream_t st = (cudaStream_t)stream;                                                                           \
     if (!trans) rowdot_kernel<T><<<dim3(rows, L), 256, 0, st>>>(A, v, out, rows, cols);                               \
-    else coldot_kernel<T><<<dim3((unsigned)cdiv(cols, 256), L), 256, 0, st>>>(A, v, out, rows, cols);                 \
+    else coldot_kernel<T><<<dim3((unsigned)cdiv(cols, 32), L), 256, 0, st>>>(A, v, out, rows, cols);                   \
     GPZ_CHECK_LAUNCH();                                                                                               \
     return GPZ_OK;                                                                                                    \
   }

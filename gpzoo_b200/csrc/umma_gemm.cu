@@ -158,6 +158,131 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// tcgen05.ld without the wait (the caller overlaps global prefetches with the TMEM read latency)
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, "
+      "%25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Specialised epilogue of one warp for a tile that lies completely inside the matrix (the common case of the N-proportional
+// split-FP16 GEMMs): 4 chunks of 32 columns, everything addressed incrementally, no runtime mode tests in the inner loop.
+//   MODE 0: plain   1: + sum_i D^2 and sum_i rowv_i D per column   2: + sum_i D^2   3: D = acc - 2 Aux colv1 + rowv colv2, rowacc
+//   OUT_D: fp32 store;  OUT_H: (hi, lo) fp16 planes of D * sd.  MODE 3 reads Aux as fp16 planes (prefetched into L2 by the caller).
+template <int MODE, bool OUT_D, bool OUT_H>
+__device__ __forceinline__ void epilogue_tile_fast(const Params& p, int b, int i0, int j0, int q, int lane, int c_begin,
+                                                   uint32_t tmem_acc, float* epi, float alpha_b, float sd_b, float inv_saux,
+                                                   float& amx) {
+  const int lr = lane >> 3, cq = (lane & 7) * 4;
+  const int row0 = i0 + q * 32;
+  const int64_t ld4 = 4 * p.ldd;
+  int64_t o_chunk = (int64_t)b * p.sD + (int64_t)(row0 + lr) * p.ldd + j0 + c_begin * 32 + cq;   // element of (row lr, this lane's 4 columns)
+  const int64_t colbase = (int64_t)b * p.n + j0 + c_begin * 32 + cq;
+  float qreg[8], racc[8];
+  if (MODE == 1 || MODE == 3) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { qreg[u] = __ldg(p.rowv + (int64_t)b * p.m + row0 + u * 4 + lr); racc[u] = 0.f; }
+  }
+  uint2 axh[8], axl[8];
+  const float* srd = epi + lr * 32;                  // staging read: row (4 itr + lr), 16-byte slot (lane & 7) ^ (row & 7)
+  float* swr = epi + lane * 32;                      // staging write: row lane
+#pragma unroll
+  for (int cc = 0; cc < BN / 64; ++cc) {
+    uint32_t r[32];
+    tmem_ld32_nowait(tmem_acc + (uint32_t)((c_begin + cc) * 32), r);
+    float4 cv1, cv2;
+    if (MODE == 3) {
+      cv1 = __ldg(reinterpret_cast<const float4*>(p.colv1 + colbase + cc * 32));
+      cv2 = __ldg(reinterpret_cast<const float4*>(p.colv2 + colbase + cc * 32));
+      // (the whole Aux region of this warp was prefetched into L2 when the tile was handed out)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        axh[u] = __ldcs(reinterpret_cast<const uint2*>(p.AuxH + o_chunk + u * ld4));
+        axl[u] = __ldcs(reinterpret_cast<const uint2*>(p.AuxL + o_chunk + u * ld4));
+      }
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int u = 0; u < 32; u += 4)
+      *reinterpret_cast<float4*>(swr + (((u >> 2) ^ (lane & 7)) << 2)) =
+          make_float4(__uint_as_float(r[u]), __uint_as_float(r[u + 1]), __uint_as_float(r[u + 2]), __uint_as_float(r[u + 3]));
+    __syncwarp();
+    float4 cs1 = make_float4(0.f, 0.f, 0.f, 0.f), cs2 = cs1;
+#pragma unroll
+    for (int itr = 0; itr < 8; ++itr) {
+      // row = 4 itr + lr, so row & 7 = (4 (itr & 1) + lr) & 7
+      float4 v = *reinterpret_cast<const float4*>(srd + itr * 128 + ((((lane & 7) ^ ((4 * (itr & 1) + lr) & 7))) << 2));
+      v.x *= alpha_b; v.y *= alpha_b; v.z *= alpha_b; v.w *= alpha_b;
+      const int64_t o = o_chunk + itr * ld4;
+      if (MODE == 3) {
+        const uint2 hh = axh[itr], ll = axl[itr];
+        float4 ax;
+        ax.x = unpack_sum(hh.x, ll.x, 0) * inv_saux; ax.y = unpack_sum(hh.x, ll.x, 1) * inv_saux;
+        ax.z = unpack_sum(hh.y, ll.y, 0) * inv_saux; ax.w = unpack_sum(hh.y, ll.y, 1) * inv_saux;
+        const float qv = qreg[itr];
+        v.x += fmaf(qv, cv2.x, -2.f * ax.x * cv1.x);
+        v.y += fmaf(qv, cv2.y, -2.f * ax.y * cv1.y);
+        v.z += fmaf(qv, cv2.z, -2.f * ax.z * cv1.z);
+        v.w += fmaf(qv, cv2.w, -2.f * ax.w * cv1.w);
+        racc[itr] += ax.x * cv2.x + ax.y * cv2.y + ax.z * cv2.z + ax.w * cv2.w;     // reduced over the lanes once per tile
+      } else if (MODE != 0) {
+        cs1.x = fmaf(v.x, v.x, cs1.x); cs1.y = fmaf(v.y, v.y, cs1.y); cs1.z = fmaf(v.z, v.z, cs1.z); cs1.w = fmaf(v.w, v.w, cs1.w);
+        if (MODE == 1) {
+          const float qv = qreg[itr];
+          cs2.x = fmaf(qv, v.x, cs2.x); cs2.y = fmaf(qv, v.y, cs2.y); cs2.z = fmaf(qv, v.z, cs2.z); cs2.w = fmaf(qv, v.w, cs2.w);
+        }
+      }
+      if (OUT_D) *reinterpret_cast<float4*>(p.D + o) = v;
+      if (OUT_H) {
+        uint2 ph, pl;
+        split_half2(v.x * sd_b, v.y * sd_b, ph.x, pl.x);
+        split_half2(v.z * sd_b, v.w * sd_b, ph.y, pl.y);
+        *reinterpret_cast<uint2*>(p.Dh + o) = ph;
+        *reinterpret_cast<uint2*>(p.Dl + o) = pl;
+      }
+      amx = fmaxf(amx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    if (MODE == 1 || MODE == 2) {
+#pragma unroll
+      for (int sh = 8; sh <= 16; sh <<= 1) {
+        cs1.x += __shfl_xor_sync(0xffffffffu, cs1.x, sh); cs1.y += __shfl_xor_sync(0xffffffffu, cs1.y, sh);
+        cs1.z += __shfl_xor_sync(0xffffffffu, cs1.z, sh); cs1.w += __shfl_xor_sync(0xffffffffu, cs1.w, sh);
+        if (MODE == 1) {
+          cs2.x += __shfl_xor_sync(0xffffffffu, cs2.x, sh); cs2.y += __shfl_xor_sync(0xffffffffu, cs2.y, sh);
+          cs2.z += __shfl_xor_sync(0xffffffffu, cs2.z, sh); cs2.w += __shfl_xor_sync(0xffffffffu, cs2.w, sh);
+        }
+      }
+      if (lane < 8) {
+        float* c1 = p.col1 + colbase + cc * 32;
+        atomicAdd(c1, cs1.x); atomicAdd(c1 + 1, cs1.y); atomicAdd(c1 + 2, cs1.z); atomicAdd(c1 + 3, cs1.w);
+        if (MODE == 1) {
+          float* c2 = p.col2 + colbase + cc * 32;
+          atomicAdd(c2, cs2.x); atomicAdd(c2 + 1, cs2.y); atomicAdd(c2 + 2, cs2.z); atomicAdd(c2 + 3, cs2.w);
+        }
+      }
+    }
+    __syncwarp();
+    o_chunk += 32;
+  }
+  if (MODE == 3) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      float rp = racc[u];
+      rp += __shfl_xor_sync(0xffffffffu, rp, 1);
+      rp += __shfl_xor_sync(0xffffffffu, rp, 2);
+      rp += __shfl_xor_sync(0xffffffffu, rp, 4);
+      if ((lane & 7) == 0) atomicAdd(p.rowacc + (int64_t)b * p.m + row0 + u * 4 + lr, rp);
+    }
+  }
+}
+
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
 // version=1 [46,48) | layout type [61,64)  (1 = SWIZZLE_128B_BASE32B, 2 = SWIZZLE_128B, 4 = SWIZZLE_64B)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
@@ -303,7 +428,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       // a_major [15]=0 (K), b_major [16], N>>3 [17,23), M>>4 [24,29)
       // operand format 2 = TF32, 0 = F16
       const uint32_t fmt = F16 ? 0u : 2u;
-      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((B_KMAJOR ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) |
+      const uint32_t idesc_full = (1u << 4) | (fmt << 7) | (fmt << 10) | ((B_KMAJOR ? 0u : 1u) << 16) | ((uint32_t)(BN >> 3) << 17) |
                              ((uint32_t)(BM >> 4) << 24);
       uint32_t it = 0, acc_iter = 0;
       for (uint32_t iter = 0;; ++iter) {
@@ -318,6 +443,10 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         mbar_wait(accum_empty + as, ((acc_iter >> 1) & 1u) ^ 1u);       // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_d = tmem_base + as * (uint32_t)BN;
+        // lower-triangular output, tile on the diagonal with its right half above it: a 128-column MMA is enough
+        // (the epilogue masks columns > row, so the stale right half of the accumulator is never stored)
+        const uint32_t idesc = (p.d_tri == 1 && ti.i0 + BM <= ti.j0 + BN / 2)
+                                   ? ((idesc_full & ~(0x3Fu << 17)) | ((uint32_t)(BN >> 4) << 17)) : idesc_full;
         for (int kb = 0; kb < ti.nkb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1u;
@@ -391,6 +520,15 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const bool has_acc = ti.nkb > 0;
       if (!has_acc && !ti.zero) continue;
       const uint32_t as = acc_iter & 1u;
+      if (F16 && p.epi_mode == 3 && p.AuxH && has_acc && ti.i0 + BM <= p.m && ti.j0 + BN <= p.n) {
+        // while the MMAs of this tile run: pull this warp's part of the Aux planes (32 rows x 128 columns x 2 planes) into L2
+        const __half* ah = p.AuxH + (int64_t)ti.b * p.sD + (int64_t)(ti.i0 + q * 32 + lane) * p.ldd + ti.j0 + c_begin * 32;
+        const __half* al = p.AuxL + (int64_t)ti.b * p.sD + (int64_t)(ti.i0 + q * 32 + lane) * p.ldd + ti.j0 + c_begin * 32;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ah));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ah + 64));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(al));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(al + 64));
+      }
       if (has_acc) {
         mbar_wait(accum_full + as, (acc_iter >> 1) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -402,6 +540,29 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const float sd_b = (p.Dh && p.sd) ? p.sd[ti.b] : 1.0f;
       const float inv_saux = (p.AuxH && p.saux) ? 1.0f / p.saux[ti.b] : 1.0f;
       float amx = 0.f;
+      if (F16 && has_acc && vec_ok && p.splitk == 1 && p.d_tri == 0 && !p.Cin && !p.Dlo && ti.i0 + BM <= p.m && ti.j0 + BN <= p.n) {
+        // tile completely inside the matrix: specialised, branch-free inner loops
+        const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)BN;
+        bool done = true;
+        if (p.epi_mode == 1 && p.Dh && !p.D) epilogue_tile_fast<1, false, true>(p, ti.b, ti.i0, ti.j0, q, lane, c_begin, tacc, epi, alpha_b, sd_b, inv_saux, amx);
+        else if (p.epi_mode == 2 && p.D && !p.Dh) epilogue_tile_fast<2, true, false>(p, ti.b, ti.i0, ti.j0, q, lane, c_begin, tacc, epi, alpha_b, sd_b, inv_saux, amx);
+        else if (p.epi_mode == 3 && p.AuxH && p.Dh && !p.D) epilogue_tile_fast<3, false, true>(p, ti.b, ti.i0, ti.j0, q, lane, c_begin, tacc, epi, alpha_b, sd_b, inv_saux, amx);
+        else if (p.epi_mode == 0 && p.D && !p.Dh) epilogue_tile_fast<0, true, false>(p, ti.b, ti.i0, ti.j0, q, lane, c_begin, tacc, epi, alpha_b, sd_b, inv_saux, amx);
+        else if (p.epi_mode == 0 && p.Dh && !p.D) epilogue_tile_fast<0, false, true>(p, ti.b, ti.i0, ti.j0, q, lane, c_begin, tacc, epi, alpha_b, sd_b, inv_saux, amx);
+        else done = false;
+        if (done) {
+          if (p.amax) {
+#pragma unroll
+            for (int sh = 16; sh > 0; sh >>= 1) amx = fmaxf(amx, __shfl_xor_sync(0xffffffffu, amx, sh));
+            if (lane == 0 && amx > 0.f) atomicMax(p.amax + ti.b, __float_as_uint(amx));
+          }
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(accum_empty + as);
+          ++acc_iter;
+          continue;
+        }
+      }
       const int gi = ti.i0 + q * 32 + lane;
       const int wrow0 = ti.i0 + q * 32;
       float racc[8];                          // mode 3: per-row partial sums of this lane's 8 rows (coalesced path)
