@@ -479,8 +479,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             if (F16) {
               if (p.n_terms == 3) {
                 umma_f16(tmem_d, a_raw, b_lo, idesc, acc0);
-                umma_f16(tmem_d, a_lo, b_raw, idesc, 1u);
                 umma_f16(tmem_d, a_raw, b_raw, idesc, 1u);
+                umma_f16(tmem_d, a_lo, b_raw, idesc, 1u);
               } else {
                 umma_f16(tmem_d, a_raw, b_raw, idesc, acc0);
               }
