@@ -63,8 +63,33 @@ def ptr(t):
     return c_p(t.data_ptr())
 
 
+_launch_stream = None       # see launch_on()
+
+
 def stream():
+    if _launch_stream is not None:
+        # side-stream launch: everything already queued on torch's current stream (the tensors' producers, and earlier users of
+        # the recycled memory the outputs live in) is ordered before the kernel
+        _launch_stream.wait_stream(torch.cuda.current_stream())
+        return c_p(_launch_stream.cuda_stream)
     return c_p(torch.cuda.current_stream().cuda_stream)
+
+
+class launch_on:
+    """`with launch_on(side):` — C-ABI calls inside the block are launched on `side` while torch's current stream (and with it
+    the caching allocator's stream of every tensor allocated inside) stays the same.  The caller joins with
+    `torch.cuda.current_stream().wait_stream(side)` before anything consumes the outputs."""
+
+    def __init__(self, st):
+        self.st = st
+
+    def __enter__(self):
+        global _launch_stream
+        self.prev, _launch_stream = _launch_stream, self.st
+
+    def __exit__(self, *exc):
+        global _launch_stream
+        _launch_stream = self.prev
 
 
 profile = None             # set to {} to record CUDA events around every C-ABI call (bench.py roofline numbers)
@@ -84,9 +109,11 @@ def call(name, dtype, *args):
         fn.restype = c_i
     if profile is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        rc = fn(*args, stream())
-        ev1.record()
+        st = stream()
+        tst = _launch_stream if _launch_stream is not None else torch.cuda.current_stream()
+        ev0.record(tst)
+        rc = fn(*args, st)
+        ev1.record(tst)
         profile.setdefault(name, []).append((ev0, ev1))
     else:
         rc = fn(*args, stream())

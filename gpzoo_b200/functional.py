@@ -25,6 +25,19 @@ USE_TENSOR_CORES = True      # fp32: route large contractions through the tcgen0
 # rate), "tf32x3" = split-TF32 (fp32 + lo planes, half the rate; also used when a shape is not 8-aligned)
 TENSOR_CORE_ARITH = os.environ.get("GPZ_TC_ARITH", "fp16x3")
 _pending_info = []
+# build Kzx on a side stream, concurrently with the Cholesky chain of Kzz (gp.py moments); GPZ_OVERLAP=0 turns it off
+OVERLAP_KERNEL_BUILD = os.environ.get("GPZ_OVERLAP", "1") != "0"
+_side_streams = {}
+launch_on = _cabi.launch_on
+
+
+def side_stream(device):
+    """The per-device side stream used for work that is independent of the Kzz chain."""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    st = _side_streams.get(key)
+    if st is None:
+        st = _side_streams[key] = torch.cuda.Stream(device=key)
+    return st
 
 
 def set_sync_checks(flag: bool):

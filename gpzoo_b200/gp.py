@@ -58,19 +58,24 @@ class _SparseGPBase(nn.Module):
         self.constraint = constraints.lower_cholesky
 
     # -- kernel calls -------------------------------------------------------------------------------
-    def _kernel_matrices(self, X, groupsX=None, want_lo=False, want_h=False):
+    def _kernel_matrices(self, X, groupsX=None, want_lo=False, want_h=False, skip_kzz=False, skip_kzx=False):
         """Kxx (diag), Kzx, Kzz (+jitter).  want_lo: Kzx comes back as (Kzx, Kzx_lo) for the split-TF32 tensor-core path;
-        want_h: as (stand-in, Kh, Kl, scale) fp16 planes for the split-FP16 path."""
+        want_h: as (stand-in, Kh, Kl, scale) fp16 planes for the split-FP16 path.  skip_*: leave that matrix out (None)."""
         kw = {"_want_h": True} if want_h else ({"_want_lo": True} if want_lo else {})
+        Kxx = Kzx = Kzz = None
         if groupsX is not None:
             gZ = self.groupsZ
-            Kxx = self.kernel(X, X, groupsX, groupsX, diag=True)
-            Kzx = self.kernel(self.Z, X, gZ, groupsX, **kw)
-            Kzz = self.kernel(self.Z, self.Z, gZ, gZ, _jitter=self.jitter)      # add_jitter fused (gp.py:209/360)
+            if not skip_kzx:
+                Kxx = self.kernel(X, X, groupsX, groupsX, diag=True)
+                Kzx = self.kernel(self.Z, X, gZ, groupsX, **kw)
+            if not skip_kzz:
+                Kzz = self.kernel(self.Z, self.Z, gZ, gZ, _jitter=self.jitter)      # add_jitter fused (gp.py:209/360)
         else:
-            Kxx = self.kernel(X, X, diag=True)
-            Kzx = self.kernel(self.Z, X, **kw)
-            Kzz = self.kernel(self.Z, self.Z, _jitter=self.jitter)
+            if not skip_kzx:
+                Kxx = self.kernel(X, X, diag=True)
+                Kzx = self.kernel(self.Z, X, **kw)
+            if not skip_kzz:
+                Kzz = self.kernel(self.Z, self.Z, _jitter=self.jitter)
         return Kxx, Kzx, Kzz
 
     def _whitened(self, Kzz):
@@ -95,8 +100,19 @@ class _SparseGPBase(nn.Module):
         F.clear_step_cache()
         want_h = F.predict_h_ok(X.dtype, self.Z.shape[0], X.shape[0])
         want_lo = (not want_h) and F.tensor_core_predict_ok(X.dtype, self.Z.shape[0], X.shape[0])
-        Kxx, Kzx, Kzz = self._kernel_matrices(X, groupsX, want_lo, want_h)
-        Lc, Linv, Lu, T, q, L = self._whitened(Kzz)
+        if want_h and F.OVERLAP_KERNEL_BUILD:
+            # The Kzz chain (Cholesky + inverse: one 8-CTA cluster per factor, latency-bound, about half of the SMs) and the
+            # HBM-bound Kzx build are independent: the Kzx kernel is launched on a side stream (torch's current stream, and so
+            # the allocator's view of every tensor, stays the same) and joins before the predictive GEMMs.
+            side = F.side_stream(X.device)
+            with F.launch_on(side):
+                Kxx, Kzx, _ = self._kernel_matrices(X, groupsX, want_lo, want_h, skip_kzz=True)
+            _, _, Kzz = self._kernel_matrices(X, groupsX, skip_kzx=True)
+            Lc, Linv, Lu, T, q, L = self._whitened(Kzz)
+            torch.cuda.current_stream().wait_stream(side)
+        else:
+            Kxx, Kzx, Kzz = self._kernel_matrices(X, groupsX, want_lo, want_h)
+            Lc, Linv, Lu, T, q, L = self._whitened(Kzz)
         Kxx = Kxx if Kxx.dim() == 2 else Kxx.unsqueeze(0)
         if Kxx.shape[0] != L:
             Kxx = Kxx.expand(L, -1)
