@@ -45,8 +45,20 @@ def set_sync_checks(flag: bool):
     SYNC_CHECKS = bool(flag)
 
 
+_pending_amax = []        # (stats tensor, names) of split-FP16 predict calls whose tracked maxima have not been examined yet
+
+
 def check_cholesky_info():
-    global _pending_info
+    """Deferred error checks of the step (one device sync): LAPACK-style `info` of every Cholesky and the overflow guard of
+    the split-FP16 planes (a scale bound that did not hold makes an entry inf, which shows up as a non-finite tracked max)."""
+    global _pending_info, _pending_amax
+    pend16, _pending_amax = _pending_amax, []
+    for amax, scale, names in pend16:
+        bad = ~(amax * scale <= 65504.0)               # also true for NaN / inf
+        if bool(bad.any()):
+            which = sorted({names[int(i)] for i in bad.nonzero()[:, 0]})
+            raise _cabi.GpzError("split-FP16 predict: " + ", ".join(which) + " left the fp16 range its scale bound allows (or the "
+                                 "inputs contain inf/NaN); GPZ_TC_ARITH=tf32x3 selects the split-TF32 kernels")
     pend, _pending_info = _pending_info, []
     for info in pend:
         bad = info.nonzero()
@@ -398,6 +410,13 @@ class PredictH(Function):
         call("svgp_predict_fwd_h", dt, ptr(Kh), ptr(Kl), ptr(sK), ptr(Linv), ptr(T), ptr(q), ptr(Kxx), ptr(Ah), ptr(Al), ptr(C),
              ptr(mean), ptr(var), ptr(ws_h), ptr(ws_f), c_i(M), c_i(N), c_i(L))
         ctx.save_for_backward(Kh, Kl, sK, Linv, T, q, Ah, Al, C, ws_h, ws_f)
+        # tracked max |A|, max |C| (slots 7, 8 of the stats block, csrc/predict.cu): examined lazily with the Cholesky info
+        st = ws_f[2 * L * N:].view(-1, L)
+        _pending_amax.append((st[7:9], torch.stack((st[2], torch.ones_like(st[2]))), ("A", "C")))
+        if len(_pending_amax) > 64:
+            del _pending_amax[:-64]
+        if SYNC_CHECKS:
+            check_cholesky_info()
         return mean, var
 
     @staticmethod
@@ -417,6 +436,8 @@ class PredictH(Function):
         call("svgp_predict_bwd_h", dt, ptr(Kh), ptr(Kl), ptr(sK), ptr(T), ptr(q), ptr(Ah), ptr(Al), ptr(C), ptr(gm), ptr(gv),
              ptr(gCh), ptr(gCl), ptr(gAh), ptr(gAl), ptr(gKzx), ptr(gLinv), ptr(gT), ptr(gq), ptr(ws_h), ptr(ws_f),
              c_i(M), c_i(N), c_i(L))
+        st = ws_f[2 * L * N:].view(-1, L)
+        _pending_amax.append((st[14:15], st[4:5], ("dL/dA",)))          # tracked max |gA| against its scale
         return gv, gKzx, gLinv, gT, gq, None, None, None
 
 

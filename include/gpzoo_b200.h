@@ -208,6 +208,16 @@ int gpz_svgp_predict_bwd_h_f32(const void* Kh, const void* Kl, const float* sK, 
                                void* gAl, float* gKzx, float* gLinv, float* gT, float* gq, void* ws_h, float* ws_f, int M, int N,
                                int L, void* stream);
 
+/* ---- training-step update: multi-tensor Adam in one launch (torch.optim.Adam without weight decay /
+ *      amsgrad; utilities.py:621 optimizer.step()) with the reference's post-step clamp W.clamp_(min=0) (utilities.py:623) fused in
+ *      for the tensors flagged in clamp0.  The pointer tables are HOST arrays of device pointers; step counts from 1. */
+int gpz_adam_step_f32(int n_tensors, void* const* params, void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+                      const int64_t* numel, const int* clamp0, double lr, double beta1, double beta2, double eps, int step,
+                      void* stream);
+int gpz_adam_step_f64(int n_tensors, void* const* params, void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+                      const int64_t* numel, const int* clamp0, double lr, double beta1, double beta2, double eps, int step,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -249,7 +249,7 @@ def test_training_loops_run_and_improve():
     assert len(losses) == 15 and losses[-1] < losses[0]
     losses = gz.utilities.train_batched(model, opt, prob["X"], prob["y"], steps=10, E=1, batch_size=512)
     assert len(losses) == 10 and all(l == l for l in losses)
-    assert float(model.W.min()) >= 0.0
+    assert float(model.W.detach().min()) >= 0.0
 
 
 def test_hybrid_raw_loadings_elbo_matches_dropin():

@@ -348,3 +348,48 @@ def test_predict_tensor_core_path_vs_exact(arith):
         res[dt] = dict(mean=mean, var=var, gZ=Zd.grad, gmu=mud.grad, gLu=Lud.grad, gls=lsd.grad, gsg=sgd.grad)
     for k in res[torch.float64]:
         assert relerr(res[torch.float32][k], res[torch.float64][k]) < 1e-4, k
+
+
+def test_split_fp16_overflow_guard():
+    """The fp16 planes rely on |A[:,n]|^2 <= Kxx[n]; if a caller breaks that contract (here: a Kxx that is far too small for the
+    kernel matrix it is paired with) the planes overflow and the deferred check must say so instead of returning garbage."""
+    from gpzoo_b200 import _cabi, functional as F
+    g = torch.Generator().manual_seed(14)
+    L, M, N = 1, 128, 512
+    Z = (torch.rand(M, 2, generator=g) * 10).to(DEV)
+    X = (torch.rand(N, 2, generator=g) * 10).to(DEV)
+    sg, ls = torch.ones(L, device=DEV), torch.ones(L, device=DEV)
+    Kzz = F.KernelBuild.apply(Z, Z, sg, ls, None, None, None, None, 1.0, 0.05)
+    Lc, Linv = F.CholeskyInverse.apply(Kzz)
+    T, q = F.Whiten.apply(Linv, torch.eye(M, device=DEV).expand(L, -1, -1).contiguous(), torch.zeros(L, M, device=DEV))
+    Kzx, Kh, Kl, sK = F.KernelBuildH.apply(Z, X, sg, ls, None, None, None, None, 1.0, 0.0)
+    ok = (sg ** 2)[:, None].expand(-1, N).contiguous()
+    F.PredictH.apply(ok, Kzx, Linv, T, q, Kh, Kl, sK)                      # the contract holds: no complaint
+    with pytest.raises(_cabi.GpzError, match="fp16 range"):
+        F.PredictH.apply(ok * 1e-12, Kzx, Linv, T, q, Kh, Kl, sK)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float64])
+def test_fused_adam_matches_torch(dt):
+    """gpzoo_b200.optim.Adam (one multi-tensor launch, clamp fused) against torch.optim.Adam + clamp_ (utilities.py:621-623)."""
+    import gpzoo_b200 as gz
+    g = torch.Generator().manual_seed(21)
+    shapes = [(7,), (33, 5), (2, 129, 65), (1,), (3000,)]
+    ref = [torch.nn.Parameter(torch.randn(s, generator=g, dtype=dt).to(DEV)) for s in shapes]
+    ours = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+    o_ref = torch.optim.Adam(ref, lr=3e-2, betas=(0.9, 0.99), eps=1e-8)
+    o_ours = gz.optim.Adam(ours, lr=3e-2, betas=(0.9, 0.99), eps=1e-8, clamp_nonneg=[ours[1]])
+    for it in range(6):
+        for a, b in zip(ref, ours):
+            gr = torch.randn(a.shape, generator=g, dtype=dt).to(DEV)
+            a.grad, b.grad = gr.clone(), gr.clone()
+        if it == 3:
+            ref[0].grad = ours[0].grad = None                     # a parameter without gradient is skipped (its step count too)
+        o_ref.step()
+        with torch.no_grad():
+            ref[1].clamp_(min=0)
+        o_ours.step()
+    tol = 1e-6 if dt == torch.float32 else 1e-13
+    for a, b in zip(ref, ours):
+        assert relerr(b, a) < tol
+    assert float(ours[1].min()) >= 0.0
