@@ -158,6 +158,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// explicit shared-memory accesses of the epilogue staging tile (the tile's address is derived by integer arithmetic from the
+// dynamic shared-memory base, so plain pointer dereferences compile to generic LD.E / ST.E with their longer latency)
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 // tcgen05.ld without the wait (the caller overlaps global prefetches with the TMEM read latency)
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -185,15 +195,16 @@ __device__ __forceinline__ void epilogue_tile_fast(const Params& p, int b, int i
   const int64_t ld4 = 4 * p.ldd;
   int64_t o_chunk = (int64_t)b * p.sD + (int64_t)(row0 + lr) * p.ldd + j0 + c_begin * 32 + cq;   // element of (row lr, this lane's 4 columns)
   const int64_t colbase = (int64_t)b * p.n + j0 + c_begin * 32 + cq;
-  float qreg[8], racc[8];
-  if (MODE == 1 || MODE == 3) {
+  float racc[8];
+  const float* qrow = p.rowv + (int64_t)b * p.m + row0 + lr;      // rowv of row (4 itr + lr): re-read per use (L1), saves 8 registers
+  if (MODE == 3) {
 #pragma unroll
-    for (int u = 0; u < 8; ++u) { qreg[u] = __ldg(p.rowv + (int64_t)b * p.m + row0 + u * 4 + lr); racc[u] = 0.f; }
+    for (int u = 0; u < 8; ++u) racc[u] = 0.f;
   }
-  uint2 axh[8], axl[8];
-  const float* srd = epi + lr * 32;                  // staging read: row (4 itr + lr), 16-byte slot (lane & 7) ^ (row & 7)
-  float* swr = epi + lane * 32;                      // staging write: row lane
-#pragma unroll
+  uint2 axh[4], axl[4];                              // Aux planes of 4 rows at a time (two batches per chunk)
+  const uint32_t srd = smem_u32(epi) + lr * 128;     // staging read: row (4 itr + lr), 16-byte slot (lane & 7) ^ (row & 7)
+  const uint32_t swr = smem_u32(epi) + lane * 128;   // staging write: row lane
+#pragma unroll 1
   for (int cc = 0; cc < BN / 64; ++cc) {
     uint32_t r[32];
     tmem_ld32_nowait(tmem_acc + (uint32_t)((c_begin + cc) * 32), r);
@@ -203,7 +214,7 @@ __device__ __forceinline__ void epilogue_tile_fast(const Params& p, int b, int i
       cv2 = __ldg(reinterpret_cast<const float4*>(p.colv2 + colbase + cc * 32));
       // (the whole Aux region of this warp was prefetched into L2 when the tile was handed out)
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < 4; ++u) {
         axh[u] = __ldcs(reinterpret_cast<const uint2*>(p.AuxH + o_chunk + u * ld4));
         axl[u] = __ldcs(reinterpret_cast<const uint2*>(p.AuxL + o_chunk + u * ld4));
       }
@@ -211,22 +222,26 @@ __device__ __forceinline__ void epilogue_tile_fast(const Params& p, int b, int i
     tmem_ld_wait();
 #pragma unroll
     for (int u = 0; u < 32; u += 4)
-      *reinterpret_cast<float4*>(swr + (((u >> 2) ^ (lane & 7)) << 2)) =
-          make_float4(__uint_as_float(r[u]), __uint_as_float(r[u + 1]), __uint_as_float(r[u + 2]), __uint_as_float(r[u + 3]));
+      sts128(swr + (((u >> 2) ^ (lane & 7)) << 4), __uint_as_float(r[u]), __uint_as_float(r[u + 1]), __uint_as_float(r[u + 2]),
+             __uint_as_float(r[u + 3]));
     __syncwarp();
     float4 cs1 = make_float4(0.f, 0.f, 0.f, 0.f), cs2 = cs1;
 #pragma unroll
     for (int itr = 0; itr < 8; ++itr) {
       // row = 4 itr + lr, so row & 7 = (4 (itr & 1) + lr) & 7
-      float4 v = *reinterpret_cast<const float4*>(srd + itr * 128 + ((((lane & 7) ^ ((4 * (itr & 1) + lr) & 7))) << 2));
+      float4 v = lds128(srd + itr * 512 + ((((lane & 7) ^ ((4 * (itr & 1) + lr) & 7))) << 4));
       v.x *= alpha_b; v.y *= alpha_b; v.z *= alpha_b; v.w *= alpha_b;
       const int64_t o = o_chunk + itr * ld4;
       if (MODE == 3) {
-        const uint2 hh = axh[itr], ll = axl[itr];
+        const uint2 hh = axh[itr & 3], ll = axl[itr & 3];
+        if (itr < 4) {                                 // this slot is free again: fetch row itr + 4
+          axh[itr] = __ldcs(reinterpret_cast<const uint2*>(p.AuxH + o_chunk + (itr + 4) * ld4));
+          axl[itr] = __ldcs(reinterpret_cast<const uint2*>(p.AuxL + o_chunk + (itr + 4) * ld4));
+        }
         float4 ax;
         ax.x = unpack_sum(hh.x, ll.x, 0) * inv_saux; ax.y = unpack_sum(hh.x, ll.x, 1) * inv_saux;
         ax.z = unpack_sum(hh.y, ll.y, 0) * inv_saux; ax.w = unpack_sum(hh.y, ll.y, 1) * inv_saux;
-        const float qv = qreg[itr];
+        const float qv = __ldg(qrow + itr * 4);
         v.x += fmaf(qv, cv2.x, -2.f * ax.x * cv1.x);
         v.y += fmaf(qv, cv2.y, -2.f * ax.y * cv1.y);
         v.z += fmaf(qv, cv2.z, -2.f * ax.z * cv1.z);
@@ -235,7 +250,7 @@ __device__ __forceinline__ void epilogue_tile_fast(const Params& p, int b, int i
       } else if (MODE != 0) {
         cs1.x = fmaf(v.x, v.x, cs1.x); cs1.y = fmaf(v.y, v.y, cs1.y); cs1.z = fmaf(v.z, v.z, cs1.z); cs1.w = fmaf(v.w, v.w, cs1.w);
         if (MODE == 1) {
-          const float qv = qreg[itr];
+          const float qv = __ldg(qrow + itr * 4);
           cs2.x = fmaf(qv, v.x, cs2.x); cs2.y = fmaf(qv, v.y, cs2.y); cs2.z = fmaf(qv, v.z, cs2.z); cs2.w = fmaf(qv, v.w, cs2.w);
         }
       }
@@ -337,6 +352,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 // Persistent kernel: one CTA per SM, tiles handed out by an atomic counter.  The 512 TMEM columns hold two 128 x 256 fp32
 // accumulators, so the epilogue of tile i overlaps the MMAs of tile i+1.
+// (320 threads are allocated like 384: the register cap is 168 per thread)
 template <bool B_KMAJOR, bool F16>
 __global__ void __launch_bounds__(NTHREADS, 1)
 umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
@@ -604,8 +620,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           // (staging tile: row r keeps its 16-byte column c4 at slot c4 ^ (r & 7): conflict-free both ways without padding)
 #pragma unroll
           for (int u = 0; u < 32; u += 4)
-            *reinterpret_cast<float4*>(epi + lane * 32 + (((u >> 2) ^ (lane & 7)) << 2)) =
-                make_float4(__uint_as_float(r[u]), __uint_as_float(r[u + 1]), __uint_as_float(r[u + 2]), __uint_as_float(r[u + 3]));
+            sts128(smem_u32(epi) + lane * 128 + (((u >> 2) ^ (lane & 7)) << 4), __uint_as_float(r[u]), __uint_as_float(r[u + 1]),
+                   __uint_as_float(r[u + 2]), __uint_as_float(r[u + 3]));
           __syncwarp();
           const int cq = (lane & 7) * 4;
           float4 cs1 = make_float4(0.f, 0.f, 0.f, 0.f), cs2 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -617,7 +633,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 #pragma unroll
           for (int itr = 0; itr < 8; ++itr) {
             const int rr = itr * 4 + (lane >> 3);
-            float4 v = *reinterpret_cast<const float4*>(epi + rr * 32 + (((lane & 7) ^ (rr & 7)) << 2));
+            float4 v = lds128(smem_u32(epi) + rr * 128 + (((lane & 7) ^ (rr & 7)) << 4));
             v.x *= alpha_b; v.y *= alpha_b; v.z *= alpha_b; v.w *= alpha_b;
             const int64_t o = (int64_t)ti.b * p.sD + (int64_t)(ti.i0 + q * 32 + rr) * p.ldd + gj0 + cq;
             if (p.Cin) {

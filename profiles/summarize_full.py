@@ -1,4 +1,5 @@
-"""Key metrics per profiled launch from an `ncu --set full` report (read on the CPU box: ncu -i rep --page raw --csv)."""
+"""Key metrics per profiled launch from an `ncu --set full` report: either the .ncu-rep (read here with `ncu -i rep --page raw
+--csv`) or that raw CSV already exported on the GPU box (reports with many launches exceed the 64 MiB that travel back)."""
 import csv
 import subprocess
 import sys
@@ -11,7 +12,10 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 
 def main(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     kn = hdr.index("Kernel Name")
