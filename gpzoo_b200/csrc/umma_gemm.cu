@@ -212,11 +212,14 @@ __device__ __forceinline__ void epilogue_tile_fast(const Params& p, int b, int i
     if (MODE == 3) {
       cv1 = __ldg(reinterpret_cast<const float4*>(p.colv1 + colbase + cc * 32));
       cv2 = __ldg(reinterpret_cast<const float4*>(p.colv2 + colbase + cc * 32));
-      // (the whole Aux region of this warp was prefetched into L2 when the tile was handed out)
+      // (the whole Aux region of this warp was prefetched into L2 when the tile was handed out; rows 0..3 of the later chunks
+      // are fetched into the register slots freed by rows 4..7 of the chunk before)
+      if (cc == 0) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        axh[u] = __ldcs(reinterpret_cast<const uint2*>(p.AuxH + o_chunk + u * ld4));
-        axl[u] = __ldcs(reinterpret_cast<const uint2*>(p.AuxL + o_chunk + u * ld4));
+        for (int u = 0; u < 4; ++u) {
+          axh[u] = __ldcs(reinterpret_cast<const uint2*>(p.AuxH + o_chunk + u * ld4));
+          axl[u] = __ldcs(reinterpret_cast<const uint2*>(p.AuxL + o_chunk + u * ld4));
+        }
       }
     }
     tmem_ld_wait();
@@ -237,6 +240,9 @@ __device__ __forceinline__ void epilogue_tile_fast(const Params& p, int b, int i
         if (itr < 4) {                                 // this slot is free again: fetch row itr + 4
           axh[itr] = __ldcs(reinterpret_cast<const uint2*>(p.AuxH + o_chunk + (itr + 4) * ld4));
           axl[itr] = __ldcs(reinterpret_cast<const uint2*>(p.AuxL + o_chunk + (itr + 4) * ld4));
+        } else if (cc + 1 < BN / 64) {                 // ... and row itr - 4 of the next chunk
+          axh[itr - 4] = __ldcs(reinterpret_cast<const uint2*>(p.AuxH + o_chunk + 32 + (itr - 4) * ld4));
+          axl[itr - 4] = __ldcs(reinterpret_cast<const uint2*>(p.AuxL + o_chunk + 32 + (itr - 4) * ld4));
         }
         float4 ax;
         ax.x = unpack_sum(hh.x, ll.x, 0) * inv_saux; ax.y = unpack_sum(hh.x, ll.x, 1) * inv_saux;
