@@ -304,9 +304,16 @@ def run_ours(args):
         kernels.append(dict(kernel=name, bound=bound, ms=avg, achieved=ach, peak=peak, unit=unit, frac=ach / peak))
     dom = max(kernels, key=lambda k: k["ms"]) if kernels else None
     roofline = None
+    # DRAM traffic per call (dram__bytes_read.sum + dram__bytes_write.sum summed over the call's launches) from the committed
+    # `ncu --set full` capture profiles/r1e_fp16_ncu_full_summary.txt; only valid for the workload it was captured on
+    NCU_TRAFFIC = {"svgp_predict_bwd_h": (3.008 + 4.884 + 2.700 + 3.040 + 2.632) * 1e9,      # gT, gA, gKzx, gLinv GEMMs + gC pass
+                   "svgp_predict_fwd_h": (2.696 + 2.695) * 1e9, "kernel_build_fwd_h": 1.283e9, "kernel_build_bwd": 1.385e9}
     if dom:
+        traffic = NCU_TRAFFIC.get(dom["kernel"]) if (N, M, L) == (32768, 1024, 10) else None
         roofline = dict(kernel=dom["kernel"], bound=dom["bound"], achieved=dom["achieved"], peak=dom["peak"], unit=dom["unit"],
-                        frac=dom["frac"], traffic=None, peak_source=pk["src"] + (" (bf16 dense, sustained)" if dom["bound"] == "tensor" else ""))
+                        frac=dom["frac"], traffic=traffic, traffic_unit="B/call (ncu, profiles/r1e_fp16_ncu_full_summary.txt)",
+                        peak_source=pk["src"] + (" (bf16 dense, sustained)" if dom["bound"] == "tensor" else ""),
+                        note="split-FP16 arithmetic issues 3 f16 MMAs per product: a perfect kernel reads frac = 0.333")
     h2d = hX.numel() * 4 + hy.numel() * 4
     # value: 32768-spot ELBO steps per second summed over the ranks (weak scaling: every GPU runs configs[1]'s 32768 spots per step
     # and the shared gradients are all-reduced, i.e. the global minibatch is world x 32768 spots)

@@ -95,12 +95,17 @@ class _SparseGPBase(nn.Module):
         T, q = F.Whiten.apply(Linv, Lu, mu.to(Kzz.dtype))
         return Lc, Linv, Lu, T, q, L
 
-    def moments(self, X, groupsX=None):
-        """Fused predictive moments: returns dict(mean, var (unclamped), T, q, Lc, Lu), all L-batched."""
-        F.clear_step_cache()
+    def moments(self, X, groupsX=None, _chain=None):
+        """Fused predictive moments: returns dict(mean, var (unclamped), T, q, Lc, Lu), all L-batched.
+        _chain: (Lc, Linv, Lu, T, q, L) of an earlier call with the same parameters (tiled prediction reuses the Kzz chain)."""
+        if _chain is None:
+            F.clear_step_cache()
         want_h = F.predict_h_ok(X.dtype, self.Z.shape[0], X.shape[0])
         want_lo = (not want_h) and F.tensor_core_predict_ok(X.dtype, self.Z.shape[0], X.shape[0])
-        if want_h and F.OVERLAP_KERNEL_BUILD:
+        if _chain is not None:
+            Kxx, Kzx, _ = self._kernel_matrices(X, groupsX, want_lo, want_h, skip_kzz=True)
+            Lc, Linv, Lu, T, q, L = _chain
+        elif want_h and F.OVERLAP_KERNEL_BUILD:
             # The Kzz chain (Cholesky + inverse: one 8-CTA cluster per factor, latency-bound, about half of the SMs) and the
             # HBM-bound Kzx build are independent: the Kzx kernel is launched on a side stream (torch's current stream, and so
             # the allocator's view of every tensor, stays the same) and joins before the predictive GEMMs.
@@ -121,7 +126,7 @@ class _SparseGPBase(nn.Module):
             if Kh.shape[0] != L:
                 Kzx, Kh, Kl, sK = Kzx.expand(L, -1, -1), Kh.expand(L, -1, -1), Kl.expand(L, -1, -1), sK.expand(L)
             mean, var = F.PredictH.apply(Kxx, Kzx, Linv, T, q, Kh, Kl, sK)
-            return dict(mean=mean, var=var, T=T, q=q, Lc=Lc, Lu=Lu)
+            return dict(mean=mean, var=var, T=T, q=q, Lc=Lc, Lu=Lu, _chain=(Lc, Linv, Lu, T, q, L))
         Kzx_lo = None
         if want_lo:
             Kzx, Kzx_lo = Kzx
@@ -132,7 +137,25 @@ class _SparseGPBase(nn.Module):
             Kzx = Kzx.expand(L, -1, -1)
             Kzx_lo = Kzx_lo.expand(L, -1, -1) if Kzx_lo is not None else None
         mean, var = F.Predict.apply(Kxx, Kzx, Linv, T, q, Kzx_lo)
-        return dict(mean=mean, var=var, T=T, q=q, Lc=Lc, Lu=Lu)
+        return dict(mean=mean, var=var, T=T, q=q, Lc=Lc, Lu=Lu, _chain=(Lc, Linv, Lu, T, q, L))
+
+    @torch.no_grad()
+    def predict_moments(self, X, groupsX=None, tile=32768):
+        """Predictive mean and (unclamped) variance at ALL rows of X, tile by tile and without autograd state, so the
+        footprint is one tile's worth of L x M x tile arrays whatever N is (the reference's notebooks
+        move the model to the CPU to evaluate `model.prior(X)` on every spot, Slideseq_NSF_newest_version.ipynb:624).
+        The Kzz chain (Cholesky, inverse, whitening) is computed once and reused by every tile.  Returns (mean, var), L x N."""
+        means, variances, chain = [], [], None
+        for s0 in range(0, X.shape[0], int(tile)):
+            gx = groupsX[s0:s0 + tile] if groupsX is not None else None
+            m = self.moments(X[s0:s0 + tile].contiguous(), gx) if chain is None else \
+                self.moments(X[s0:s0 + tile].contiguous(), gx, _chain=chain)
+            chain = m.get("_chain", None)
+            means.append(m["mean"])
+            variances.append(m["var"])
+        if not means:
+            raise ValueError("predict_moments needs at least one point")
+        return torch.cat(means, dim=1), torch.cat(variances, dim=1)
 
     def _batched(self):
         return self.mu.dim() == 2 or self.Lu.dim() == 3 or getattr(self.kernel, "_batched", False)
@@ -185,10 +208,10 @@ class MGGP_SVGP(_SparseGPBase):
     def forward(self, X, groupsX, verbose=False):
         return self._distributions(self.moments(X, groupsX))
 
-    def moments(self, X, groupsX=None):
+    def moments(self, X, groupsX=None, _chain=None):
         if groupsX is None:
             raise TypeError("MGGP_SVGP needs groupsX")
-        return super().moments(X, groupsX)
+        return super().moments(X, groupsX, _chain=_chain)
 
 
 class WSVGP(_SparseGPBase):

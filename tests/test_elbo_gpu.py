@@ -306,3 +306,20 @@ def test_ragged_and_degenerate_sizes():
     empty = torch.zeros(0, dtype=torch.int64, device=DEV)
     e0 = model.elbo(prob["X"], prob["y"], idx=empty, E=2, eps=prob["eps"][:, :, empty], return_parts=True)[1]
     assert float(e0["ll"]) == 0.0 and relerr(e0["kl"], full["kl"]) < 1e-12
+
+
+def test_tiled_prediction_matches_full():
+    """gp.predict_moments (no-grad, tile by tile, Kzz chain shared) == the one-shot moments, including a
+    ragged last tile that falls off the tensor-core path."""
+    from gpzoo_b200 import synthetic
+    prob = synthetic.nsf_problem(N=2500, M=128, L=3, G=8, E=1, seed=9, coord_scale=20.0, lengthscale=3.0, jitter=1e-1)
+    model, named = build_nsf(prob, torch.float32)
+    X = prob["X"].to(DEV, torch.float32)
+    gp = model.prior
+    with torch.no_grad():
+        full = gp.moments(X)
+    mean, var = gp.predict_moments(X, tile=1024)
+    assert mean.shape == full["mean"].shape
+    assert relerr(mean, full["mean"]) < 2e-5 and relerr(var, full["var"]) < 2e-5
+    qF, _, _ = gp(X)
+    assert relerr(qF.mean, mean) < 2e-5
