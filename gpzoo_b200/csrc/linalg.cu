@@ -662,34 +662,41 @@ template <typename T> int chol_inv(T* W, T* Lc, T* X, T* tmp, int M, int L, int*
 // ---- element-wise O(M^2) helpers -------------------------------------------------------------------
 // lower-Cholesky transform (torch transforms.py LowerCholeskyTransform._call; gp.py:220):
 //   out = tril(raw,-1) + diag(exp(diag raw))
-template <typename T> __global__ void lct_fwd_kernel(const T* __restrict__ raw, T* __restrict__ out, int M, int64_t total) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= total) return;
-  const int64_t r = e % ((int64_t)M * M);
-  const int i = (int)(r / M), j = (int)(r % M);
-  out[e] = j < i ? raw[e] : (j == i ? Num<T>::exp(raw[e]) : T(0));
+// Row-wise element-wise kernels: blockIdx.x = row i, blockIdx.y = matrix b, threads stride over the columns (no index
+// division; consecutive threads touch consecutive addresses).
+template <typename T> __global__ void __launch_bounds__(256) lct_fwd_kernel(const T* __restrict__ raw, T* __restrict__ out, int M) {
+  const int i = blockIdx.x;
+  const int64_t row = ((int64_t)blockIdx.y * M + i) * M;
+  for (int j = threadIdx.x; j < M; j += blockDim.x) {
+    const T x = j <= i ? raw[row + j] : T(0);
+    out[row + j] = j < i ? x : (j == i ? Num<T>::exp(x) : T(0));
+  }
 }
 // graw = tril(g,-1) + diag(g_ii * Lu_ii)
 template <typename T>
-__global__ void lct_bwd_kernel(const T* __restrict__ g, const T* __restrict__ out, T* __restrict__ graw, int M, int64_t total) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= total) return;
-  const int64_t r = e % ((int64_t)M * M);
-  const int i = (int)(r / M), j = (int)(r % M);
-  graw[e] = j < i ? g[e] : (j == i ? g[e] * out[e] : T(0));
+__global__ void __launch_bounds__(256) lct_bwd_kernel(const T* __restrict__ g, const T* __restrict__ out, T* __restrict__ graw, int M) {
+  const int i = blockIdx.x;
+  const int64_t row = ((int64_t)blockIdx.y * M + i) * M;
+  for (int j = threadIdx.x; j < M; j += blockDim.x) {
+    const T x = j <= i ? g[row + j] : T(0);
+    graw[row + j] = j < i ? x : (j == i ? x * out[row + j] : T(0));
+  }
 }
 // mode 0: out = tril(in) with halved diagonal (the Phi operator of the Cholesky backward)
 // mode 1: out = (in + in^T)/2
 // mode 2: out = tril(in)
 template <typename T>
-__global__ void tri_op_kernel(const T* __restrict__ in, T* __restrict__ out, int M, int64_t total, int mode) {
-  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= total) return;
-  const int64_t b = e / ((int64_t)M * M), r = e % ((int64_t)M * M);
-  const int i = (int)(r / M), j = (int)(r % M);
-  if (mode == 1) out[e] = T(0.5) * (in[e] + in[b * M * M + (int64_t)j * M + i]);
-  else if (mode == 0) out[e] = j < i ? in[e] : (j == i ? T(0.5) * in[e] : T(0));
-  else out[e] = j <= i ? in[e] : T(0);
+__global__ void __launch_bounds__(256) tri_op_kernel(const T* __restrict__ in, T* __restrict__ out, int M, int mode) {
+  const int i = blockIdx.x;
+  const int64_t mat = (int64_t)blockIdx.y * M * M, row = mat + (int64_t)i * M;
+  if (mode == 1) {
+    for (int j = threadIdx.x; j < M; j += blockDim.x) out[row + j] = T(0.5) * (in[row + j] + in[mat + (int64_t)j * M + i]);
+  } else {
+    for (int j = threadIdx.x; j < M; j += blockDim.x) {
+      const T x = j <= i ? in[row + j] : T(0);            // the strict upper triangle is never read
+      out[row + j] = (mode == 0 && j == i) ? T(0.5) * x : x;
+    }
+  }
 }
 
 // KL(N(mu, Lu Lu^T) || N(0, Lc Lc^T)) per factor from the whitened quantities T = Lc^-1 Lu, q = Lc^-1 mu:
@@ -761,28 +768,28 @@ using namespace gpz;
                    a_tri, b_tri, d_tri, splitk);                                                                  \
   }                                                                                                               \
   extern "C" int gpz_lower_cholesky_fwd_##SUF(const T* raw, T* out, int M, int L, void* stream) {                \
-    const int64_t total = (int64_t)M * M * L;                                                                     \
-    lct_fwd_kernel<T><<<(unsigned)cdiv(total, 256), 256, 0, ST(stream)>>>(raw, out, M, total);                   \
+    if (M <= 0 || L <= 0) return GPZ_OK;                                                                          \
+    lct_fwd_kernel<T><<<dim3(M, L), 256, 0, ST(stream)>>>(raw, out, M);                                          \
     GPZ_CHECK_LAUNCH();                                                                                           \
     return GPZ_OK;                                                                                                \
   }                                                                                                               \
   extern "C" int gpz_lower_cholesky_bwd_##SUF(const T* g, const T* out, T* graw, int M, int L, void* stream) {   \
-    const int64_t total = (int64_t)M * M * L;                                                                     \
-    lct_bwd_kernel<T><<<(unsigned)cdiv(total, 256), 256, 0, ST(stream)>>>(g, out, graw, M, total);               \
+    if (M <= 0 || L <= 0) return GPZ_OK;                                                                          \
+    lct_bwd_kernel<T><<<dim3(M, L), 256, 0, ST(stream)>>>(g, out, graw, M);                                      \
     GPZ_CHECK_LAUNCH();                                                                                           \
     return GPZ_OK;                                                                                                \
   }                                                                                                               \
   extern "C" int gpz_tri_op_##SUF(const T* in, T* out, int M, int L, int mode, void* stream) {                   \
-    const int64_t total = (int64_t)M * M * L;                                                                     \
     if (in == out && mode == 1) return GPZ_ERR_BADARG;                                                            \
-    tri_op_kernel<T><<<(unsigned)cdiv(total, 256), 256, 0, ST(stream)>>>(in, out, M, total, mode);               \
+    if (M <= 0 || L <= 0) return GPZ_OK;                                                                          \
+    tri_op_kernel<T><<<dim3(M, L), 256, 0, ST(stream)>>>(in, out, M, mode);                                      \
     GPZ_CHECK_LAUNCH();                                                                                           \
     return GPZ_OK;                                                                                                \
   }                                                                                                               \
   extern "C" int gpz_mvn_kl_fwd_##SUF(const T* Tm, const T* q, const T* Lc, const T* Lu, T* kl, double* ws, int M, \
                                       int L, void* stream) {                                                      \
     GPZ_CUDA(cudaMemsetAsync(ws, 0, sizeof(double) * L, ST(stream)));                                             \
-    mvn_kl_fwd_kernel<T><<<dim3((unsigned)min(M, 64), L), 256, 0, ST(stream)>>>(Tm, q, Lc, Lu, ws, M);           \
+    mvn_kl_fwd_kernel<T><<<dim3((unsigned)min(M, 256), L), 256, 0, ST(stream)>>>(Tm, q, Lc, Lu, ws, M);          \
     GPZ_CHECK_LAUNCH();                                                                                           \
     mvn_kl_finish_kernel<T><<<(unsigned)cdiv(L, 128), 128, 0, ST(stream)>>>(ws, kl, M, L);                       \
     GPZ_CHECK_LAUNCH();                                                                                           \

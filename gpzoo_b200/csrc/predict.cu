@@ -468,6 +468,18 @@ extern "C" int gpz_svgp_predict_bwd_tc_f32(const float* Kzx, const float* Kzx_lo
 }
 
 // split-FP16 tensor-core variant (see predict_fwd_h): planes are fp16, ws_h holds 8 L*M*M halfs, ws_f 2 L*N + 16 L floats
+// row of the stats block (L floats each, starting at ws_f + 2 L N) holding: 0 scale of A, 1 max|A|, 2 max|C|, 3 scale of gA,
+// 4 max|gA|  (read by the host-side overflow guard); -1 for an unknown id
+extern "C" int gpz_svgp_predict_h_stat_row(int which) {
+  switch (which) {
+    case 0: return ST_S_A;
+    case 1: return ST_AMAX_A;
+    case 2: return ST_AMAX_C;
+    case 3: return ST_S_GA;
+    case 4: return ST_AMAX_GA;
+    default: return -1;
+  }
+}
 extern "C" int gpz_svgp_predict_h_supported(int M, int N) { return (M % 8 == 0 && N % 8 == 0 && M >= 64 && N >= 256) ? 1 : 0; }
 extern "C" int gpz_svgp_predict_fwd_h_f32(const void* Kh, const void* Kl, const float* sK, const float* Linv, const float* T,
                                           const float* q, const float* kxx, void* Ah, void* Al, float* C, float* mean, float* var,

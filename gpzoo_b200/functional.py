@@ -391,6 +391,10 @@ def predict_h_ok(dtype, M, N):
             and bool(_cabi.lib().gpz_svgp_predict_h_supported(c_i(int(M)), c_i(int(N)))))
 
 
+def _stat_row(which):
+    return int(_cabi.lib().gpz_svgp_predict_h_stat_row(c_i(which)))
+
+
 class PredictH(Function):
     """Predict on fp16 operand planes (split-FP16 tcgen05 GEMMs, csrc/predict.cu predict_fwd_h / predict_bwd_h).
     `Kzx` is KernelBuildH's stand-in (it only routes dL/dKzx); (Kh, Kl, sK) are the planes it wrote."""
@@ -412,7 +416,8 @@ class PredictH(Function):
         ctx.save_for_backward(Kh, Kl, sK, Linv, T, q, Ah, Al, C, ws_h, ws_f)
         # tracked max |A|, max |C| (slots 7, 8 of the stats block, csrc/predict.cu): examined lazily with the Cholesky info
         st = ws_f[2 * L * N:].view(-1, L)
-        _pending_amax.append((st[7:9], torch.stack((st[2], torch.ones_like(st[2]))), ("A", "C")))
+        r_sA, r_aA, r_aC = (_stat_row(i) for i in (0, 1, 2))
+        _pending_amax.append((torch.stack((st[r_aA], st[r_aC])), torch.stack((st[r_sA], torch.ones_like(st[r_sA]))), ("A", "C")))
         if len(_pending_amax) > 64:
             del _pending_amax[:-64]
         if SYNC_CHECKS:
@@ -437,7 +442,7 @@ class PredictH(Function):
              ptr(gCh), ptr(gCl), ptr(gAh), ptr(gAl), ptr(gKzx), ptr(gLinv), ptr(gT), ptr(gq), ptr(ws_h), ptr(ws_f),
              c_i(M), c_i(N), c_i(L))
         st = ws_f[2 * L * N:].view(-1, L)
-        _pending_amax.append((st[14:15], st[4:5], ("dL/dA",)))          # tracked max |gA| against its scale
+        _pending_amax.append((st[_stat_row(4)].unsqueeze(0), st[_stat_row(3)].unsqueeze(0), ("dL/dA",)))   # max |gA| vs its scale
         return gv, gKzx, gLinv, gT, gq, None, None, None
 
 

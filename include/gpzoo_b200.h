@@ -200,6 +200,9 @@ int gpz_kernel_build_fwd_h_f32(const float* x1, const float* x2, const float* si
                                const float* r2, const int64_t* g1, const int64_t* g2, int n1, int n2, int D, int L, int ng,
                                float p_half, float jitter, void* out_h, void* out_l, float* out_scale, void* stream);
 int gpz_svgp_predict_h_supported(int M, int N);
+/* row (of L floats, counted from ws_f + 2 L N) of: 0 scale of A, 1 max|A|, 2 max|C|, 3 scale of gA, 4 max|gA| — what the
+ * host-side overflow guard of the fp16 planes reads */
+int gpz_svgp_predict_h_stat_row(int which);
 int gpz_svgp_predict_fwd_h_f32(const void* Kh, const void* Kl, const float* sK, const float* Linv, const float* T, const float* q,
                                const float* kxx, void* Ah, void* Al, float* C, float* mean, float* var, void* ws_h, float* ws_f,
                                int M, int N, int L, void* stream);
