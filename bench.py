@@ -237,9 +237,16 @@ def run_ours(args):
             ev.record(copy_stream)
         return Xd, yd, ev
 
+    host_loss = [torch.empty((), dtype=dt).pin_memory() for _ in range(2)]
+
     def e2e_steps(n):
+        """n steps, n uploads, n loss read-backs.  The loss of step i is copied to pinned host memory asynchronously and read on
+        the host after step i+1 has been queued (one-step lag, the usual logging pattern), so neither the upload nor the
+        read-back leaves the GPU idle; the last read-back is waited for before the timed region ends."""
         cur = torch.cuda.current_stream()
         nxt = upload()
+        pending = None
+        losses = []
         for i in range(n):
             Xd, yd, ev = nxt
             cur.wait_event(ev)
@@ -247,7 +254,17 @@ def run_ours(args):
             yd.record_stream(cur)
             if i + 1 < n:
                 nxt = upload()
-            float(step(Xd, yd, None))          # eps drawn on the device, loss D2H (host sync)
+            loss = step(Xd, yd, None)              # eps drawn on the device
+            host_loss[i & 1].copy_(loss.detach().reshape(()), non_blocking=True)      # loss D2H
+            done = torch.cuda.Event()
+            done.record(cur)
+            if pending is not None:
+                pending[0].synchronize()
+                losses.append(float(pending[1]))
+            pending = (done, host_loss[i & 1])
+        pending[0].synchronize()
+        losses.append(float(pending[1]))
+        assert len(losses) == n and all(v == v for v in losses)
 
     hX_keep = None
     ms_e2e = None
@@ -321,7 +338,9 @@ def run_ours(args):
                 ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                 config=dict(workload="NSF2(SVGP(NSF_RBF)) N=32768 M=1024 L=10 G=2000 E=1 (BASELINE.json configs[1]) per GPU",
                             spots_per_gpu=n_loc, global_spots=n_loc * world, parallelism=f"dp{world} over spots, 1 NCCL all-reduce/step",
-                            l2="inputs larger than L2 (y 262 MB, Kzx 1.3 GB)", inducing="jittered 32x32 grid"),
+                            l2="inputs larger than L2 (y 262 MB, Kzx 1.3 GB)", inducing="jittered 32x32 grid",
+                            e2e="per step: X, y uploaded from pinned host memory on a copy stream (double buffered) + loss read back "
+                                "to the host with one-step lag"),
                 clocks=clocks, gpu_launches=int(launches),
                 e2e=(dict(value=world * 1e3 / ms_e2e, unit="steps/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4) if ms_e2e else None),
                 roofline=roofline, kernels=kernels, per_call_ms=per_call)

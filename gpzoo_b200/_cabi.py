@@ -12,7 +12,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgpzoo_b200.so")
+LIB_PATH = os.environ.get("GPZ_LIB") or os.path.join(_HERE, "lib", "libgpzoo_b200.so")     # GPZ_LIB: A/B runs of two builds
 _lib = None
 _lock = threading.Lock()
 launch_count = 0          # number of C-ABI compute calls issued (bench.py reports kernel launches from this)
