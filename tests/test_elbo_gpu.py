@@ -323,3 +323,39 @@ def test_tiled_prediction_matches_full():
     assert relerr(mean, full["mean"]) < 2e-5 and relerr(var, full["var"]) < 2e-5
     qF, _, _ = gp(X)
     assert relerr(qF.mean, mean) < 2e-5
+
+
+def test_tensor_core_mggp_and_scalar_kernel_midsize():
+    """Split-FP16 path with (a) the multi-group kernel (the MG variant of the plane-writing kernel build, minibatch idx, ragged
+    M = 200 that is not a multiple of the 128-row tile) and (b) a scalar RBF kernel whose single Kzx is shared by L = 3 factors
+    (planes expanded over the factors): fp32 step against the fp64 CUDA-core step, ELBO and every gradient within 1e-4."""
+    import gpzoo_b200 as gz
+    from gpzoo_b200 import synthetic
+    # (a) MGGP
+    prob = synthetic.nsf_problem(N=2048, M=200, L=3, G=64, E=1, seed=11, coord_scale=50.0, lengthscale=6.0, jitter=1e-1, n_groups=4)
+    idx = torch.randperm(2048, generator=torch.Generator().manual_seed(3))[:1536]
+    res = {}
+    for dt in (torch.float64, torch.float32):
+        model, named = build_nsf(prob, dt)
+        elbo = model.elbo(prob["X"].to(DEV, dt), prob["y"].to(DEV, dt), idx=idx.to(DEV), E=1, eps=prob["eps"][:, :, idx].to(DEV, dt),
+                          groupsX=prob["groupsX"][idx].to(DEV))
+        elbo.backward()
+        res[dt] = dict(elbo=elbo.detach(), **{k: v.grad.clone() for k, v in named.items()})
+    for k in res[torch.float64]:
+        assert relerr(res[torch.float32][k], res[torch.float64][k]) < 1e-4, k
+    # (b) scalar RBF kernel under L-batched variational parameters
+    prob = synthetic.nsf_problem(N=1024, M=128, L=3, G=32, E=1, seed=12, coord_scale=30.0, lengthscale=5.0, jitter=1e-1)
+    res = {}
+    for dt in (torch.float64, torch.float32):
+        kern = gz.kernels.RBF(sigma=1.3, lengthscale=5.0)
+        kern.sigma, kern.lengthscale = _P(torch.tensor(1.3), dt), _P(torch.tensor(5.0), dt)
+        gp = gz.gp.SVGP(kern, dim=2, M=128, jitter=prob["jitter"])
+        gp.Z, gp.mu, gp.Lu = _P(prob["Z"], dt), _P(prob["mu"], dt), _P(prob["Lu_raw"], dt)
+        model = gz.likelihoods.NSF2(gp, prob["y"], L=3)
+        model.W, model.V = _P(prob["W"], dt), _P(prob["V"], dt)
+        elbo = model.elbo(prob["X"].to(DEV, dt), prob["y"].to(DEV, dt), E=1, eps=prob["eps"].to(DEV, dt))
+        elbo.backward()
+        res[dt] = dict(elbo=elbo.detach(), Z=gp.Z.grad.clone(), sigma=kern.sigma.grad.clone(), ls=kern.lengthscale.grad.clone(),
+                       mu=gp.mu.grad.clone(), Lu=gp.Lu.grad.clone(), W=model.W.grad.clone())
+    for k in res[torch.float64]:
+        assert relerr(res[torch.float32][k], res[torch.float64][k]) < 1e-4, k
