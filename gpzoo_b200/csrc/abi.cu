@@ -2,7 +2,7 @@
 #include "common.cuh"
 #include "gpzoo_b200.h"
 
-extern "C" int gpz_abi_version(void) { return 1; }
+extern "C" int gpz_abi_version(void) { return 2; }      // 2: kernel_build_* take `kind`
 
 extern "C" const char* gpz_error_string(int rc) {
   if (rc == 0) return "success";

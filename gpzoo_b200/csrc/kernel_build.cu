@@ -5,7 +5,10 @@
 //
 //   K[l,i,j] = sigma_l^2 * exp(-0.5 * |x1_i - x2_j|^2 / (ls_l^2 * den)) / den^(p/2),   den = a_l * r2[g1_i, g2_j] + 1
 //
-// (den = 1 without groups).  d^2 is a direct sum of squared differences (never |x|^2+|z|^2-2xz), which is
+// (den = 1 without groups), and the Matern-3/2 covariance functor of kernels.py:6-30 (batched_Matern32):
+//
+//   K[l,i,j] = sigma_l^2 (1 + v) exp(-v),   v = sqrt(3) |x1_i - x2_j| / ls_l.
+//  d^2 is a direct sum of squared differences (never |x|^2+|z|^2-2xz), which is
 // what makes fp32 results track the fp64 reference.  Output layout L x n1 x n2, n2 contiguous.
 // HBM-bound: one pass writes 4*L*n1*n2 bytes; each thread owns 4 consecutive j and streams float4 stores.
 #include "common.cuh"
@@ -30,18 +33,19 @@ template <typename T> struct KBArgs {
   int n1, n2, D, L, ng;
   T p_half;                         // input_dim / 2
   T jitter;                         // added to K[l,i,i] (add_jitter, utilities.py:407-418); 0 for cross matrices
+  int kind;                         // 0: RBF (squared exponential); 1: Matern-3/2 (kernels.py:6-30), no groups
 };
 
 template <typename T> struct Vec4 { T v[4]; };
 
-template <typename T, bool MG, bool ALIGNED>
+template <typename T, bool MG, bool ALIGNED, bool MAT = false>
 __global__ void __launch_bounds__(KB_THREADS) kbuild_fwd_kernel(const KBArgs<T> a, T* __restrict__ out, T* __restrict__ out_lo) {
   __shared__ T s_c[KB_LMAX * 8], s_s2[KB_LMAX * 8], s_a[KB_LMAX * 8];
   __shared__ T s_r2[MG ? KB_GMAX * KB_GMAX : 1];
   const int tid = threadIdx.x;
   for (int l = tid; l < a.L; l += KB_THREADS) {
     const T ls = a.ls[l], sg = a.sigma[l];
-    s_c[l] = T(-0.5) / (ls * ls);
+    s_c[l] = MAT ? Num<T>::sqrt(T(3)) / ls : T(-0.5) / (ls * ls);
     s_s2[l] = sg * sg;
     if (MG) s_a[l] = a.a[l];
   }
@@ -87,6 +91,9 @@ __global__ void __launch_bounds__(KB_THREADS) kbuild_fwd_kernel(const KBArgs<T> 
           const T den = fma(s_a[l], r2[v], T(1));
           const T sc = a.p_half == T(1) ? T(1) / den : Num<T>::pow(den, -a.p_half);
           val = s2 * Num<T>::exp(c * d2[v] / den) * sc;
+        } else if (MAT) {
+          const T vv = c * Num<T>::sqrt(d2[v]);
+          val = s2 * (T(1) + vv) * Num<T>::exp(-vv);
         } else {
           val = s2 * Num<T>::exp(c * d2[v]);
         }
@@ -124,7 +131,7 @@ __global__ void __launch_bounds__(KB_THREADS) kbuild_fwd_kernel(const KBArgs<T> 
 // in (2^14, 2^15].  4 bytes per entry leave the SM (half of K + lo plane in fp32); each thread owns 8 consecutive j and
 // streams one 16-byte store per plane, row and factor.
 constexpr int KB_VEC8 = 8;
-template <bool MG>
+template <bool MG, bool MAT = false>
 __global__ void __launch_bounds__(KB_THREADS) kbuild_fwd_h_kernel(const KBArgs<float> a, __half* __restrict__ out_h,
                                                                   __half* __restrict__ out_l, float* __restrict__ out_scale) {
   __shared__ float s_c[KB_LMAX * 8], s_s2[KB_LMAX * 8], s_a[KB_LMAX * 8], s_sc[KB_LMAX * 8];
@@ -132,7 +139,7 @@ __global__ void __launch_bounds__(KB_THREADS) kbuild_fwd_h_kernel(const KBArgs<f
   const int tid = threadIdx.x;
   for (int l = tid; l < a.L; l += KB_THREADS) {
     const float ls = a.ls[l], sg = a.sigma[l];
-    s_c[l] = -0.5f / (ls * ls);
+    s_c[l] = MAT ? sqrtf(3.f) / ls : -0.5f / (ls * ls);
     s_s2[l] = sg * sg;
     s_sc[l] = gpz_pow2_scale(sg * sg + fabsf(a.jitter));
     if (MG) s_a[l] = a.a[l];
@@ -179,6 +186,9 @@ __global__ void __launch_bounds__(KB_THREADS) kbuild_fwd_h_kernel(const KBArgs<f
           const float den = fmaf(s_a[l], r2[v], 1.f);
           const float scd = a.p_half == 1.f ? 1.f / den : powf(den, -a.p_half);
           val = s2 * expf(c * d2[v] / den) * scd;
+        } else if (MAT) {
+          const float vv = c * sqrtf(d2[v]);
+          val = s2 * (1.f + vv) * expf(-vv);
         } else {
           val = s2 * expf(c * d2[v]);
         }
@@ -211,7 +221,9 @@ __global__ void __launch_bounds__(KB_THREADS) kbuild_fwd_h_kernel(const KBArgs<f
 //   g_a[l]     += sum G K0 (0.5 d2/(ls^2 den^2) - p_half/den) r2             (MG)
 //   g_x1[i,:]  -= sum_{l,j} G K0 (x1_i - x2_j)/(ls^2 den) ;  g_x2[j,:] += same
 // One CTA covers KB_ROWS rows x (KB_THREADS*4) columns; the L accumulators live in registers.
-template <typename T, bool MG, bool ALIGNED, int LMAX>
+// Matern-3/2 (MAT): with e = exp(-v), K0 = s2 (1 + v) e and u = G s2 (3 / ls^2) e the same three accumulations apply:
+//   g_sigma += (2/sigma) sum G K0 ;  g_ls += sum u d2 / ls  (= G s2 v^2 e / ls) ;  dK/dx1 = -u (x1 - x2)  (finite at d = 0)
+template <typename T, bool MG, bool ALIGNED, int LMAX, bool MAT = false>
 __global__ void __launch_bounds__(KB_THREADS, (sizeof(T) == 4 && LMAX <= 12) ? 2 : 1) kbuild_bwd_kernel(const KBArgs<T> a, const T* __restrict__ G, int l0, int Lc,
                                                                  double* __restrict__ g_x1, T* __restrict__ g_x2,
                                                                  double* __restrict__ g_sigma, double* __restrict__ g_ls,
@@ -223,7 +235,7 @@ __global__ void __launch_bounds__(KB_THREADS, (sizeof(T) == 4 && LMAX <= 12) ? 2
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int l = tid; l < Lc; l += KB_THREADS) {
     const T ls = a.ls[l0 + l], sg = a.sigma[l0 + l];
-    s_c[l] = T(-0.5) / (ls * ls);
+    s_c[l] = MAT ? Num<T>::sqrt(T(3)) / ls : T(-0.5) / (ls * ls);
     s_s2[l] = sg * sg;
     if (MG) s_a[l] = a.a[l0 + l];
   }
@@ -292,18 +304,24 @@ __global__ void __launch_bounds__(KB_THREADS, (sizeof(T) == 4 && LMAX <= 12) ? 2
           const T c = s_c[l], s2 = s_s2[l];
 #pragma unroll
           for (int v = 0; v < KB_VEC; ++v) {
-            T k0, idn;
+            T k0, idn, ee = T(0);
             if (MG) {
               const T den = fma(s_a[l], r2[v], T(1));
               idn = T(1) / den;
               const T sc = a.p_half == T(1) ? idn : Num<T>::pow(den, -a.p_half);
               k0 = s2 * Num<T>::exp(c * d2[v] * idn) * sc;
+            } else if (MAT) {
+              idn = T(1);
+              const T vv = c * Num<T>::sqrt(d2[v]);
+              ee = s2 * Num<T>::exp(-vv);
+              k0 = (T(1) + vv) * ee;
             } else {
               idn = T(1);
               k0 = s2 * Num<T>::exp(c * d2[v]);
             }
             const T gk = g[l][v] * k0;
-            const T u = gk * (T(-2) * c) * idn;          // G K0 / (ls^2 den)
+            const T u = MAT ? g[l][v] * ee * c * c       // G s2 exp(-v) 3 / ls^2
+                            : gk * (T(-2) * c) * idn;    // G K0 / (ls^2 den)
             acc_s[l] += gk;
             acc_l[l] = fma(u, d2[v], acc_l[l]);          // later divided by ls
             if (MG) acc_a[l] = fma(gk * r2[v], (T(-1) * c * d2[v] * idn - a.p_half) * idn, acc_a[l]);
@@ -390,7 +408,11 @@ int kbuild_fwd(const KBArgs<T>& a, T* out, T* out_lo, cudaStream_t st) {
   const bool al = (a.n2 % KB_VEC == 0) && ((reinterpret_cast<uintptr_t>(out) & 31) == 0) &&
                   ((reinterpret_cast<uintptr_t>(out_lo) & 15) == 0);
   dim3 grid((unsigned)cdiv(a.n2, (int64_t)KB_THREADS * KB_VEC), (unsigned)cdiv(a.n1, KB_ROWS));
-  if (mg) {
+  if (a.kind != 0 && (a.kind != 1 || mg)) return GPZ_ERR_UNSUPPORTED;       // Matern-3/2 has no multi-group form in the reference
+  if (a.kind == 1) {
+    if (al) kbuild_fwd_kernel<T, false, true, true><<<grid, KB_THREADS, 0, st>>>(a, out, out_lo);
+    else kbuild_fwd_kernel<T, false, false, true><<<grid, KB_THREADS, 0, st>>>(a, out, out_lo);
+  } else if (mg) {
     if (al) kbuild_fwd_kernel<T, true, true><<<grid, KB_THREADS, 0, st>>>(a, out, out_lo);
     else kbuild_fwd_kernel<T, true, false><<<grid, KB_THREADS, 0, st>>>(a, out, out_lo);
   } else {
@@ -413,7 +435,8 @@ int kbuild_bwd(const KBArgs<T>& a, const T* G, T* g_x1, T* g_x2, T* g_sigma, T* 
   if (a.n1 > 0 && a.n2 > 0) {
     const bool al = (a.n2 % KB_VEC == 0) && ((reinterpret_cast<uintptr_t>(G) & 31) == 0);
     dim3 grid((unsigned)cdiv(a.n2, (int64_t)KB_THREADS * KB_VEC), (unsigned)cdiv(a.n1, KB_ROWS));
-    const int lmax = a.L <= 4 ? 4 : (a.L <= 8 ? 8 : (a.L <= 12 ? 12 : (a.L <= 16 ? 16 : KB_LMAX)));
+    if (a.kind != 0 && (a.kind != 1 || mg)) return GPZ_ERR_UNSUPPORTED;
+    const int lmax = a.kind == 1 ? KB_LMAX : (a.L <= 4 ? 4 : (a.L <= 8 ? 8 : (a.L <= 12 ? 12 : (a.L <= 16 ? 16 : KB_LMAX))));
     for (int l0 = 0; l0 < a.L; l0 += lmax) {
       const int Lc = min(lmax, a.L - l0);
       // g_x1/g_x2 accumulate over all l-chunks (atomics), so every chunk launch adds its share
@@ -424,7 +447,10 @@ int kbuild_bwd(const KBArgs<T>& a, const T* G, T* g_x1, T* g_x2, T* g_sigma, T* 
     if (mg) { if (al) GPZ_KB_LAUNCH(true, true, LM); else GPZ_KB_LAUNCH(true, false, LM); }     \
     else { if (al) GPZ_KB_LAUNCH(false, true, LM); else GPZ_KB_LAUNCH(false, false, LM); }      \
   } while (0)
-      if (lmax == 4) GPZ_KB_DISPATCH(4);
+      if (a.kind == 1) {
+        if (al) kbuild_bwd_kernel<T, false, true, KB_LMAX, true><<<grid, KB_THREADS, 0, st>>>(a, G, l0, Lc, w_x1, g_x2, w_sigma, w_ls, w_a);
+        else kbuild_bwd_kernel<T, false, false, KB_LMAX, true><<<grid, KB_THREADS, 0, st>>>(a, G, l0, Lc, w_x1, g_x2, w_sigma, w_ls, w_a);
+      } else if (lmax == 4) GPZ_KB_DISPATCH(4);
       else if (lmax == 8) GPZ_KB_DISPATCH(8);
       else if (lmax == 12) GPZ_KB_DISPATCH(12);
       else if (lmax == 16) GPZ_KB_DISPATCH(16);
@@ -447,16 +473,16 @@ using namespace gpz;
 #define GPZ_KB_IMPL(SUF, T)                                                                                        \
   extern "C" int gpz_kernel_build_fwd_##SUF(const T* x1, const T* x2, const T* sigma, const T* ls, const T* a,     \
                                             const T* r2, const int64_t* g1, const int64_t* g2, int n1, int n2,     \
-                                            int D, int L, int ng, T p_half, T jitter, T* out, T* out_lo,           \
+                                            int D, int L, int ng, int kind, T p_half, T jitter, T* out, T* out_lo, \
                                             void* stream) {                                                        \
-    KBArgs<T> k{x1, x2, sigma, ls, a, r2, g1, g2, n1, n2, D, L, ng, p_half, jitter};                               \
+    KBArgs<T> k{x1, x2, sigma, ls, a, r2, g1, g2, n1, n2, D, L, ng, p_half, jitter, kind};                         \
     return kbuild_fwd<T>(k, out, out_lo, (cudaStream_t)stream);                                                    \
   }                                                                                                                \
   extern "C" int gpz_kernel_build_bwd_##SUF(const T* x1, const T* x2, const T* sigma, const T* ls, const T* a,     \
                                             const T* r2, const int64_t* g1, const int64_t* g2, int n1, int n2,     \
-                                            int D, int L, int ng, T p_half, const T* G, T* g_x1, T* g_x2,          \
+                                            int D, int L, int ng, int kind, T p_half, const T* G, T* g_x1, T* g_x2, \
                                             T* g_sigma, T* g_ls, T* g_a, double* ws, void* stream) {               \
-    KBArgs<T> k{x1, x2, sigma, ls, a, r2, g1, g2, n1, n2, D, L, ng, p_half, T(0)};                                 \
+    KBArgs<T> k{x1, x2, sigma, ls, a, r2, g1, g2, n1, n2, D, L, ng, p_half, T(0), kind};                           \
     return kbuild_bwd<T>(k, G, g_x1, g_x2, g_sigma, g_ls, g_a, ws, (cudaStream_t)stream);                          \
   }                                                                                                                \
   extern "C" int gpz_cdist_##SUF(const T* x1, const T* x2, T* out, int n1, int n2, int D, void* stream) {          \
@@ -473,16 +499,18 @@ GPZ_KB_IMPL(f64, double)
 // fp16-plane forward (fp32 arithmetic): see kbuild_fwd_h_kernel
 extern "C" int gpz_kernel_build_fwd_h_f32(const float* x1, const float* x2, const float* sigma, const float* ls, const float* a,
                                           const float* r2, const int64_t* g1, const int64_t* g2, int n1, int n2, int D, int L,
-                                          int ng, float p_half, float jitter, void* out_h, void* out_l, float* out_scale,
-                                          void* stream) {
-  KBArgs<float> k{x1, x2, sigma, ls, a, r2, g1, g2, n1, n2, D, L, ng, p_half, jitter};
+                                          int ng, int kind, float p_half, float jitter, void* out_h, void* out_l,
+                                          float* out_scale, void* stream) {
+  KBArgs<float> k{x1, x2, sigma, ls, a, r2, g1, g2, n1, n2, D, L, ng, p_half, jitter, kind};
   if (D < 1 || D > KB_DMAX || L < 1 || L > KB_LMAX * 8) return GPZ_ERR_UNSUPPORTED;
   const bool mg = g1 != nullptr;
   if (mg && (ng < 1 || ng > KB_GMAX)) return GPZ_ERR_UNSUPPORTED;
   if (n2 % KB_VEC8 || (reinterpret_cast<uintptr_t>(out_h) & 15) || (reinterpret_cast<uintptr_t>(out_l) & 15)) return GPZ_ERR_UNSUPPORTED;
   if (n1 == 0 || n2 == 0) return GPZ_OK;
   dim3 grid((unsigned)cdiv(n2, (int64_t)KB_THREADS * KB_VEC8), (unsigned)cdiv(n1, KB_ROWS));
-  if (mg) kbuild_fwd_h_kernel<true><<<grid, KB_THREADS, 0, (cudaStream_t)stream>>>(k, (__half*)out_h, (__half*)out_l, out_scale);
+  if (kind != 0 && (kind != 1 || mg)) return GPZ_ERR_UNSUPPORTED;
+  if (kind == 1) kbuild_fwd_h_kernel<false, true><<<grid, KB_THREADS, 0, (cudaStream_t)stream>>>(k, (__half*)out_h, (__half*)out_l, out_scale);
+  else if (mg) kbuild_fwd_h_kernel<true><<<grid, KB_THREADS, 0, (cudaStream_t)stream>>>(k, (__half*)out_h, (__half*)out_l, out_scale);
   else kbuild_fwd_h_kernel<false><<<grid, KB_THREADS, 0, (cudaStream_t)stream>>>(k, (__half*)out_h, (__half*)out_l, out_scale);
   GPZ_CHECK_LAUNCH();
   return GPZ_OK;

@@ -140,7 +140,7 @@ class KernelBuild(Function):
     Replaces kernels.py:114-130 / 141-155 / 172-191 / 204-228 (+ utilities.py:407-418 add_jitter)."""
 
     @staticmethod
-    def forward(ctx, x1, x2, sigma, ls, a, r2, g1, g2, p_half, jitter, want_lo=False):
+    def forward(ctx, x1, x2, sigma, ls, a, r2, g1, g2, p_half, jitter, want_lo=False, kind=0):
         x1, x2, sigma, ls = _c(x1), _c(x2), _c(sigma), _c(ls)
         dt = x1.dtype
         n1, D = x1.shape
@@ -154,10 +154,11 @@ class KernelBuild(Function):
         out_lo = torch.empty_like(out) if want_lo else None
         call("kernel_build_fwd", dt, ptr(x1), ptr(x2), ptr(sigma), ptr(ls), ptr(a if mg else None),
              ptr(r2 if mg else None), ptr(g1 if mg else None), ptr(g2 if mg else None), c_i(n1), c_i(n2), c_i(D), c_i(L),
-             c_i(r2.shape[0] if mg else 0), scalar(dt, p_half), scalar(dt, jitter), ptr(out), ptr(out_lo))
+             c_i(r2.shape[0] if mg else 0), c_i(int(kind)), scalar(dt, p_half), scalar(dt, jitter), ptr(out), ptr(out_lo))
         ctx.save_for_backward(x1, x2, sigma, ls, a if mg else None, r2 if mg else None, g1 if mg else None,
                               g2 if mg else None)
         ctx.p_half = p_half
+        ctx.kind = int(kind)
         ctx.want_lo = want_lo
         ctx.set_materialize_grads(False)      # no zero-filled "gradient" tensors for the non-differentiable lo plane
         if want_lo:
@@ -169,7 +170,7 @@ class KernelBuild(Function):
     @once_differentiable
     def backward(ctx, G, *unused):
         if G is None:
-            return (None,) * 11
+            return (None,) * 12
         x1, x2, sigma, ls, a, r2, g1, g2 = ctx.saved_tensors
         dt = x1.dtype
         G = _c(G)
@@ -185,9 +186,10 @@ class KernelBuild(Function):
         g_a = torch.empty_like(a) if mg else None
         ws = torch.empty(3 * L + n1 * D, dtype=torch.float64, device=x1.device)
         call("kernel_build_bwd", dt, ptr(x1), ptr(x2), ptr(sigma), ptr(ls), ptr(a), ptr(r2), ptr(g1), ptr(g2),
-             c_i(n1), c_i(n2), c_i(D), c_i(L), c_i(r2.shape[0] if mg else 0), scalar(dt, ctx.p_half), ptr(G),
+             c_i(n1), c_i(n2), c_i(D), c_i(L), c_i(r2.shape[0] if mg else 0), c_i(getattr(ctx, "kind", 0)), scalar(dt, ctx.p_half),
+             ptr(G),
              ptr(g_x1), ptr(g_x2), ptr(g_sigma), ptr(g_ls), ptr(g_a), ptr(ws))
-        return g_x1, g_x2, g_sigma, g_ls, g_a, None, None, None, None, None, None
+        return g_x1, g_x2, g_sigma, g_ls, g_a, None, None, None, None, None, None, None
 
 
 class KernelBuildH(Function):
@@ -196,7 +198,7 @@ class KernelBuildH(Function):
     whose only job is to carry dL/dK back to `gpz_kernel_build_bwd` (which recomputes K and never needed it stored)."""
 
     @staticmethod
-    def forward(ctx, x1, x2, sigma, ls, a, r2, g1, g2, p_half, jitter):
+    def forward(ctx, x1, x2, sigma, ls, a, r2, g1, g2, p_half, jitter, kind=0):
         x1, x2, sigma, ls = _c(x1), _c(x2), _c(sigma), _c(ls)
         dt = x1.dtype
         assert dt == torch.float32
@@ -211,10 +213,11 @@ class KernelBuildH(Function):
         sK = torch.empty(L, dtype=dt, device=x1.device)
         call("kernel_build_fwd_h", dt, ptr(x1), ptr(x2), ptr(sigma), ptr(ls), ptr(a if mg else None),
              ptr(r2 if mg else None), ptr(g1 if mg else None), ptr(g2 if mg else None), c_i(n1), c_i(n2), c_i(D), c_i(L),
-             c_i(r2.shape[0] if mg else 0), scalar(dt, p_half), scalar(dt, jitter), ptr(Kh), ptr(Kl), ptr(sK))
+             c_i(r2.shape[0] if mg else 0), c_i(int(kind)), scalar(dt, p_half), scalar(dt, jitter), ptr(Kh), ptr(Kl), ptr(sK))
         ctx.save_for_backward(x1, x2, sigma, ls, a if mg else None, r2 if mg else None, g1 if mg else None,
                               g2 if mg else None)
         ctx.p_half = p_half
+        ctx.kind = int(kind)
         handle = torch.empty(1, dtype=dt, device=x1.device).expand(L, n1, n2)
         ctx.set_materialize_grads(False)      # otherwise autograd zero-fills "gradients" for the fp16 planes (2 x 0.67 GB)
         ctx.mark_non_differentiable(Kh, Kl, sK)
@@ -223,7 +226,7 @@ class KernelBuildH(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, G, *unused):
-        return KernelBuild.backward(ctx, G)[:10]
+        return KernelBuild.backward(ctx, G)[:11]
 
 
 def cdist(x1, x2):

@@ -36,6 +36,7 @@ def _flat(p):
 class _RBFBase(nn.Module):
     input_dim = 2
     _batched = False        # True: parameters are per-factor, output keeps the leading L dimension
+    _kind = 0               # covariance functor of the fused kernel build: 0 = RBF, 1 = Matern-3/2
 
     def _params(self):
         return _flat(self.sigma), _flat(self.lengthscale)
@@ -51,14 +52,14 @@ class _RBFBase(nn.Module):
             if groupsX is not None:
                 return F.KernelBuildH.apply(X, Z, sigma, ls, self._group_coeff().to(dt), _r2_table(self.embedding, dt).to(X.device),
                                             groupsX, groupsZ, 0.5 * float(self.input_dim), float(jitter))
-            return F.KernelBuildH.apply(X, Z, sigma, ls, None, None, None, None, 1.0, float(jitter))
+            return F.KernelBuildH.apply(X, Z, sigma, ls, None, None, None, None, 1.0, float(jitter), self._kind)
         if groupsX is not None:
             a = self._group_coeff().to(dt)
             r2 = _r2_table(self.embedding, dt).to(X.device)
             K = F.KernelBuild.apply(X, Z, sigma, ls, a, r2, groupsX, groupsZ, 0.5 * float(self.input_dim), float(jitter),
                                     want_lo)
         else:
-            K = F.KernelBuild.apply(X, Z, sigma, ls, None, None, None, None, 1.0, float(jitter), want_lo)
+            K = F.KernelBuild.apply(X, Z, sigma, ls, None, None, None, None, 1.0, float(jitter), want_lo, self._kind)
         if want_lo and isinstance(K, tuple):          # (K, K_lo): lo part for the split-TF32 tensor-core GEMMs
             return K if self._batched else (K[0][0], K[1][0])
         if want_lo:
@@ -167,6 +168,17 @@ class batched_RBF(_RBFBase):
         if diag:
             return self._diag(X)
         return self._build(X, Z, jitter=_jitter, want_lo=_want_lo, want_h=_want_h)
+
+
+class batched_Matern32(batched_RBF):
+    """Matern-3/2 covariance sigma^2 (1 + v) exp(-v), v = sqrt(3) |x - z| / lengthscale (kernels.py:6-30), scalar or (L,)
+    parameters: the second covariance functor of the fused kernel build (`kind = 1` of gpz_kernel_build_*).  The analytic
+    backward is finite at x == z, where the reference's autograd of sqrt(sum diff^2) returns NaN."""
+    _kind = 1
+
+    def forward_distance(self, distance_squared):
+        v = (3.0 * distance_squared).sqrt() / self.lengthscale
+        return (self.sigma ** 2) * (1 + v) * torch.exp(-v)
 
 
 class batched_MGGP_RBF(batched_RBF):

@@ -33,21 +33,23 @@ long long gpz_launch_count(void);
  *      204-228 (MGGP_NSF_RBF); jitter = utilities.py:407-418 (add_jitter) fused on the diagonal.
  *      out[l,i,j] = sigma_l^2 exp(-0.5 |x1_i-x2_j|^2/(ls_l^2 den))/den^p_half (+ jitter if i==j),
  *      den = a_l r2[g1_i,g2_j] + 1.  Pass a=r2=g1=g2=NULL, ng=0 for the plain RBF.
+ *      kind = 0: the RBF forms above; kind = 1: Matern-3/2, kernels.py:6-30 (batched_Matern32),
+ *      out[l,i,j] = sigma_l^2 (1 + v) exp(-v), v = sqrt(3) |x1_i-x2_j| / ls_l (no groups; its gradients are finite at |x1-x2| = 0).
  *      out_lo (optional, f32 only): lo = out - tf32_trunc(out), the second operand of the split-TF32 GEMMs. */
 int gpz_kernel_build_fwd_f32(const float* x1, const float* x2, const float* sigma, const float* ls, const float* a,
-                             const float* r2, const int64_t* g1, const int64_t* g2, int n1, int n2, int D, int L, int ng,
+                             const float* r2, const int64_t* g1, const int64_t* g2, int n1, int n2, int D, int L, int ng, int kind,
                              float p_half, float jitter, float* out, float* out_lo, void* stream);
 int gpz_kernel_build_fwd_f64(const double* x1, const double* x2, const double* sigma, const double* ls, const double* a,
-                             const double* r2, const int64_t* g1, const int64_t* g2, int n1, int n2, int D, int L, int ng,
+                             const double* r2, const int64_t* g1, const int64_t* g2, int n1, int n2, int D, int L, int ng, int kind,
                              double p_half, double jitter, double* out, double* out_lo, void* stream);
 /* backward of the above (autograd of kernels.py forward): G = dLoss/dout; g_x1/g_x2/g_a may be NULL.
  * ws: 3*L + n1*D doubles of scratch (parameter and x1 gradients are accumulated in fp64). */
 int gpz_kernel_build_bwd_f32(const float* x1, const float* x2, const float* sigma, const float* ls, const float* a,
-                             const float* r2, const int64_t* g1, const int64_t* g2, int n1, int n2, int D, int L, int ng,
+                             const float* r2, const int64_t* g1, const int64_t* g2, int n1, int n2, int D, int L, int ng, int kind,
                              float p_half, const float* G, float* g_x1, float* g_x2, float* g_sigma, float* g_ls, float* g_a,
                              double* ws, void* stream);
 int gpz_kernel_build_bwd_f64(const double* x1, const double* x2, const double* sigma, const double* ls, const double* a,
-                             const double* r2, const int64_t* g1, const int64_t* g2, int n1, int n2, int D, int L, int ng,
+                             const double* r2, const int64_t* g1, const int64_t* g2, int n1, int n2, int D, int L, int ng, int kind,
                              double p_half, const double* G, double* g_x1, double* g_x2, double* g_sigma, double* g_ls,
                              double* g_a, double* ws, void* stream);
 /* kernels.py:118,123-124 (return_distance=True): Euclidean distances n1 x n2 */
@@ -197,7 +199,7 @@ int gpz_umma_gemm16_f32(int b_kmajor, int m, int n, int k, float alpha, const vo
  *      on those planes: A, gC, gA travel as fp16 planes as well, C, gKzx, gLinv, gT, gq, mean, var are fp32.
  *      ws_h: 8 L M M halfs, ws_f: 2 L N + 16 L floats, both written by fwd and read by bwd; gT and gLinv zero-initialised. */
 int gpz_kernel_build_fwd_h_f32(const float* x1, const float* x2, const float* sigma, const float* ls, const float* a,
-                               const float* r2, const int64_t* g1, const int64_t* g2, int n1, int n2, int D, int L, int ng,
+                               const float* r2, const int64_t* g1, const int64_t* g2, int n1, int n2, int D, int L, int ng, int kind,
                                float p_half, float jitter, void* out_h, void* out_l, float* out_scale, void* stream);
 int gpz_svgp_predict_h_supported(int M, int N);
 /* row (of L floats, counted from ws_f + 2 L N) of: 0 scale of A, 1 max|A|, 2 max|C|, 3 scale of gA, 4 max|gA| — what the

@@ -359,3 +359,25 @@ def test_tensor_core_mggp_and_scalar_kernel_midsize():
                        mu=gp.mu.grad.clone(), Lu=gp.Lu.grad.clone(), W=model.W.grad.clone())
     for k in res[torch.float64]:
         assert relerr(res[torch.float32][k], res[torch.float64][k]) < 1e-4, k
+
+
+def test_matern32_model_tensor_core_vs_fp64():
+    """NSF2(SVGP(batched_Matern32)) at a size that takes the split-FP16 path (the Matern variant of the plane-writing kernel
+    build and of its backward): fp32 step against the fp64 CUDA-core step."""
+    import gpzoo_b200 as gz
+    from gpzoo_b200 import synthetic
+    prob = synthetic.nsf_problem(N=1024, M=128, L=3, G=32, E=1, seed=13, coord_scale=30.0, lengthscale=8.0, jitter=1e-1)
+    res = {}
+    for dt in (torch.float64, torch.float32):
+        kern = gz.kernels.batched_Matern32()
+        kern.sigma, kern.lengthscale = _P(prob["sigma"].reshape(-1), dt), _P(prob["lengthscale"].reshape(-1), dt)
+        gp = gz.gp.SVGP(kern, dim=2, M=128, jitter=prob["jitter"])
+        gp.Z, gp.mu, gp.Lu = _P(prob["Z"], dt), _P(prob["mu"], dt), _P(prob["Lu_raw"], dt)
+        model = gz.likelihoods.NSF2(gp, prob["y"], L=3)
+        model.W, model.V = _P(prob["W"], dt), _P(prob["V"], dt)
+        elbo = model.elbo(prob["X"].to(DEV, dt), prob["y"].to(DEV, dt), E=1, eps=prob["eps"].to(DEV, dt))
+        elbo.backward()
+        res[dt] = dict(elbo=elbo.detach(), Z=gp.Z.grad.clone(), sigma=kern.sigma.grad.clone(), ls=kern.lengthscale.grad.clone(),
+                       mu=gp.mu.grad.clone(), Lu=gp.Lu.grad.clone(), W=model.W.grad.clone())
+    for k in res[torch.float64]:
+        assert relerr(res[torch.float32][k], res[torch.float64][k]) < 1e-4, k
