@@ -50,6 +50,8 @@ template <> struct Num<double> {
 
 // fast-math variants for the HBM-bound fp32 kernels (MUFU-based, ~2 ulp): used where the value only enters sums whose
 // parity tolerance is 1e-4; fp64 keeps the exact functions
+__device__ inline float fast_exp(float x) { return __expf(x); }
+__device__ inline double fast_exp(double x) { return ::exp(x); }
 __device__ inline float fast_log(float x) { return __logf(x); }
 __device__ inline double fast_log(double x) { return ::log(x); }
 __device__ inline float fast_div(float a, float b) { return __fdividef(a, b); }
