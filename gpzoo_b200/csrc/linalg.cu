@@ -13,6 +13,7 @@
 
 #include "gemm_simt.cuh"
 #include "gpzoo_b200.h"
+#include "umma_gemm.h"
 
 namespace gpz {
 
@@ -659,6 +660,75 @@ template <typename T> int chol_inv(T* W, T* Lc, T* X, T* tmp, int M, int L, int*
   return GPZ_OK;
 }
 
+// ---- large M (fp32): the same divide and conquer with the O(M^3) products on the tcgen05 split-TF32 GEMM ---------------
+// For M > 1536 the right-looking sweep above is dominated by its rank-64 trailing updates (each a memory-bound read-modify-write
+// of the whole trailing matrix on the CUDA cores: 29 ms at M = 4096, L = 10).  Here the recursion of chol_inv_rec is cut off at
+// 256 x 256 diagonal blocks (factored + inverted by the CUDA-core recursion) and every product above that size is ONE batched
+// tensor-core GEMM on sub-blocks in place (row stride M): 4 GEMMs per internal node, half of the flops in the top node.
+// The split-TF32 kernel needs the lo plane (x - tf32(x)) of each operand: Wlo / Llo / Xlo / Tlo shadow W / Lc / X / tmp with
+// the same layout; GEMM epilogues write the lo plane of what they produce, leaf blocks get theirs from a small strided pass.
+constexpr int TC_LEAF = 256;
+
+__global__ void tf32_lo_block_kernel(const float* __restrict__ x, float* __restrict__ lo, int n, int M) {
+  // one n x n block (row stride M) per blockIdx.z; blockIdx.y = row, threads over the columns
+  const int64_t base = (int64_t)blockIdx.z * M * M + (int64_t)blockIdx.y * M;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+    const float v = x[base + j];
+    lo[base + j] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  }
+}
+static int lo_block(const float* x, float* lo, int n, int M, int L, cudaStream_t st) {
+  tf32_lo_block_kernel<<<dim3((unsigned)cdiv(n, 256), n, L), 256, 0, st>>>(x, lo, n, M);
+  GPZ_CHECK_LAUNCH();
+  return GPZ_OK;
+}
+
+static int chol_inv_rec_tc(float* W, float* Lc, float* X, float* tmp, float* Wlo, float* Llo, float* Xlo, float* Tlo, int M, int L,
+                           int r0, int n, int* info, cudaStream_t st) {
+  const int64_t sL = (int64_t)M * M;
+  const int64_t o11 = (int64_t)r0 * M + r0;
+  if (n <= TC_LEAF) {
+    int rc = chol_inv_rec<float>(W, Lc, X, tmp, M, L, r0, n, info, st);
+    if (rc) return rc;
+    rc = lo_block(Lc + o11, Llo + o11, n, M, L, st);
+    if (rc) return rc;
+    return lo_block(X + o11, Xlo + o11, n, M, L, st);
+  }
+  const int nb = (int)cdiv(n, 128);
+  const int n1 = (nb / 2) * 128, n2 = n - n1;
+  int rc = chol_inv_rec_tc(W, Lc, X, tmp, Wlo, Llo, Xlo, Tlo, M, L, r0, n1, info, st);
+  if (rc) return rc;
+  const int64_t o21 = (int64_t)(r0 + n1) * M + r0, o22 = (int64_t)(r0 + n1) * M + r0 + n1;
+  // L21 = A21 X11^T            (B = X11 stored n x k: K-major; op(B) = X11^T is upper triangular)
+  rc = umma_gemm_ex(1, n2, n1, n1, 1.0f, W + o21, Wlo + o21, M, sL, X + o11, Xlo + o11, M, sL, nullptr, Lc + o21, Llo + o21, M, sL, L,
+                    0, 2, 0, 1, 3, nullptr, (void*)st);
+  if (rc) return rc;
+  // A22 -= L21 L21^T  (lower triangle, in place)
+  rc = umma_gemm_ex(1, n2, n2, n1, -1.0f, Lc + o21, Llo + o21, M, sL, Lc + o21, Llo + o21, M, sL, W + o22, W + o22, Wlo + o22, M, sL,
+                    L, 0, 0, 1, 1, 3, nullptr, (void*)st);
+  if (rc) return rc;
+  rc = chol_inv_rec_tc(W, Lc, X, tmp, Wlo, Llo, Xlo, Tlo, M, L, r0 + n1, n2, info, st);
+  if (rc) return rc;
+  // tmp21 = L21 X11  (X11 lower triangular, stored k x n) ;  X21 = -X22 tmp21  (X22 lower triangular)
+  rc = umma_gemm_ex(0, n2, n1, n1, 1.0f, Lc + o21, Llo + o21, M, sL, X + o11, Xlo + o11, M, sL, nullptr, tmp + o21, Tlo + o21, M, sL, L,
+                    0, 1, 0, 1, 3, nullptr, (void*)st);
+  if (rc) return rc;
+  return umma_gemm_ex(0, n2, n1, n2, -1.0f, X + o22, Xlo + o22, M, sL, tmp + o21, Tlo + o21, M, sL, nullptr, X + o21, Xlo + o21, M, sL,
+                      L, 1, 0, 0, 1, 3, nullptr, (void*)st);
+}
+
+// lo_ws: 4 L M M floats (shadow lo planes of W, Lc, X, tmp)
+static int chol_inv_tc(float* W, float* Lc, float* X, float* tmp, float* lo_ws, int M, int L, int* info, cudaStream_t st) {
+  const int64_t sL = (int64_t)M * M, tot = sL * L;
+  GPZ_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * L, st));
+  GPZ_CUDA(cudaMemsetAsync(Lc, 0, sizeof(float) * tot, st));
+  GPZ_CUDA(cudaMemsetAsync(X, 0, sizeof(float) * tot, st));
+  float* Wlo = lo_ws; float* Llo = lo_ws + tot; float* Xlo = lo_ws + 2 * tot; float* Tlo = lo_ws + 3 * tot;
+  int rc = gpz_tf32_lo_f32(W, Wlo, tot, (void*)st);
+  if (rc) return rc;
+  return chol_inv_rec_tc(W, Lc, X, tmp, Wlo, Llo, Xlo, Tlo, M, L, 0, M, info, st);
+}
+
 // ---- element-wise O(M^2) helpers -------------------------------------------------------------------
 // lower-Cholesky transform (torch transforms.py LowerCholeskyTransform._call; gp.py:220):
 //   out = tril(raw,-1) + diag(exp(diag raw))
@@ -806,3 +876,11 @@ using namespace gpz;
 
 GPZ_LINALG_IMPL(f32, float)
 GPZ_LINALG_IMPL(f64, double)
+
+// fp32 Cholesky + inverse for large M with the O(M^3) products on the tensor cores (see chol_inv_rec_tc); lo_ws: 4 L M M floats.
+// Same outputs and info convention as gpz_chol_inv_f32.  M % 4 == 0.
+extern "C" int gpz_chol_inv_tc_f32(float* W, float* Lc, float* X, float* tmp, float* lo_ws, int M, int L, int* info, void* stream) {
+  if (M <= 0 || L <= 0) return GPZ_ERR_BADARG;
+  if (M % 4) return GPZ_ERR_UNSUPPORTED;
+  return chol_inv_tc(W, Lc, X, tmp, lo_ws, M, L, info, ST(stream));
+}

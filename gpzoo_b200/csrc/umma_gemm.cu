@@ -1030,8 +1030,9 @@ int umma_gemm16_ex(const Umma16Args& g, void* stream) {
   p.colv2 = epi ? epi->colv2 : nullptr; p.col1 = epi ? epi->col1 : nullptr; p.col2 = epi ? epi->col2 : nullptr;
   p.rowacc = epi ? epi->rowacc : nullptr;
   if (p.epi_mode != 0 && (splitk > 1 || g.d_tri != 0)) return GPZ_ERR_BADARG;
-  p.D = g.D; p.Dlo = nullptr; p.Cin = nullptr; p.m = g.m; p.n = g.n; p.k = g.k; p.ldd = g.ldd; p.sD = g.sD; p.batch = g.batch;
-  p.splitk = splitk; p.a_tri = g.a_tri; p.b_tri = 0; p.d_tri = g.d_tri; p.n_terms = g.n_terms == 1 ? 1 : 3; p.alpha = g.alpha;
+  if (g.Cin && (splitk > 1 || !g.D)) return GPZ_ERR_BADARG;
+  p.D = g.D; p.Dlo = nullptr; p.Cin = g.Cin; p.m = g.m; p.n = g.n; p.k = g.k; p.ldd = g.ldd; p.sD = g.sD; p.batch = g.batch;
+  p.splitk = splitk; p.a_tri = g.a_tri; p.b_tri = g.b_tri; p.d_tri = g.d_tri; p.n_terms = g.n_terms == 1 ? 1 : 3; p.alpha = g.alpha;
   p.bk = BK16; p.sa = g.sa; p.sb = g.sb; p.Dh = g.Dh; p.Dl = g.Dl; p.sd = g.sd; p.amax = g.amax;
   p.AuxH = g.AuxH; p.AuxL = g.AuxL; p.saux = g.saux;
   return launch_gemm(g.b_kmajor != 0, true, mA, mAlo, mB, mBlo, p, (cudaStream_t)stream);
@@ -1092,11 +1093,39 @@ namespace umma {
 __global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ x, int64_t per_batch, unsigned int* __restrict__ amax) {
   const float* xb = x + (int64_t)blockIdx.y * per_batch;
   float m = 0.f;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_batch; i += (int64_t)gridDim.x * blockDim.x)
-    m = fmaxf(m, fabsf(xb[i]));
+  if ((per_batch & 3) == 0 && (reinterpret_cast<uintptr_t>(xb) & 15) == 0) {
+    const float4* x4 = reinterpret_cast<const float4*>(xb);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_batch / 4; i += (int64_t)gridDim.x * blockDim.x) {
+      const float4 v = x4[i];
+      m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_batch; i += (int64_t)gridDim.x * blockDim.x)
+      m = fmaxf(m, fabsf(xb[i]));
+  }
 #pragma unroll
   for (int sh = 16; sh > 0; sh >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, sh));
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax + blockIdx.y, __float_as_uint(m));
+}
+
+// planes only (no transpose): 8 consecutive elements per thread, 16-byte stores
+__global__ void __launch_bounds__(256) split16_flat_kernel(const float* __restrict__ x, int64_t per_batch,
+                                                            const unsigned int* __restrict__ amax, float* __restrict__ scale,
+                                                            __half* __restrict__ h, __half* __restrict__ l) {
+  const int b = blockIdx.y;
+  const float s = gpz_pow2_scale(__uint_as_float(amax[b]));
+  if (blockIdx.x == 0 && threadIdx.x == 0) scale[b] = s;
+  const int64_t base = (int64_t)b * per_batch;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < per_batch; i += (int64_t)gridDim.x * blockDim.x * 8) {
+    const float4 v0 = *reinterpret_cast<const float4*>(x + base + i), v1 = *reinterpret_cast<const float4*>(x + base + i + 4);
+    uint4 ph, pl;
+    split_half2(v0.x * s, v0.y * s, ph.x, pl.x);
+    split_half2(v0.z * s, v0.w * s, ph.y, pl.y);
+    split_half2(v1.x * s, v1.y * s, ph.z, pl.z);
+    split_half2(v1.z * s, v1.w * s, ph.w, pl.w);
+    *reinterpret_cast<uint4*>(h + base + i) = ph;
+    *reinterpret_cast<uint4*>(l + base + i) = pl;
+  }
 }
 
 __global__ void split16_kernel(const float* __restrict__ x, int rows, int cols, const unsigned int* __restrict__ amax,
@@ -1144,6 +1173,14 @@ int split16_amax(const float* x, int64_t per_batch, int batch, unsigned int* ama
 int split16_planes(const float* x, int rows, int cols, int batch, const unsigned int* amax_bits, float* scale, __half* h, __half* l,
                    __half* hT, __half* lT, void* stream) {
   if (rows <= 0 || cols <= 0 || batch <= 0) return GPZ_OK;
+  const int64_t per_batch = (int64_t)rows * cols;
+  if (!hT && h && per_batch % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(h) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(l) & 15) == 0) {
+    const unsigned chunks = (unsigned)std::min<int64_t>(cdiv(per_batch, 256 * 8 * 4), 2048);
+    split16_flat_kernel<<<dim3(chunks, batch), 256, 0, (cudaStream_t)stream>>>(x, per_batch, amax_bits, scale, h, l);
+    GPZ_CHECK_LAUNCH();
+    return GPZ_OK;
+  }
   dim3 grid((unsigned)cdiv(cols, 32), (unsigned)cdiv(rows, 32), batch);
   split16_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(x, rows, cols, amax_bits, scale, h, l, hT, lT);
   GPZ_CHECK_LAUNCH();
@@ -1162,13 +1199,14 @@ extern "C" int gpz_split16_f32(const float* x, int rows, int cols, int batch, vo
 
 extern "C" int gpz_umma_gemm16_f32(int b_kmajor, int m, int n, int k, float alpha, const void* Ah, const void* Al, int64_t lda,
                                    int64_t sA, const float* sa, const void* Bh, const void* Bl, int64_t ldb, int64_t sB,
-                                   const float* sb, float* D, void* Dh, void* Dl, const float* sd, void* amax, int64_t ldd, int64_t sD,
-                                   int batch, int a_tri, int d_tri, int splitk, int n_terms, void* stream) {
+                                   const float* sb, const float* Cin, float* D, void* Dh, void* Dl, const float* sd, void* amax,
+                                   int64_t ldd, int64_t sD, int batch, int a_tri, int b_tri, int d_tri, int splitk, int n_terms,
+                                   void* stream) {
   Umma16Args g{};
   g.b_kmajor = b_kmajor; g.m = m; g.n = n; g.k = k; g.alpha = alpha;
   g.Ah = (const __half*)Ah; g.Al = (const __half*)Al; g.lda = lda; g.sA = sA; g.sa = sa;
   g.Bh = (const __half*)Bh; g.Bl = (const __half*)Bl; g.ldb = ldb; g.sB = sB; g.sb = sb;
   g.D = D; g.ldd = ldd; g.sD = sD; g.Dh = (__half*)Dh; g.Dl = (__half*)Dl; g.sd = sd; g.amax = (unsigned int*)amax;
-  g.batch = batch; g.a_tri = a_tri; g.d_tri = d_tri; g.splitk = splitk; g.n_terms = n_terms;
+  g.batch = batch; g.a_tri = a_tri; g.b_tri = b_tri; g.d_tri = d_tri; g.splitk = splitk; g.n_terms = n_terms; g.Cin = Cin;
   return umma_gemm16_ex(g, stream);
 }

@@ -22,6 +22,8 @@ struct Umma16Args {
   const __half* Ah; const __half* Al; int64_t lda, sA; const float* sa;     // A: m x k, k contiguous
   const __half* Bh; const __half* Bl; int64_t ldb, sB; const float* sb;     // B: k x n (n contiguous) or, b_kmajor, n x k
   float* D; int64_t ldd, sD;                                                // optional fp32 output
+  const float* Cin;                                                         // optional fp32 addend (same layout as D; may be D)
+  int b_tri;                                                                // op(B) (k x n) lower (1) / upper (2) triangular
   __half* Dh; __half* Dl; const float* sd;                                  // optional fp16 (hi, lo) output of D * sd[b]
   unsigned int* amax;                                                       // optional per-batch max |D| (float bits)
   int batch, a_tri, d_tri, splitk, n_terms;

@@ -24,6 +24,7 @@ USE_TENSOR_CORES = True      # fp32: route large contractions through the tcgen0
 # arithmetic of the N-proportional tensor-core GEMMs (K3/K4 and backward): "fp16x3" = split-FP16 (fp16 operand planes, f16 MMA
 # rate), "tf32x3" = split-TF32 (fp32 + lo planes, half the rate; also used when a shape is not 8-aligned)
 TENSOR_CORE_ARITH = os.environ.get("GPZ_TC_ARITH", "fp16x3")
+CHOL_TC_MIN_M = 1536         # above this size the fp32 Cholesky + inverse runs its O(M^3) products on the tensor cores
 _pending_info = []
 # build Kzx on a side stream, concurrently with the Cholesky chain of Kzz (gp.py moments); GPZ_OVERLAP=0 turns it off
 OVERLAP_KERNEL_BUILD = os.environ.get("GPZ_OVERLAP", "1") != "0"
@@ -86,6 +87,14 @@ def gemm(A, B, ta=False, tb=False, alpha=1.0, beta=0.0, out=None, a_tri=0, b_tri
     if out is None:
         out = (torch.zeros if (d_tri or splitk > 1) else torch.empty)((bsz, m, n), dtype=A.dtype, device=A.device)
     dt = A.dtype
+    if (USE_TENSOR_CORES and TENSOR_CORE_ARITH == "fp16x3" and dt == torch.float32 and min(m, n, k) >= GEMM16_MIN_DIM
+            and splitk == 1 and beta in (0.0, 1.0) and m % 8 == 0 and n % 8 == 0 and k % 8 == 0):
+        # large products: split-FP16 (twice the tensor-core rate; the two operand passes are O(M^2) and only pay off here)
+        Ah, Al, sa = split16_cached(A, transposed=ta)
+        Bh, Bl, sb = split16_cached(B)
+        umma_gemm16((Ah, Al, sa), (Bh, Bl, sb), int(tb), a_tri=a_tri, b_tri=b_tri, d_tri=d_tri, alpha=alpha,
+                    Cin=out if beta == 1.0 else None, out=out)
+        return out
     if (USE_TENSOR_CORES and dt == torch.float32 and min(m, n, k) >= 128 and splitk == 1 and beta in (0.0, 1.0)
             and m % 4 == 0 and n % 4 == 0 and k % 4 == 0):
         if ta:
@@ -102,6 +111,23 @@ def gemm(A, B, ta=False, tb=False, alpha=1.0, beta=0.0, out=None, a_tri=0, b_tri
          scalar(dt, beta), ptr(out), c_i64(out.shape[2]), c_i64(out.shape[1] * out.shape[2]),
          c_i(bsz), c_i(a_tri), c_i(b_tri), c_i(d_tri), c_i(splitk))
     return out
+
+
+GEMM16_MIN_DIM = 2048        # M x M x M products at least this large go to the split-FP16 kernel
+
+
+def split16_cached(x, transposed=False):
+    """(h, l, scale) fp16 planes of x — or, transposed=True, of its per-matrix transpose — cached for the duration of a step
+    (the pass that writes the transposed planes writes the plain ones too and fills both cache entries)."""
+    x = _c(x)
+    if not transposed:
+        hit = _step_cache.get(("h16T", x.data_ptr(), x._version, tuple(x.shape)))
+        if hit is not None:
+            h, l, _, _, sc = hit[0]
+            return h, l, sc
+        return _cached("h16", x, lambda: split16(x))
+    h, l, hT, lT, sc = _cached("h16T", x, lambda: split16(x, transpose=True))
+    return hT, lT, sc
 
 
 def transpose_lo(x):
@@ -251,7 +277,11 @@ class CholeskyInverse(Function):
         W = Kzz.detach().clone(memory_format=torch.contiguous_format)
         info = torch.empty(L, dtype=torch.int32, device=Kzz.device)
         Lc, Linv, tmp = torch.empty_like(W), torch.empty_like(W), torch.empty_like(W)
-        call("chol_inv", dt, ptr(W), ptr(Lc), ptr(Linv), ptr(tmp), c_i(M), c_i(L), ptr(info))
+        if USE_TENSOR_CORES and dt == torch.float32 and M > CHOL_TC_MIN_M and M % 4 == 0:
+            lo_ws = torch.empty((4,) + tuple(W.shape), dtype=dt, device=W.device)      # lo planes shadowing W, Lc, Linv, tmp
+            call("chol_inv_tc", dt, ptr(W), ptr(Lc), ptr(Linv), ptr(tmp), ptr(lo_ws), c_i(M), c_i(L), ptr(info))
+        else:
+            call("chol_inv", dt, ptr(W), ptr(Lc), ptr(Linv), ptr(tmp), c_i(M), c_i(L), ptr(info))
         _pending_info.append(info)
         if SYNC_CHECKS:
             check_cholesky_info()
@@ -482,8 +512,8 @@ def split16(x, transpose=False):
     return (h, l, hT, lT, scale) if transpose else (h, l, scale)
 
 
-def umma_gemm16(A, B, b_kmajor, a_tri=0, d_tri=0, splitk=1, n_terms=3, alpha=1.0, out_planes=False, out_scale=None,
-                want_amax=False):
+def umma_gemm16(A, B, b_kmajor, a_tri=0, b_tri=0, d_tri=0, splitk=1, n_terms=3, alpha=1.0, out_planes=False, out_scale=None,
+                want_amax=False, Cin=None, out=None):
     """Direct access to the tcgen05 split-FP16 batched GEMM.  A = (hi, lo, scale) planes of (b, m, k); B = planes of (b, k, n) or,
     b_kmajor, (b, n, k).  Returns fp32 D, or with out_planes the fp16 planes (Dh, Dl) of D * out_scale; want_amax adds max |D|."""
     Ah, Al, sa = A
@@ -491,14 +521,14 @@ def umma_gemm16(A, B, b_kmajor, a_tri=0, d_tri=0, splitk=1, n_terms=3, alpha=1.0
     bsz, m, k = Ah.shape
     n = Bh.shape[1] if b_kmajor else Bh.shape[2]
     dev = Ah.device
-    D = None if out_planes else torch.zeros((bsz, m, n), dtype=torch.float32, device=dev)
+    D = None if out_planes else (out if out is not None else torch.zeros((bsz, m, n), dtype=torch.float32, device=dev))
     Dh = torch.zeros((bsz, m, n), dtype=torch.float16, device=dev) if out_planes else None
     Dl = torch.zeros_like(Dh) if out_planes else None
     amax = torch.zeros(bsz, dtype=torch.int32, device=dev) if want_amax else None
     call("umma_gemm16", torch.float32, c_i(int(b_kmajor)), c_i(m), c_i(n), c_i(k), c_f(alpha), ptr(Ah), ptr(Al), c_i64(Ah.shape[2]),
          c_i64(Ah.shape[1] * Ah.shape[2]), ptr(sa), ptr(Bh), ptr(Bl), c_i64(Bh.shape[2]), c_i64(Bh.shape[1] * Bh.shape[2]), ptr(sb),
-         ptr(D), ptr(Dh), ptr(Dl), ptr(out_scale), ptr(amax), c_i64(n), c_i64(m * n), c_i(bsz), c_i(a_tri), c_i(d_tri), c_i(splitk),
-         c_i(n_terms))
+         ptr(Cin), ptr(D), ptr(Dh), ptr(Dl), ptr(out_scale), ptr(amax), c_i64(n), c_i64(m * n), c_i(bsz), c_i(a_tri), c_i(b_tri),
+         c_i(d_tri), c_i(splitk), c_i(n_terms))
     res = (Dh, Dl) if out_planes else D
     return (res, amax.view(torch.float32)) if want_amax else res
 

@@ -68,6 +68,9 @@ int gpz_trtri_f64(const double* Lc, double* X, double* tmp, int M, int L, void* 
  * (both lower, upper triangle zero), tmp = L x M x M scratch, info as gpz_potrf.  All O(M^3) work is GEMMs. */
 int gpz_chol_inv_f32(float* W, float* Lc, float* X, float* tmp, int M, int L, int* info, void* stream);
 int gpz_chol_inv_f64(double* W, double* Lc, double* X, double* tmp, int M, int L, int* info, void* stream);
+/* the same for large M in fp32 (M % 4 == 0; used for M > 1536): divide and conquer whose products above 256 x 256 run on the
+ * tcgen05 split-TF32 GEMM in place; lo_ws: 4 L M M floats of scratch (lo planes shadowing W, Lc, X, tmp) */
+int gpz_chol_inv_tc_f32(float* W, float* Lc, float* X, float* tmp, float* lo_ws, int M, int L, int* info, void* stream);
 /* strided-batched D = alpha op(A) op(B) + beta D with triangular-structure skipping (see csrc/gemm_simt.cuh):
  * S = Lu Lu^T (gp.py:221), W@(S-Kzz) (utilities.py:395) and the O(M^3) backward products are built from it. */
 int gpz_gemm_f32(int ta, int tb, int m, int n, int k, float alpha, const float* A, int64_t lda, int64_t sA, const float* B,
@@ -185,13 +188,14 @@ int gpz_transpose_lo_f32(const float* x, float* xt, float* xt_lo, int M, int L, 
  *      Operands are pairs of fp16 planes (hi, lo) of x * s[b]: hi = rn(x s), lo = rn(x s - hi), s[b] a per-batch power of two
  *      in device memory chosen from a bound on max |x| so that nothing overflows (gpz_split16 picks it from the exact max).
  *      The kernel issues hi*lo + lo*hi + hi*hi into one TMEM accumulator and undoes the scales in the epilogue.
- *      Outputs (each optional): D fp32; (Dh, Dl) fp16 planes of D * sd[b]; amax[b] = max |D| as float bits (atomicMax). */
+ *      Outputs (each optional): D fp32 (+ Cin, an fp32 addend that may alias D); (Dh, Dl) fp16 planes of D * sd[b];
+ *      amax[b] = max |D| as float bits (atomicMax).  a_tri / b_tri / d_tri: op(A) / op(B) / D lower (1) or upper (2) triangular. */
 int gpz_split16_f32(const float* x, int rows, int cols, int batch, void* h, void* l, void* hT, void* lT, float* scale,
                     void* amax_ws, void* stream);
 int gpz_umma_gemm16_f32(int b_kmajor, int m, int n, int k, float alpha, const void* Ah, const void* Al, int64_t lda, int64_t sA,
-                        const float* sa, const void* Bh, const void* Bl, int64_t ldb, int64_t sB, const float* sb, float* D,
-                        void* Dh, void* Dl, const float* sd, void* amax, int64_t ldd, int64_t sD, int batch, int a_tri,
-                        int d_tri, int splitk, int n_terms, void* stream);
+                        const float* sa, const void* Bh, const void* Bl, int64_t ldb, int64_t sB, const float* sb,
+                        const float* Cin, float* D, void* Dh, void* Dl, const float* sd, void* amax, int64_t ldd, int64_t sD,
+                        int batch, int a_tri, int b_tri, int d_tri, int splitk, int n_terms, void* stream);
 
 /* split-FP16 K1 forward and SVGP predictive op (the default fp32 hot path; csrc/kernel_build.cu, csrc/predict.cu):
  *      kernel_build_fwd_h writes K as fp16 planes (out_h + out_l ~= K * out_scale[l], 4 bytes per entry) instead of fp32;

@@ -48,7 +48,7 @@ def test_gemm_triangular_flags(dt):
 
 
 @pytest.mark.parametrize("dt", [torch.float64, torch.float32])
-@pytest.mark.parametrize("M", [25, 64, 200, 515, 1100])
+@pytest.mark.parametrize("M", [25, 64, 200, 515, 1100, 1600, 2048])      # > 1536: tensor-core divide and conquer in fp32
 def test_cholesky_and_inverse(dt, M):
     from gpzoo_b200 import functional as F
     g = torch.Generator().manual_seed(M)
@@ -443,3 +443,31 @@ def test_matern32_kernel_vs_oracle(dt):
     assert relerr(Kzz, Kzz_ref) < tolb
     (Kzz * Wz.to(DEV, dt)).sum().backward()
     assert bool(torch.isfinite(zd.grad).all()) and relerr(zd.grad, zz.grad) < tolb
+
+
+def test_gemm_split_fp16_route(monkeypatch):
+    """functional.gemm sends large fp32 M x M x M products to the split-FP16 kernel (GEMM16_MIN_DIM, 2048 by default); with the
+    threshold lowered the same route is checked here at small sizes: transposes, triangular flags, beta = 1 accumulation."""
+    from gpzoo_b200 import functional as F
+    monkeypatch.setattr(F, "GEMM16_MIN_DIM", 128)
+    g = torch.Generator().manual_seed(17)
+    b, m = 2, 256
+    A = torch.randn(b, m, m, generator=g)
+    B = torch.randn(b, m, m, generator=g) * 50.0
+    Ad, Bd = A.to(DEV), B.to(DEV)
+    for ta in (False, True):
+        for tb in (False, True):
+            F.clear_step_cache()
+            opA = A.double().transpose(1, 2) if ta else A.double()
+            opB = B.double().transpose(1, 2) if tb else B.double()
+            assert relerr(F.gemm(Ad, Bd, ta=ta, tb=tb), opA @ opB) < 5e-6, (ta, tb)
+    F.clear_step_cache()
+    Lo, Up = torch.tril(A), torch.triu(B)
+    out = F.gemm(Lo.to(DEV), Up.to(DEV), a_tri=1, b_tri=2, d_tri=0)
+    assert relerr(out, Lo.double() @ Up.double()) < 5e-6
+    C0 = torch.randn(b, m, m, generator=g)
+    acc = C0.to(DEV).clone()
+    F.gemm(Lo.to(DEV), Lo.to(DEV), tb=True, alpha=-1.0, beta=1.0, out=acc, b_tri=2, d_tri=1)        # lower triangle updated in place
+    ref = C0.double() - Lo.double() @ Lo.double().transpose(1, 2)
+    assert relerr(torch.tril(acc), torch.tril(ref)) < 5e-6
+    assert torch.equal(torch.triu(acc, 1).cpu(), torch.triu(C0, 1))
