@@ -15,6 +15,7 @@ import argparse
 import json
 import os
 import subprocess
+import threading
 import sys
 import time
 
@@ -41,14 +42,26 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc = index, None
+        self.index, self.proc, self.lines, self.thread, self.n0 = index, None, [], None, 0
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            if line.strip():
+                self.lines.append(line)
 
     def start(self):
+        """Returns once nvidia-smi is streaming (first sample seen, at most 3 s), so that the samples counted from here on
+        fall inside the timed region."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            time.sleep(0.15)          # let it emit its first samples before the timed region starts
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 3.0:
+                time.sleep(0.01)
+            self.n0 = len(self.lines)
         except Exception:
             self.proc = None
 
@@ -58,11 +71,12 @@ class ClockSampler:
             time.sleep(0.05)
             self.proc.terminate()
             try:
-                out, _ = self.proc.communicate(timeout=5)
+                self.proc.wait(timeout=5)
             except Exception:
                 self.proc.kill()
-                out = ""
-            rows = [[c.strip() for c in l.split(",")] for l in out.splitlines() if l.strip()]
+            if self.thread is not None:
+                self.thread.join(timeout=2)
+            rows = [[c.strip() for c in l.split(",")] for l in self.lines[max(0, self.n0 - 1):] if l.strip()]
         sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in rows)]
