@@ -244,14 +244,18 @@ def run_ours(args):
     # The upload of step i+1 runs on a copy stream while step i computes (double buffering, the usual input pipeline of a
     # training loop); every upload and every read-back lies inside the timed region: n steps = n uploads + n read-backs.
     copy_stream = torch.cuda.Stream(device=dev)
+    dbuf = [(torch.empty_like(X), torch.empty_like(y)) for _ in range(2)]      # device landing buffers, reused every other step
+    free_ev = [None, None]                                                      # "the step that read buffer k has finished"
 
-    def upload():
+    def upload(k):
         with torch.cuda.stream(copy_stream):
-            Xd = hX.to(dev, non_blocking=True)
-            yd = hy.to(dev, non_blocking=True)
+            if free_ev[k] is not None:
+                copy_stream.wait_event(free_ev[k])
+            dbuf[k][0].copy_(hX, non_blocking=True)
+            dbuf[k][1].copy_(hy, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy_stream)
-        return Xd, yd, ev
+        return dbuf[k][0], dbuf[k][1], ev
 
     host_loss = [torch.empty((), dtype=dt).pin_memory() for _ in range(2)]
 
@@ -260,20 +264,19 @@ def run_ours(args):
         the host after step i+1 has been queued (one-step lag, the usual logging pattern), so neither the upload nor the
         read-back leaves the GPU idle; the last read-back is waited for before the timed region ends."""
         cur = torch.cuda.current_stream()
-        nxt = upload()
+        nxt = upload(0)
         pending = None
         losses = []
         for i in range(n):
             Xd, yd, ev = nxt
             cur.wait_event(ev)
-            Xd.record_stream(cur)
-            yd.record_stream(cur)
             if i + 1 < n:
-                nxt = upload()
+                nxt = upload((i + 1) & 1)
             loss = step(Xd, yd, None)              # eps drawn on the device
             host_loss[i & 1].copy_(loss.detach().reshape(()), non_blocking=True)      # loss D2H
             done = torch.cuda.Event()
             done.record(cur)
+            free_ev[i & 1] = done
             if pending is not None:
                 pending[0].synchronize()
                 losses.append(float(pending[1]))
