@@ -122,6 +122,33 @@ def cpu_reference_full_step(steps, warmup, n1=128, n2=768):
     return full, cores, note
 
 
+def eager_gpu_reference_step(steps, warmup):
+    """Optional context number (--ref-device cuda): the same oracle port of the reference's op sequence, but with every tensor on
+    the GPU — i.e. the reference's stock PyTorch-eager path (cuBLAS / cuSOLVER / ATen kernels) on this B200 at the FULL config,
+    CUDA-event timed.  Not the reference arm's value (that is the CPU path); reported next to it as `eager_gpu`."""
+    import torch
+    from gpzoo_b200 import synthetic
+    from oracle import gpzoo_oracle as O
+    cfg = CFG
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    prob = synthetic.nsf_problem(N=cfg["N"], M=cfg["M"], L=cfg["L"], G=cfg["G"], E=cfg["E"], seed=cfg["seed"],
+                                 coord_scale=cfg["coord_scale"], lengthscale=cfg["lengthscale"], jitter=cfg["jitter"],
+                                 dtype=torch.float32)
+    p = O.NSFParams(**{k: prob[k].to(dev) for k in ("Z", "sigma", "lengthscale", "mu", "Lu_raw", "W", "V")}, jitter=prob["jitter"])
+    X, y, eps = prob["X"].to(dev), prob["y"].to(dev), prob["eps"].to(dev)
+    run = lambda: O.value_and_grads(lambda: O.nsf_svgp_terms(p, X, y, eps), p.leaves())
+    for _ in range(max(1, warmup)):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps, torch.cuda.max_memory_allocated(dev) / 1e9
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -133,6 +160,10 @@ def run_reference(args):
                 config=dict(workload="NSF2(SVGP(NSF_RBF)) N=32768 M=1024 L=10 G=2000 E=1 (BASELINE.json configs[1])", parallelism="cpu"),
                 cpu_baseline=dict(value=val, unit="steps/s", cores=cores, kind="port", sample=note),
                 e2e=dict(value=val, unit="steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    if args.ref_device == "cuda":
+        ms, gb = eager_gpu_reference_step(max(2, args.steps), args.warmup)
+        line["eager_gpu"] = dict(ms_per_step=ms, value=1e3 / ms, unit="steps/s", peak_mem_gb=gb,
+                                 note="oracle port of the reference's op sequence with all tensors on this GPU (stock PyTorch eager, fp32)")
     print(json.dumps(line), flush=True)
 
 
@@ -379,6 +410,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-device", default="cpu", choices=["cpu", "cuda"],
+                    help="--impl reference only: 'cuda' adds the PyTorch-eager-on-GPU time of the same op sequence (context number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--N", type=int, default=None, help="override the number of spots (debugging only)")

@@ -46,7 +46,7 @@ def squared_dist(X, Z):
 def embed_distance_matrix(D):
     """Classical MDS embedding of a group-distance matrix (utilities.py:459-469)."""
     n = D.shape[0]
-    C = torch.eye(n, dtype=D.dtype) - torch.ones(n, n, dtype=D.dtype) / n
+    C = torch.eye(n, dtype=D.dtype, device=D.device) - torch.ones(n, n, dtype=D.dtype, device=D.device) / n
     B = -0.5 * (C @ (D * D) @ C)
     lam, Q = torch.linalg.eigh(B)
     lam = torch.where(lam < 0, torch.zeros_like(lam), lam)
@@ -57,7 +57,7 @@ def with_jitter(K, jitter):
     """add_jitter (utilities.py:407-418) adds `jitter` to the diagonal IN PLACE and the
     jittered matrix is what flows on; the out-of-place form has the same value/gradient."""
     M = K.shape[-1]
-    return K + jitter * torch.eye(M, dtype=K.dtype)
+    return K + jitter * torch.eye(M, dtype=K.dtype, device=K.device)
 
 
 def lower_cholesky_transform(raw):
