@@ -372,13 +372,13 @@ def run_ours(args):
     dom = max(kernels, key=lambda k: k["ms"]) if kernels else None
     roofline = None
     # DRAM traffic per call (dram__bytes_read.sum + dram__bytes_write.sum summed over the call's launches) from the committed
-    # `ncu --set full` capture profiles/r1e_fp16_ncu_full_summary.txt; only valid for the workload it was captured on
-    NCU_TRAFFIC = {"svgp_predict_bwd_h": (3.008 + 4.884 + 2.700 + 3.040 + 2.632) * 1e9,      # gT, gA, gKzx, gLinv GEMMs + gC pass
-                   "svgp_predict_fwd_h": (2.696 + 2.695) * 1e9, "kernel_build_fwd_h": 1.283e9, "kernel_build_bwd": 1.385e9}
+    # `ncu --set full` capture profiles/r1f_fp16_ncu_full_summary.txt; only valid for the workload it was captured on
+    NCU_TRAFFIC = {"svgp_predict_bwd_h": (3.085 + 4.853 + 2.673 + 3.321 + 2.633) * 1e9,      # gT, gA, gKzx, gLinv GEMMs + gC pass
+                   "svgp_predict_fwd_h": (2.675 + 2.677) * 1e9, "kernel_build_fwd_h": 1.283e9, "kernel_build_bwd": 1.381e9}
     if dom:
         traffic = NCU_TRAFFIC.get(dom["kernel"]) if (N, M, L) == (32768, 1024, 10) else None
         roofline = dict(kernel=dom["kernel"], bound=dom["bound"], achieved=dom["achieved"], peak=dom["peak"], unit=dom["unit"],
-                        frac=dom["frac"], traffic=traffic, traffic_unit="B/call (ncu, profiles/r1e_fp16_ncu_full_summary.txt)",
+                        frac=dom["frac"], traffic=traffic, traffic_unit="B/call (ncu, profiles/r1f_fp16_ncu_full_summary.txt)",
                         peak_source=pk["src"] + (" (bf16 dense, sustained)" if dom["bound"] == "tensor" else ""),
                         note="split-FP16 arithmetic issues 3 f16 MMAs per product: a perfect kernel reads frac = 0.333")
     h2d = hX.numel() * 4 + hy.numel() * 4
