@@ -381,3 +381,21 @@ def test_matern32_model_tensor_core_vs_fp64():
                        mu=gp.mu.grad.clone(), Lu=gp.Lu.grad.clone(), W=model.W.grad.clone())
     for k in res[torch.float64]:
         assert relerr(res[torch.float32][k], res[torch.float64][k]) < 1e-4, k
+
+
+@pytest.mark.parametrize("shape", [dict(N=264, M=72, L=1, G=5, E=1), dict(N=1000, M=136, L=5, G=7, E=3), dict(N=4104, M=64, L=2, G=3, E=2),
+                                   dict(N=256, M=64, L=12, G=4, E=1)])
+def test_tensor_core_ragged_shapes(shape):
+    """Split-FP16 path at awkward sizes (M and N multiples of 8 only: every tile ragged, M below the 128-row tile, a single factor,
+    more factors than the 10 of the benchmark, several Monte-Carlo samples): fp32 step against the fp64 CUDA-core step."""
+    from gpzoo_b200 import functional as Fn, synthetic
+    assert Fn.predict_h_ok(torch.float32, shape["M"], shape["N"])
+    prob = synthetic.nsf_problem(seed=21, coord_scale=20.0, lengthscale=20.0 / max(2.0, shape["M"] ** 0.5) * 2.4, jitter=1e-1, **shape)
+    res = {}
+    for dt in (torch.float64, torch.float32):
+        model, named = build_nsf(prob, dt)
+        elbo = model.elbo(prob["X"].to(DEV, dt), prob["y"].to(DEV, dt), E=shape["E"], eps=prob["eps"].to(DEV, dt))
+        elbo.backward()
+        res[dt] = dict(elbo=elbo.detach(), **{k: v.grad.clone() for k, v in named.items()})
+    for k in res[torch.float64]:
+        assert relerr(res[torch.float32][k], res[torch.float64][k]) < 1e-4, (k, relerr(res[torch.float32][k], res[torch.float64][k]))
