@@ -38,3 +38,29 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_fused_adam_and_tiled_predict_refuse_cpu(lib):
+    """The pieces next to the path have no CPU route either: the fused optimiser and the tiled predictor raise on CPU tensors."""
+    import gpzoo_b200 as gz
+    p = torch.nn.Parameter(torch.randn(7))
+    p.grad = torch.randn(7)
+    with pytest.raises(gz._cabi.GpzError):
+        gz.optim.Adam([p], lr=1e-2).step()
+    gp = gz.gp.SVGP(gz.kernels.NSF_RBF(L=2), dim=2, M=8, jitter=1e-2)
+    gp.mu = torch.nn.Parameter(torch.zeros(2, 8))
+    gp.Lu = torch.nn.Parameter(torch.eye(8).expand(2, -1, -1).contiguous())
+    with pytest.raises(gz._cabi.GpzError):
+        gp.predict_moments(torch.randn(20, 2), tile=8)
+
+
+def test_abi_version_and_new_entry_points(lib):
+    """ABI 2 added `kind` to the kernel-build calls; the split-FP16 / large-M / training-step entry points are exported."""
+    assert lib.gpz_abi_version() >= 2
+    for s in ("gpz_kernel_build_fwd_h_f32", "gpz_svgp_predict_fwd_h_f32", "gpz_svgp_predict_bwd_h_f32", "gpz_split16_f32",
+              "gpz_umma_gemm16_f32", "gpz_chol_inv_tc_f32", "gpz_adam_step_f32", "gpz_adam_step_f64", "gpz_svgp_predict_h_stat_row"):
+        assert hasattr(lib, s), s
+    assert lib.gpz_svgp_predict_h_supported(1024, 32768) == 1 and lib.gpz_svgp_predict_h_supported(1020, 32768) == 0
+    rows = [lib.gpz_svgp_predict_h_stat_row(i) for i in range(5)]
+    assert len(set(rows)) == 5 and min(rows) >= 0                       # five distinct rows of the stats block
+    assert lib.gpz_svgp_predict_h_stat_row(99) == -1
