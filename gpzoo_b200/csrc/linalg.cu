@@ -667,7 +667,11 @@ template <typename T> int chol_inv(T* W, T* Lc, T* X, T* tmp, int M, int L, int*
 // tensor-core GEMM on sub-blocks in place (row stride M): 4 GEMMs per internal node, half of the flops in the top node.
 // The split-TF32 kernel needs the lo plane (x - tf32(x)) of each operand: Wlo / Llo / Xlo / Tlo shadow W / Lc / X / tmp with
 // the same layout; GEMM epilogues write the lo plane of what they produce, leaf blocks get theirs from a small strided pass.
-constexpr int TC_LEAF = 256;
+static int tc_leaf() {            // diagonal blocks up to this size stay on the CUDA-core recursion (GPZ_CHOL_TC_LEAF overrides)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GPZ_CHOL_TC_LEAF"); v = e ? atoi(e) : 256; if (v < 64) v = 64; }
+  return v;
+}
 
 __global__ void tf32_lo_block_kernel(const float* __restrict__ x, float* __restrict__ lo, int n, int M) {
   // one n x n block (row stride M) per blockIdx.z; blockIdx.y = row, threads over the columns
@@ -687,7 +691,7 @@ static int chol_inv_rec_tc(float* W, float* Lc, float* X, float* tmp, float* Wlo
                            int r0, int n, int* info, cudaStream_t st) {
   const int64_t sL = (int64_t)M * M;
   const int64_t o11 = (int64_t)r0 * M + r0;
-  if (n <= TC_LEAF) {
+  if (n <= tc_leaf()) {
     int rc = chol_inv_rec<float>(W, Lc, X, tmp, M, L, r0, n, info, st);
     if (rc) return rc;
     rc = lo_block(Lc + o11, Llo + o11, n, M, L, st);
