@@ -1,21 +1,26 @@
-// tcgen05 / TMEM / TMA batched GEMM in split-TF32 ("3xTF32") arithmetic for the fp32 hot path.
+// tcgen05 / TMEM / TMA batched GEMM in split-precision arithmetic for the fp32 hot path.
 //
 // The big contractions of the SVGP step (the triangular products that replace cholesky_solve, gp.py:218, and
 // svgp_forward, utilities.py:392-395, plus their backward) are genuine dense GEMMs.  The parity target (1e-4 of the
-// fp64 reference on gradients) rules out single-pass TF32 (10-bit mantissa), so every operand x travels as the pair
-// (x, lo) with lo = x - tf32_trunc(x) and each k-step issues three tensor-core MMAs into the same TMEM accumulator:
-//     D += A*B_lo ;  D += A_lo*B ;  D += A*B          (the tensor core truncates A, B to tf32 itself)
-// which recovers ~2^-21 relative accuracy per product at 1/3 of the TF32 rate.
+// fp64 reference on gradients, through a Cholesky factor of condition ~100) rules out a single tensor-core pass (TF32: 7.7e-4,
+// FP16: 2.9e-4 per GEMM), so every operand travels as a pair (hi, lo) and each k-step issues three MMAs into the same TMEM
+// accumulator,  D += hi_A*lo_B ;  D += hi_A*hi_B ;  D += lo_A*hi_B,  which recovers ~2^-22 per product.  Two arithmetics:
+//   split-FP16 (template F16, the default): operands are two fp16 planes of x * s[b] (hi = rn(x s), lo = rn(x s - hi), s[b] a
+//     per-batch power of two in device memory, 4 bytes per entry), kind::f16 MMAs (K = 16) at the f16 rate;
+//   split-TF32: operands are fp32 x plus an fp32 plane lo = x - tf32_trunc(x) (8 bytes per entry; the tensor core truncates x
+//     itself), kind::tf32 MMAs (K = 8) at half that rate.  Kept for the M x M x M products and for shapes that are not 8-aligned.
 //
 //   D[b] (m x n) = alpha * A[b] (m x k, K-major: row-major, k contiguous) * op(B[b]) (+ Cin[b])
 //   op(B): B stored k x n with n contiguous ("MN-major", the layout of Kzx / A / gC / gA: L x M x N), or
 //          B stored n x k with k contiguous ("K-major", used for the reductions over the N spots).
 //
-// One CTA = one 128 x 256 output tile.  Warp 0: TMA producer (cp.async.bulk.tensor into a 4-stage ring of 48 KB
-// stages, 64B-swizzled K-major tiles / 128B(32B-atom)-swizzled MN-major tiles).  Warp 1: allocates 256 TMEM columns and issues
-// tcgen05.mma.kind::tf32 (M=128, N=256, K=8) from one thread, releasing stages with tcgen05.commit.  Warps 2-5:
-// epilogue, tcgen05.ld of the fp32 accumulator -> alpha/Cin/lo-split -> global (or fp32 atomics for split-K).
-// Triangular operands skip whole k-blocks; lower-triangular outputs skip whole tiles.
+// Persistent: one CTA per SM (320 threads), 128 x 256 output tiles from an atomic counter.  Warp 0: scheduler + TMA producer
+// (cp.async.bulk.tensor into a 4-stage ring of 48 KB stages of 64 bytes of k per row; 64B-swizzled K-major tiles, MN-major tiles
+// 128B-swizzled in fp16 / 128B(32B-atom)-swizzled in tf32).  Warp 1: allocates the 512 TMEM columns (two accumulators) and issues
+// tcgen05.mma (M=128, N=256) from one thread, releasing stages and publishing accumulators with tcgen05.commit.  Warps 2-9:
+// epilogue (two warps per TMEM lane quadrant): tcgen05.ld -> XOR-swizzled shared-memory transpose -> scales / fused reductions /
+// fp16 split / max tracking -> full-line stores (or fp32 atomics for split-K), overlapping the next tile's MMAs.
+// Triangular operands skip whole k-blocks; lower-triangular outputs skip whole tiles and use N=128 MMAs on diagonal tiles.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
