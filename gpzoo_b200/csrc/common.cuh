@@ -50,7 +50,11 @@ template <> struct Num<double> {
 
 // fast-math variants for the HBM-bound fp32 kernels (MUFU-based, ~2 ulp): used where the value only enters sums whose
 // parity tolerance is 1e-4; fp64 keeps the exact functions
+#ifdef GPZ_EXACT_EXP
+__device__ inline float fast_exp(float x) { return expf(x); }
+#else
 __device__ inline float fast_exp(float x) { return __expf(x); }
+#endif
 __device__ inline double fast_exp(double x) { return ::exp(x); }
 __device__ inline float fast_log(float x) { return __logf(x); }
 __device__ inline double fast_log(double x) { return ::log(x); }

@@ -24,6 +24,8 @@ USE_TENSOR_CORES = True      # fp32: route large contractions through the tcgen0
 # arithmetic of the N-proportional tensor-core GEMMs (K3/K4 and backward): "fp16x3" = split-FP16 (fp16 operand planes, f16 MMA
 # rate), "tf32x3" = split-TF32 (fp32 + lo planes, half the rate; also used when a shape is not 8-aligned)
 TENSOR_CORE_ARITH = os.environ.get("GPZ_TC_ARITH", "fp16x3")
+# fp32 models: up to this many inducing points the O(M^3) chain runs in fp64 (gp.py `_chain_dtype`); GPZ_CHAIN_FP64_MAX_M=0 turns it off
+CHAIN_FP64_MAX_M = int(os.environ.get("GPZ_CHAIN_FP64_MAX_M", "256"))
 CHOL_TC_MIN_M = 1536         # above this size the fp32 Cholesky + inverse runs its O(M^3) products on the tensor cores
 _pending_info = []
 # build Kzx on a side stream, concurrently with the Cholesky chain of Kzz (gp.py moments); GPZ_OVERLAP=0 turns it off
@@ -54,13 +56,13 @@ def check_cholesky_info():
     the split-FP16 planes (a scale bound that did not hold makes an entry inf, which shows up as a non-finite tracked max)."""
     global _pending_info, _pending_amax
     pend16, _pending_amax = _pending_amax, []
+    pend, _pending_info = _pending_info, []          # both lists are cleared before anything can raise
     for amax, scale, names in pend16:
         bad = ~(amax * scale <= 65504.0)               # also true for NaN / inf
         if bool(bad.any()):
             which = sorted({names[int(i)] for i in bad.nonzero()[:, 0]})
             raise _cabi.GpzError("split-FP16 predict: " + ", ".join(which) + " left the fp16 range its scale bound allows (or the "
                                  "inputs contain inf/NaN); GPZ_TC_ARITH=tf32x3 selects the split-TF32 kernels")
-    pend, _pending_info = _pending_info, []
     for info in pend:
         bad = info.nonzero()
         if bad.numel():
@@ -68,6 +70,23 @@ def check_cholesky_info():
             raise torch.linalg.LinAlgError(
                 f"gpzoo_b200.cholesky: (Batch element {l}): the input is not positive-definite "
                 f"(leading minor of order {int(info[l])} is not positive-definite)")
+
+
+def _fold_pending_amax():
+    """Long unsynchronised runs: fold the queued overflow guards into ONE entry per name (running max of amax * scale on the
+    device, no sync), so that no guard is ever dropped unexamined."""
+    global _pending_amax
+    acc = {}
+    for amax, scale, names in _pending_amax:
+        v = amax * scale
+        v = torch.where(torch.isnan(v), torch.full_like(v, float("inf")), v)       # fmax would hide a NaN
+        for i, nm in enumerate(names):
+            cur = v[i].max().reshape(1)
+            acc[nm] = cur if nm not in acc else torch.maximum(acc[nm], cur)
+    names = tuple(acc)
+    if names:
+        _pending_amax = [(torch.stack([acc[n] for n in names]), torch.ones((len(names), 1), dtype=acc[names[0]].dtype,
+                                                                          device=acc[names[0]].device), names)]
 
 
 def _c(t):
@@ -141,6 +160,62 @@ def transpose_lo(x):
     return _cached("T", x, make)
 
 
+class BatchedMatmul(Function):
+    """A @ B for (batch, m, k) x (batch, k, n) through `gemm` (C-ABI GEMMs), with gA = g B^T and gB = A^T g."""
+
+    @staticmethod
+    def forward(ctx, A, B):
+        A, B = _c(A), _c(B)
+        ctx.save_for_backward(A, B)
+        return gemm(A, B)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        A, B = ctx.saved_tensors
+        g = _c(g)
+        return (gemm(g, B, tb=True) if ctx.needs_input_grad[0] else None,
+                gemm(A, g, ta=True) if ctx.needs_input_grad[1] else None)
+
+
+def matmul(A, B):
+    """Batched matrix product on the library's GEMM kernels; 2-D operands are treated as a batch of one and a 2-D / 3-D mix
+    broadcasts the 2-D operand over the batch."""
+    a3, b3 = A.dim() == 3, B.dim() == 3
+    A3 = A if a3 else A.unsqueeze(0)
+    B3 = B if b3 else B.unsqueeze(0)
+    nb = max(A3.shape[0], B3.shape[0])
+    if A3.shape[0] != nb:
+        A3 = A3.expand(nb, -1, -1)
+    if B3.shape[0] != nb:
+        B3 = B3.expand(nb, -1, -1)
+    out = BatchedMatmul.apply(A3, B3)
+    return out if (a3 or b3) else out[0]
+
+
+class SquaredDist(Function):
+    """|x_i - z_j|^2 by direct differences (the `cdist` kernel squared), with the gradients to both point sets."""
+
+    @staticmethod
+    def forward(ctx, X, Z):
+        X, Z = _c(X), _c(Z)
+        d = cdist(X, Z)
+        ctx.save_for_backward(X, Z)
+        return d * d
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        X, Z = ctx.saved_tensors
+        g = _c(g)
+        gX = gZ = None
+        if ctx.needs_input_grad[0]:      # 2 (x_i sum_j g_ij - sum_j g_ij z_j)
+            gX = 2 * (X * g.sum(1, keepdim=True) - gemm(g.unsqueeze(0), Z.unsqueeze(0))[0])
+        if ctx.needs_input_grad[1]:
+            gZ = 2 * (Z * g.sum(0).unsqueeze(1) - gemm(g.unsqueeze(0), X.unsqueeze(0), ta=True)[0])
+        return gX, gZ
+
+
 def gemv(A, v, trans=False):
     """out[l] = A[l] v[l] (trans=False) or A[l]^T v[l]; A: (L, rows, cols), v: (L, cols) or (L, rows)."""
     A, v = _c(A), _c(v)
@@ -160,6 +235,26 @@ def tri_op(X, mode, out=None):
 # ------------------------------------------------------------------------------------------------
 # K1
 # ------------------------------------------------------------------------------------------------
+def _check_kernel_args(x1, x2, sigma, ls, a, r2, g1, g2):
+    """The C ABI takes raw pointers: every floating-point argument must share x1's dtype and device, group labels must be
+    int64 inside [0, n_groups) (they index the r^2 table in shared memory).  The range check is one small reduction on the
+    device and is skipped with the other synchronising checks (`set_sync_checks(False)`)."""
+    for name, t in (("x2", x2), ("sigma", sigma), ("lengthscale", ls), ("group coefficient", a), ("group r^2 table", r2)):
+        if t is not None and (t.dtype != x1.dtype or t.device != x1.device):
+            raise _cabi.GpzError(f"kernel build: {name} is {t.dtype} on {t.device}, expected {x1.dtype} on {x1.device}")
+    if g1 is not None:
+        g1 = g1.to(device=x1.device, dtype=torch.int64)
+        g2 = g2.to(device=x1.device, dtype=torch.int64)
+        if g1.numel() != x1.shape[0] or g2.numel() != x2.shape[0]:
+            raise _cabi.GpzError("kernel build: one group label per point is required")
+        if SYNC_CHECKS and g1.numel() and g2.numel():
+            lo = min(int(g1.min()), int(g2.min()))
+            hi = max(int(g1.max()), int(g2.max()))
+            if lo < 0 or hi >= r2.shape[0]:
+                raise IndexError(f"group label out of range [0, {r2.shape[0]}): min {lo}, max {hi}")
+    return a, r2, g1, g2
+
+
 class KernelBuild(Function):
     """K[l,i,j] = sigma_l^2 exp(-0.5 |x1_i-x2_j|^2/(ls_l^2 den)) / den^p_half (+ jitter on i==j).
 
@@ -169,6 +264,7 @@ class KernelBuild(Function):
     def forward(ctx, x1, x2, sigma, ls, a, r2, g1, g2, p_half, jitter, want_lo=False, kind=0):
         x1, x2, sigma, ls = _c(x1), _c(x2), _c(sigma), _c(ls)
         dt = x1.dtype
+        a, r2, g1, g2 = _check_kernel_args(x1, x2, sigma, ls, a, r2, g1, g2)
         n1, D = x1.shape
         n2 = x2.shape[0]
         L = sigma.numel()
@@ -228,6 +324,7 @@ class KernelBuildH(Function):
         x1, x2, sigma, ls = _c(x1), _c(x2), _c(sigma), _c(ls)
         dt = x1.dtype
         assert dt == torch.float32
+        a, r2, g1, g2 = _check_kernel_args(x1, x2, sigma, ls, a, r2, g1, g2)
         n1, D = x1.shape
         n2 = x2.shape[0]
         L = sigma.numel()
@@ -402,6 +499,9 @@ class Predict(Function):
         L, M, N = Kzx.shape
         gm = _c(gm) if gm is not None else torch.zeros((L, N), dtype=dt, device=Kzx.device)
         gv = _c(gv) if gv is not None else torch.zeros((L, N), dtype=dt, device=Kzx.device)
+        # the kernels turn their C argument into gC in place: hand them a copy, the saved tensor must survive for a second
+        # backward over the same graph (retain_graph=True)
+        C = C.clone()
         gA = torch.empty_like(Kzx)
         gKzx = torch.empty_like(Kzx)
         gLinv = torch.zeros_like(Linv)
@@ -452,7 +552,7 @@ class PredictH(Function):
         r_sA, r_aA, r_aC = (_stat_row(i) for i in (0, 1, 2))
         _pending_amax.append((torch.stack((st[r_aA], st[r_aC])), torch.stack((st[r_sA], torch.ones_like(st[r_sA]))), ("A", "C")))
         if len(_pending_amax) > 64:
-            del _pending_amax[:-64]
+            _fold_pending_amax()
         if SYNC_CHECKS:
             check_cholesky_info()
         return mean, var

@@ -38,7 +38,7 @@ class PriorMVN(distributions.MultivariateNormal):
 @register_kl(VariationalMVN, PriorMVN)
 def _kl_variational_prior(qU, pU):
     T, q, Lc, Lu, batched = qU._gpz_state
-    kl = F.MvnKL.apply(T, q, Lc, Lu)
+    kl = F.MvnKL.apply(T, q, Lc, Lu).to(qU.loc.dtype)
     return kl if batched else kl[0]
 
 
@@ -95,13 +95,33 @@ class _SparseGPBase(nn.Module):
         T, q = F.Whiten.apply(Linv, Lu, mu.to(Kzz.dtype))
         return Lc, Linv, Lu, T, q, L
 
+    def _chain_dtype(self, dt):
+        """Arithmetic of the O(M^3) chain (Kzz build, Cholesky + inverse, whitening, KL and their backward).  The chain is where
+        the conditioning of Kzz enters (its fp32 error grows like cond(Kzz) * 6e-8, for the reference's fp32 too), and up to
+        M = F.CHAIN_FP64_MAX_M it is latency-bound and costs the same in double precision: fp32 models run it in fp64 there
+        and hand fp32 Linv / T / q to the N-proportional kernels.  Above that size it runs in the model's dtype."""
+        if dt == torch.float32 and self.Z.shape[0] <= F.CHAIN_FP64_MAX_M:
+            return torch.float64
+        return dt
+
+    def _kzz(self, X, groupsX, cdt):
+        if cdt == X.dtype:
+            return self._kernel_matrices(X, groupsX, skip_kzx=True)[2]
+        Zc = self.Z.to(cdt)
+        if groupsX is not None:
+            return self.kernel(Zc, Zc, self.groupsZ, self.groupsZ, _jitter=self.jitter)
+        return self.kernel(Zc, Zc, _jitter=self.jitter)
+
     def moments(self, X, groupsX=None, _chain=None):
-        """Fused predictive moments: returns dict(mean, var (unclamped), T, q, Lc, Lu), all L-batched.
+        """Fused predictive moments: returns dict(mean, var (unclamped), T, q, Lc, Lu), all L-batched (T, q, Lc, Lu in the
+        chain's dtype, see `_chain_dtype`).
         _chain: (Lc, Linv, Lu, T, q, L) of an earlier call with the same parameters (tiled prediction reuses the Kzz chain)."""
         if _chain is None:
             F.clear_step_cache()
-        want_h = F.predict_h_ok(X.dtype, self.Z.shape[0], X.shape[0])
-        want_lo = (not want_h) and F.tensor_core_predict_ok(X.dtype, self.Z.shape[0], X.shape[0])
+        dt = X.dtype
+        cdt = self._chain_dtype(dt)
+        want_h = F.predict_h_ok(dt, self.Z.shape[0], X.shape[0])
+        want_lo = (not want_h) and F.tensor_core_predict_ok(dt, self.Z.shape[0], X.shape[0])
         if _chain is not None:
             Kxx, Kzx, _ = self._kernel_matrices(X, groupsX, want_lo, want_h, skip_kzz=True)
             Lc, Linv, Lu, T, q, L = _chain
@@ -112,12 +132,14 @@ class _SparseGPBase(nn.Module):
             side = F.side_stream(X.device)
             with F.launch_on(side):
                 Kxx, Kzx, _ = self._kernel_matrices(X, groupsX, want_lo, want_h, skip_kzz=True)
-            _, _, Kzz = self._kernel_matrices(X, groupsX, skip_kzx=True)
-            Lc, Linv, Lu, T, q, L = self._whitened(Kzz)
+            Lc, Linv, Lu, T, q, L = self._whitened(self._kzz(X, groupsX, cdt))
             torch.cuda.current_stream().wait_stream(side)
         else:
-            Kxx, Kzx, Kzz = self._kernel_matrices(X, groupsX, want_lo, want_h)
-            Lc, Linv, Lu, T, q, L = self._whitened(Kzz)
+            Kxx, Kzx, _ = self._kernel_matrices(X, groupsX, want_lo, want_h, skip_kzz=True)
+            Lc, Linv, Lu, T, q, L = self._whitened(self._kzz(X, groupsX, cdt))
+        chain = (Lc, Linv, Lu, T, q, L)
+        out = dict(T=T, q=q, Lc=Lc, Lu=Lu, _chain=chain)
+        Linv, T, q = Linv.to(dt), T.to(dt), q.to(dt)            # the N-proportional kernels run in the model's dtype
         Kxx = Kxx if Kxx.dim() == 2 else Kxx.unsqueeze(0)
         if Kxx.shape[0] != L:
             Kxx = Kxx.expand(L, -1)
@@ -126,7 +148,7 @@ class _SparseGPBase(nn.Module):
             if Kh.shape[0] != L:
                 Kzx, Kh, Kl, sK = Kzx.expand(L, -1, -1), Kh.expand(L, -1, -1), Kl.expand(L, -1, -1), sK.expand(L)
             mean, var = F.PredictH.apply(Kxx, Kzx, Linv, T, q, Kh, Kl, sK)
-            return dict(mean=mean, var=var, T=T, q=q, Lc=Lc, Lu=Lu, _chain=(Lc, Linv, Lu, T, q, L))
+            return dict(out, mean=mean, var=var)
         Kzx_lo = None
         if want_lo:
             Kzx, Kzx_lo = Kzx
@@ -137,7 +159,7 @@ class _SparseGPBase(nn.Module):
             Kzx = Kzx.expand(L, -1, -1)
             Kzx_lo = Kzx_lo.expand(L, -1, -1) if Kzx_lo is not None else None
         mean, var = F.Predict.apply(Kxx, Kzx, Linv, T, q, Kzx_lo)
-        return dict(mean=mean, var=var, T=T, q=q, Lc=Lc, Lu=Lu, _chain=(Lc, Linv, Lu, T, q, L))
+        return dict(out, mean=mean, var=var)
 
     @torch.no_grad()
     def predict_moments(self, X, groupsX=None, tile=32768):
@@ -164,6 +186,7 @@ class _SparseGPBase(nn.Module):
         b = self._batched()
         mean, var = (m["mean"], m["var"]) if b else (m["mean"][0], m["var"][0])
         Lu, Lc = (m["Lu"], m["Lc"]) if b else (m["Lu"][0], m["Lc"][0])
+        Lu, Lc = Lu.to(mean.dtype), Lc.to(mean.dtype)            # (the KL below still uses the chain's own precision)
         qF = distributions.Normal(mean, torch.clamp(var, min=self.clamp_min) ** 0.5, validate_args=False)
         mu = self.mu.to(Lu.dtype)
         qU = VariationalMVN(mu, Lu, (m["T"], m["q"], m["Lc"], m["Lu"], b))
@@ -215,10 +238,12 @@ class MGGP_SVGP(_SparseGPBase):
 
 
 class WSVGP(_SparseGPBase):
-    """Whitened SVGP (gp.py:235-322): W = Kxz Lc^-T, var = (Kxx - sum W^2) + sum (W Lu)^2, pZ = None.
-    Same fused predict kernel with T := Lu and q := mu.  The reference clamps (Kxx - sum W^2) at 0 before adding
-    the second term (gp.py:287) — a guard against round-off only (the term is >= 0 in exact arithmetic);
-    here the sum is formed in one pass and clamped at 0 as a whole."""
+    """Whitened SVGP (gp.py:235-322): u = Lc v with q(v) = N(mu, Lu Lu^T), so W = Kxz Lc^-T, mean = W mu,
+    var = (Kxx - sum W^2) + sum (W Lu)^2 and pZ = None (the caller adds `whitened_KL`).  In the notation of `moments` this is
+    the same predictive kernel with T := Lu and q := mu (no whitening products), and KL(q(v) || N(0, I)) is the fused KL
+    kernel with Lc := I, which is what `model.elbo(...)` subtracts.  The reference clamps (Kxx - sum W^2) at 0 before adding
+    the second term (gp.py:287) — a guard against round-off only (the term is >= 0 in exact arithmetic); here the sum is
+    formed in one pass and clamped at 0 as a whole."""
     clamp_min = 0.0
 
     def __init__(self, kernel, dim=1, M=50, jitter=1e-4):
@@ -231,34 +256,55 @@ class WSVGP(_SparseGPBase):
     def forward_kernels(self, X, **args):
         return self._kernel_matrices(X, args.get("groupsX"))
 
-    def _whitened_moments(self, Kxx, Kzx, Kzz):
-        Kzz, Kzx = _as3(Kzz), _as3(Kzx)
-        Kxx = Kxx if Kxx.dim() == 2 else Kxx.unsqueeze(0)
+    def _whitened(self, Kzz):
+        Kzz = _as3(Kzz)
         mu = self.mu if self.mu.dim() == 2 else self.mu.unsqueeze(0)
-        Lu = F.LowerCholesky.apply(_as3(self.Lu).to(Kzz.dtype))
-        L = max(Kzz.shape[0], mu.shape[0], Lu.shape[0])
-        Lc, Linv = F.CholeskyInverse.apply(Kzz)
+        Lu_raw = _as3(self.Lu)
+        L = max(Kzz.shape[0], mu.shape[0], Lu_raw.shape[0])
         ex = lambda t: t if t.shape[0] == L else t.expand(L, *t.shape[1:])
-        mean, var = F.Predict.apply(ex(Kxx), ex(Kzx), ex(Linv), ex(Lu), ex(mu.to(Kzz.dtype)))
-        return mean, var, Lu
+        Lc, Linv = F.CholeskyInverse.apply(Kzz)
+        Lu = ex(F.LowerCholesky.apply(Lu_raw.to(Kzz.dtype)))
+        eye = torch.eye(Kzz.shape[-1], dtype=Kzz.dtype, device=Kzz.device).expand(L, -1, -1).contiguous()
+        return eye, ex(Linv), Lu, Lu, ex(mu.to(Kzz.dtype)), L          # (Lc := I for the KL, Linv, Lu, T := Lu, q := mu)
 
-    def forward(self, X, verbose=False, **args):
-        Kxx, Kzx, Kzz = self.forward_kernels(X, **args)
-        mean, var, Lu = self._whitened_moments(Kxx, Kzx, Kzz)
-        b = self._batched()
-        if not b:
+    def _whitened_distributions(self, mean, var, Lu):
+        if not self._batched():
             mean, var, Lu = mean[0], var[0], Lu[0]
         qF = distributions.Normal(mean, torch.clamp(var, min=0.0) ** 0.5, validate_args=False)
         qZ = distributions.MultivariateNormal(self.mu.to(Lu.dtype), scale_tril=Lu, validate_args=False)
         return qF, qZ, None
 
+    def forward(self, X, verbose=False, **args):
+        m = self.moments(X, args.get("groupsX"))
+        return self._whitened_distributions(m["mean"], m["var"], m["Lu"].to(m["mean"].dtype))
+
+    def forward_precomputed(self, W, **args):
+        """gp.py:308-322: predictive distribution from a precomputed W = Kxz Lc^-T (L x N x M), skipping the kernel build and
+        the Cholesky.  Kxx is sigma^2 per factor as in the reference ((L,) sigma of the batched kernels; (L,1,1) is accepted
+        too).  Runs the fused predictive kernel with A := W^T (the triangular product by Linv := I is the price of reusing it)."""
+        W3 = _as3(W)
+        L, N, M = W3.shape
+        dt = W3.dtype
+        mu = self.mu if self.mu.dim() == 2 else self.mu.unsqueeze(0)
+        ex = lambda t: t if t.shape[0] == L else t.expand(L, *t.shape[1:])
+        Lu = ex(F.LowerCholesky.apply(_as3(self.Lu).to(dt)))
+        Kxx = ex((self.kernel.sigma.reshape(-1, 1).to(dt) ** 2)).expand(L, N)
+        eye = torch.eye(M, dtype=dt, device=W3.device).expand(L, -1, -1).contiguous()
+        mean, var = F.Predict.apply(Kxx, W3.transpose(-2, -1), eye, Lu, ex(mu.to(dt)), None)
+        return self._whitened_distributions(mean, var, Lu)
+
 
 class MGGP_WSVGP(WSVGP):
-    """gp.py:385-399."""
+    """gp.py:385-399: forward(X, groupsX=...) as a keyword (the reference reads args['groupsX'])."""
 
     def __init__(self, kernel, dim=1, M=50, n_groups=2, jitter=1e-4):
         super().__init__(kernel, dim, M, jitter)
         self.groupsZ = nn.Parameter(torch.randint(0, n_groups, (M,)).type(torch.LongTensor), requires_grad=False)
+
+    def moments(self, X, groupsX=None, _chain=None):
+        if groupsX is None:
+            raise TypeError("MGGP_WSVGP needs groupsX")
+        return super().moments(X, groupsX, _chain=_chain)
 
 
 class VNNGP(_SparseGPBase):
@@ -283,6 +329,9 @@ class VNNGP(_SparseGPBase):
 
     def moments(self, X, groupsX=None):
         dt = X.dtype
+        if getattr(self.kernel, "_kind", 0) != 0:
+            raise NotImplementedError("VNNGP's fused neighbour kernel evaluates the RBF cross-covariance; "
+                                      f"{type(self.kernel).__name__} is not supported")
         F.clear_step_cache()
         Kzz = _as3(self.kernel(self.Z, self.Z, _jitter=self.jitter))                 # first jitter (gp.py:55)
         Kxx = self.kernel(X, X, diag=True)

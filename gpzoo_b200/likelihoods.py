@@ -26,7 +26,9 @@ def _sample(qF, E, eps=None):
 
 
 def _gp_call(gp, X, verbose, kwargs):
-    return gp(X, verbose=verbose, **kwargs) if "groupsX" not in kwargs else gp(X, kwargs["groupsX"], verbose)
+    # keywords, as the reference calls its priors (likelihoods.py:81, 111): MGGP_SVGP.forward(X, groupsX, verbose) and
+    # MGGP_WSVGP.forward(X, verbose, **args) both take groupsX by name
+    return gp(X, verbose=verbose, **kwargs)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -116,7 +118,7 @@ class _FusedPoissonMixin:
         W = self.W.to(mean.dtype)
         ll = F.PoissonLL.apply(y, idx, W, self.V.to(mean.dtype), mean, var, eps, mean.shape[0], gp.clamp_min,
                                self._w_softplus, with_lgamma)
-        kl = F.MvnKL.apply(m["T"], m["q"], m["Lc"], m["Lu"])
+        kl = F.MvnKL.apply(m["T"], m["q"], m["Lc"], m["Lu"]).to(mean.dtype)
         out = ll - kl_weight * kl.sum()
         if return_parts:
             return out, dict(ll=ll, kl=kl, mean=mean, var=var)
@@ -228,6 +230,12 @@ class Hybrid_NSF2(nn.Module):
         qF2, pF2 = self.cf.prior.forward_batched(idx)
         return self._combine(qF1, qF2, idx, E, eps, eps2), qF1, qU, pU, qF2, pF2
 
+    def forward_precomputed(self, W, idx, E=10, verbose=False, eps=None, eps2=None, **kwargs):
+        """likelihoods.py:147-163: the spatial prior evaluated from a precomputed W = Kxz Lc^-T (whitened GPs only)."""
+        qF1, qU, pU = self.sf.prior.forward_precomputed(W, verbose=verbose, **kwargs)
+        qF2, pF2 = self.cf.prior.forward_batched(idx)
+        return self._combine(qF1, qF2, idx, E, eps, eps2), qF1, qU, pU, qF2, pF2
+
     def elbo(self, X, y, idx=None, E=1, eps=None, eps2=None, with_lgamma=True, kl_weight=1.0, **kwargs):
         """Fused hybrid ELBO: ll - sum KL(qU||pU) - sum KL(qF2||pF2)   (utilities.py:509-516).
         The L spatial factors enter the likelihood kernel as (mean, variance), the T non-spatial ones as
@@ -250,7 +258,7 @@ class Hybrid_NSF2(nn.Module):
         W = torch.cat((self.sf.W, self.cf.W), dim=1).to(dt)
         ll = F.PoissonLL.apply(y, idx, W, self.V.to(dt), mean, spread, torch.cat((eps, eps2), 1), L, gp.clamp_min,
                                True, with_lgamma)
-        kl = F.MvnKL.apply(m["T"], m["q"], m["Lc"], m["Lu"])
+        kl = F.MvnKL.apply(m["T"], m["q"], m["Lc"], m["Lu"]).to(dt)
         return ll - kl_weight * kl.sum() - distributions.kl_divergence(qF2, pF2).sum()
 
 
@@ -315,5 +323,5 @@ class Hybrid_NSF(NSF):
         ll = F.PoissonLL.apply(y, idx, W, self.V.to(dt), torch.cat((mean1, qF2.loc.to(dt)), 0),
                                torch.cat((var1, qF2.scale.to(dt)), 0), torch.cat((eps, eps2), 1), L, gp.clamp_min, False,
                                with_lgamma)
-        kl = F.MvnKL.apply(m["T"], m["q"], m["Lc"], m["Lu"])
+        kl = F.MvnKL.apply(m["T"], m["q"], m["Lc"], m["Lu"]).to(dt)
         return ll - kl_weight * kl.sum() - distributions.kl_divergence(qF2, pF2).sum()

@@ -72,6 +72,23 @@ def nsf_problem(N=256, M=36, L=3, G=16, D=2, E=1, seed=0, coord_scale=2.0, lengt
     return out
 
 
+def hash_uniform(*shape, salt=0):
+    """Reproducible uniform(-1, 1) array from integer arithmetic only (no RNG stream, no floating-point intermediate), so a
+    fixture too large to commit (the 10 x 1024 x 1024 raw Lu of the config-2-conditioned golden) is regenerated bit-exactly on
+    any machine: three rounds of a 31-bit LCG + xor-shift over sum_d idx_d * prime_d + salt, top 24 bits mapped to [-1, 1)."""
+    primes = (73856093, 19349663, 83492791, 49979687, 86028121)
+    m31 = 1 << 31                                         # every product below stays under 2^62: no int64 wrap-around
+    h = torch.zeros(shape, dtype=torch.int64) + (int(salt) * 1013904223) % m31
+    for d, n in enumerate(shape):
+        view = [1] * len(shape)
+        view[d] = n
+        h = (h + (torch.arange(n, dtype=torch.int64) * primes[d % len(primes)]).view(view)) % m31
+    for mult in (1103515245, 1664525, 22695477):
+        h = (h * mult + 12345) % m31
+        h = h ^ (h >> 15)
+    return (h >> 7).to(torch.float64) / float(1 << 23) - 1.0
+
+
 def regression_problem(N=2000, M=100, D=2, E=20, seed=0, dtype=torch.float64, device="cpu", jitter=1e-3):
     """Config 1: SVGP regression, y = 2 sin(2 x0) cos(x1) + N(0, 0.1^2), X ~ U(-5,5)^D."""
     g = _gen(seed)

@@ -33,6 +33,32 @@ def add_jitter(K, jitter=1e-3):
     return K
 
 
+def reshape_param(param):
+    """(..., a, b) -> (-1, a, b)   (utilities.py:377-380)."""
+    return param.view(-1, param.shape[-2], param.shape[-1])
+
+
+def svgp_forward(Kxx, Kzz, W, inducing_mean, inducing_cov):
+    """mean = W mu (L x N x 1), cov = Kxx + sum_j ((W (S - Kzz)) o W) (L x N)   (utilities.py:382-397), for callers that hold
+    W = Kxz Kzz^-1 (L x N x M) already.  Both contractions run on the library's batched GEMM; the GP modules do not come
+    through here (they use the fused triangular form, csrc/predict.cu, which needs a third of the flops)."""
+    mean = F.matmul(W, inducing_mean.unsqueeze(-1))
+    cov = Kxx + (F.matmul(W, inducing_cov - Kzz) * W).sum(-1)
+    return mean, cov
+
+
+def _squared_dist(X, Z):
+    """Squared Euclidean distances (utilities.py:399-405).  The reference expands |x|^2 - 2 x.z + |z|^2 and clamps the
+    cancellation error at 0; here the differences are formed directly (csrc/kernel_build.cu), so the result is >= 0 by
+    construction and exact for coincident points."""
+    return F.SquaredDist.apply(X, Z)
+
+
+def _torch_sqrt(x, eps=1e-12):
+    """sqrt(x + eps): the NaN-gradient guard of utilities.py:450-456."""
+    return (x + eps).sqrt()
+
+
 def _step(model, optimizer, elbo_fn, clamp_W):
     optimizer.zero_grad(set_to_none=True)
     loss = -elbo_fn()
@@ -88,4 +114,23 @@ def train_hybrid_batched(model, optimizer, X, y, device=None, steps=200, E=20, b
     for _ in range(steps):
         idx = _sample_idx(X.shape[0], batch_size, X.device)
         losses.append(_step(model, optimizer, lambda: model.elbo(X, y, idx=idx, E=E, with_lgamma=False, **kwargs), ws))
+    return _finish(losses)
+
+
+def train_closure_batched(model, optimizer, X, groupsX, y, device=None, steps=200, E=20, batch_size=1000):
+    """Closure-driven minibatch loop of the multi-group models (utilities.py:566-596): `optimizer.step(closure)` with a fresh
+    index set per step, for optimisers that re-evaluate the loss (LBFGS).  The closure runs the fused ELBO; the reference's
+    debugging prints and its per-evaluation `loss.item()` are dropped (losses are fetched once at the end)."""
+    losses = []
+    for _ in range(steps):
+        idx = _sample_idx(X.shape[0], batch_size, X.device)
+
+        def closure(idx=idx):
+            optimizer.zero_grad(set_to_none=True)
+            loss = -model.elbo(X, y, idx=idx, E=E, groupsX=groupsX[idx])
+            loss.backward()
+            losses.append(loss.detach())
+            return loss
+
+        optimizer.step(closure)
     return _finish(losses)

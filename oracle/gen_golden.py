@@ -52,8 +52,82 @@ CASES = {
 }
 
 
+# round 2: fixtures that take the tcgen05 split-FP16 path (predict_h needs M >= 64, N >= 256) and one at the benchmark's
+# conditioning (BASELINE.json configs[1]: M=1024, L=10, G=2000, jitter 0.1, +-100 coordinates, lengthscale 1.7)
+TC_CASES = {
+    "nsf_svgp_tc64": dict(N=512, M=64, L=3, G=24, E=2, seed=1, coord_scale=2.0, jitter=1e-2),
+    "nsf_svgp_tc128": dict(N=1024, M=128, L=3, G=32, E=1, seed=2, coord_scale=2.0, jitter=1e-2),
+    "nsf_svgp_tc256_slideseq": dict(N=2048, M=256, L=4, G=40, E=1, seed=3, coord_scale=100.0, lengthscale=1.7, jitter=1e-1),
+    "nsf_mggp_tc128": dict(N=1024, M=128, L=2, G=16, E=1, seed=4, coord_scale=2.0, jitter=1e-2, n_groups=4),
+}
+CFG2_COND = dict(N=1024, M=1024, L=10, G=2000, E=1, seed=1, coord_scale=100.0, lengthscale=1.7, jitter=1e-1)
+CFG2_LU = dict(scale=0.05, salt=7)          # raw Lu = scale * synthetic.hash_uniform(L, M, M, salt): regenerated, not stored
+CFG2_PROJ = dict(cols=16, salt=11)          # d ELBO / d Lu is stored as its products with hash_uniform(M, cols, salt) (+ factor 0 in full)
+
+
+def cfg2_problem():
+    prob = synthetic.nsf_problem(**CFG2_COND)
+    L, M = prob["mu"].shape
+    prob["Lu_raw"] = CFG2_LU["scale"] * synthetic.hash_uniform(L, M, M, salt=CFG2_LU["salt"])
+    return prob
+
+
+def gen_cfg2():
+    """The benchmark's conditioning at N=1024 spots.  Lu (84 MB) and its gradient are too large to commit: Lu is regenerated
+    from integer hashing, the gradient is stored as two 16-column random projections of every factor plus factor 0 in full."""
+    prob = cfg2_problem()
+    out, grads = ref_runner.run_nsf_svgp(prob)
+    L, M = prob["mu"].shape
+    R = synthetic.hash_uniform(M, CFG2_PROJ["cols"], salt=CFG2_PROJ["salt"])
+    G = grads["Lu_raw"]
+    tri = torch.tril_indices(M, M)
+    blob = dict(in_X=prob["X"], in_Z=prob["Z"], in_y=prob["y"].to(torch.uint8), in_eps=prob["eps"], in_mu=prob["mu"],
+                in_W=prob["W"], in_V=prob["V"], in_sigma=prob["sigma"], in_lengthscale=prob["lengthscale"],
+                in_jitter=torch.tensor(prob["jitter"], dtype=torch.float64), in_lu_scale=torch.tensor(CFG2_LU["scale"], dtype=torch.float64),
+                in_lu_salt=torch.tensor(CFG2_LU["salt"]), in_proj_cols=torch.tensor(CFG2_PROJ["cols"]),
+                in_proj_salt=torch.tensor(CFG2_PROJ["salt"]),
+                proj_Lu_right=G @ R, proj_Lu_left=R.t() @ G, proj_Lu_f0=G[0][tri[0], tri[1]].float(),
+                proj_Lu_norm=G.flatten(1).norm(dim=1), proj_Lu_upper=G.triu(1).abs().max())
+    assert float(prob["y"].max()) < 256
+    for k in ("elbo", "ll", "kl", "mean", "var"):
+        blob["out_" + k] = out[k]
+    for k in ("Z", "sigma", "lengthscale", "mu", "W", "V"):
+        blob["grad_" + k] = grads[k]
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, "nsf_svgp_cfg2cond.npz"), **{k: v.detach().cpu().numpy() for k, v in blob.items()})
+    print("nsf_svgp_cfg2cond elbo=%.12g" % float(out["elbo"]))
+
+
+def gen_round2():
+    ref = load_reference()
+    if "--cfg2-only" in sys.argv:
+        return gen_cfg2()
+    for name, kw in TC_CASES.items():
+        prob = synthetic.nsf_problem(**kw)
+        out, grads = ref_runner.run_nsf_svgp(prob)
+        out.pop("Lu", None), out.pop("Lc", None)
+        save(name, prob, out, grads)
+    gen_cfg2()
+    # VNNGP at config 3's K = 8 (gp.py:19-122)
+    prob = synthetic.nsf_problem(N=192, M=100, L=3, G=12, E=2, seed=32, coord_scale=2.0, jitter=1e-2, lu_scale=0.02)
+    out, grads = ref_runner.run_vnngp(prob, K=8)
+    save("nsf_vnngp_k8", prob, out, grads, K=8)
+    # whitened path (gp.py:260-322, 385-399; utilities.py:27-36): WSVGP / MGGP_WSVGP forward + forward_precomputed, and the ELBO
+    # a user assembles from them (log-lik - sum_l whitened_KL(mu_l, Lu_l)) with its gradients
+    for name, ng in (("wsvgp", 0), ("mggp_wsvgp", 3)):
+        prob = synthetic.nsf_problem(N=96, M=25, L=3, G=10, E=2, seed=61 + ng, coord_scale=2.0, jitter=1e-2, n_groups=ng)
+        out, grads = ref_runner.run_wsvgp(prob)
+        save("nsf_" + name, prob, out, grads)
+    # state_dict keys and shapes of the reference's modules (checkpoint compatibility, SURVEY.md §8(f) row 3)
+    import json
+    json.dump(ref_runner.state_dict_shapes(), open(os.path.join(OUT, "state_dict_shapes.json"), "w"), indent=1, sort_keys=True)
+    print("state_dict_shapes.json written")
+
+
 def main():
     torch.manual_seed(0)
+    if "--round2" in sys.argv:
+        return gen_round2()
     ref = load_reference()
     for name, kw in CASES.items():
         prob = synthetic.nsf_problem(**kw)

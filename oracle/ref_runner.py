@@ -149,3 +149,84 @@ def run_hybrid(prob, extra, idx):
     grads = {k: -v for k, v in _grads(named).items()}
     out = dict(elbo=elbo, ll=ll, kl=kl, kl2=kl2.sum(), mean=qF.mean, var=qF.scale ** 2)
     return {k: v.detach() for k, v in out.items()}, grads
+
+
+def run_wsvgp(prob):
+    """NSF2(WSVGP(NSF_RBF)) or, with groups, NSF2(MGGP_WSVGP(MGGP_NSF_RBF)): forward (gp.py:260-306, 385-399), the ELBO a user
+    assembles with whitened_KL per factor (utilities.py:27-36; pZ is None so kl_divergence is never called), its gradients, and
+    forward_precomputed (gp.py:308-322) on W = Kxz Lc^-T with a batched_RBF-style (L,) sigma."""
+    ref = load_reference()
+    L, M = prob["mu"].shape
+    D = prob["X"].shape[1]
+    dt = prob["X"].dtype
+    mg = "groupsX" in prob
+    if mg:
+        ng = prob["group_distances"].shape[0]
+        kern = ref.kernels.MGGP_NSF_RBF(L=L, n_groups=ng)
+        kern.embedding = nn.Parameter(ref.utilities._embed_distance_matrix(prob["group_distances"].float()).to(dt),
+                                      requires_grad=False)
+        kern.group_diff_param = _p(prob["gdp"])
+        gp = ref.gp.MGGP_WSVGP(kern, dim=D, M=M, n_groups=ng, jitter=prob["jitter"])
+        gp.groupsZ = nn.Parameter(prob["groupsZ"].clone(), requires_grad=False)
+        kw = dict(groupsX=prob["groupsX"])
+    else:
+        kern = ref.kernels.NSF_RBF(L=L)
+        gp = ref.gp.WSVGP(kern, dim=D, M=M, jitter=prob["jitter"])
+        kw = {}
+    kern.sigma, kern.lengthscale = _p(prob["sigma"]), _p(prob["lengthscale"])
+    gp.Z, gp.mu, gp.Lu = _p(prob["Z"]), _p(prob["mu"]), _p(prob["Lu_raw"])
+    model = ref.likelihoods.NSF2(gp, prob["y"], L=L)
+    model.W, model.V = _p(prob["W"]), _p(prob["V"])
+    with fixed_eps(prob["eps"]):
+        pY, qF, qZ, pZ = model(X=prob["X"], E=prob["eps"].shape[0], **kw)
+    assert pZ is None
+    ll = pY.log_prob(prob["y"]).mean(axis=0).sum()
+    kl = torch.stack([ref.utilities.whitened_KL(gp.mu[l], qZ.scale_tril[l]) for l in range(L)])
+    elbo = ll - kl.sum()
+    (-elbo).backward()
+    named = dict(Z=gp.Z, sigma=kern.sigma, lengthscale=kern.lengthscale, mu=gp.mu, Lu_raw=gp.Lu, W=model.W, V=model.V)
+    if mg:
+        named["gdp"] = kern.group_diff_param
+    grads = {k: -v for k, v in _grads(named).items()}
+    out = dict(elbo=elbo, ll=ll, kl=kl, mean=qF.mean, var=qF.scale ** 2, Lu=qZ.scale_tril)
+    with torch.no_grad():
+        Kxx, Kzx, Kzz = gp.forward_kernels(prob["X"], **kw)
+        Lc = torch.linalg.cholesky(ref.utilities.add_jitter(Kzz.clone(), prob["jitter"]))
+        Wp = torch.linalg.solve_triangular(Lc, Kzx, upper=False).transpose(-2, -1).contiguous()          # L x N x M
+        if not mg:
+            kb = ref.kernels.batched_RBF()
+            kb.sigma, kb.lengthscale = _p(prob["sigma"].reshape(-1)), _p(prob["lengthscale"].reshape(-1))
+            gpb = ref.gp.WSVGP(kb, dim=D, M=M, jitter=prob["jitter"])
+            gpb.Z, gpb.mu, gpb.Lu = gp.Z, gp.mu, gp.Lu
+            qFp, _, _ = gpb.forward_precomputed(Wp)
+            out["pre_mean"], out["pre_var"] = qFp.mean, qFp.scale ** 2
+        out["pre_W"] = Wp
+    return {k: v.detach() for k, v in out.items()}, grads
+
+
+def model_zoo(ns, N=12, G=5, M=6, L=3, T=2, ng=3):
+    """One small instance of every model family, built from `ns.kernels / ns.gp / ns.likelihoods` (the reference or gpzoo_b200)
+    with the constructor calls the notebooks use.  Used to compare state_dict keys and shapes."""
+    y = torch.zeros(G, N)
+    k, g, lk = ns.kernels, ns.gp, ns.likelihoods
+    zoo = {
+        "GaussianLikelihood(SVGP(RBF))": lk.GaussianLikelihood(g.SVGP(k.RBF(), dim=2, M=M, jitter=1e-3)),
+        "NSF2(SVGP(NSF_RBF))": lk.NSF2(g.SVGP(k.NSF_RBF(L=L), dim=2, M=M, jitter=1e-1), y, L=L),
+        "NSF2(VNNGP(NSF_RBF))": lk.NSF2(g.VNNGP(k.NSF_RBF(L=L), dim=2, M=M, K=3, jitter=1e-2), y, L=L),
+        "NSF2(MGGP_SVGP(MGGP_NSF_RBF))": lk.NSF2(g.MGGP_SVGP(k.MGGP_NSF_RBF(L=L, n_groups=ng), dim=2, M=M, jitter=1e-1, n_groups=ng), y, L=L),
+        "MGGP_NSF(MGGP_SVGP(MGGP_RBF))": lk.MGGP_NSF(g.MGGP_SVGP(k.MGGP_RBF(n_groups=ng), dim=2, M=M, jitter=1e-1, n_groups=ng), y, L=L),
+        "NSF(SVGP(RBF))": lk.NSF(g.SVGP(k.RBF(), dim=2, M=M), y, L=L),
+        "Hybrid_NSF(SVGP(RBF))": lk.Hybrid_NSF(g.SVGP(k.RBF(), dim=2, M=M), y, L=L),
+        "Hybrid_NSF2(SVGP(NSF_RBF),GaussianPrior)": lk.Hybrid_NSF2(g.SVGP(k.NSF_RBF(L=L), dim=2, M=M), g.GaussianPrior(y, L=T), y, L=L, T=T),
+        "PNMF(GaussianPrior)": lk.PNMF(g.GaussianPrior(y, L=L), y, L=L),
+        "NSF2(WSVGP(NSF_RBF))": lk.NSF2(g.WSVGP(k.NSF_RBF(L=L), dim=2, M=M), y, L=L),
+        "NSF2(MGGP_WSVGP(batched_MGGP_RBF))": lk.NSF2(g.MGGP_WSVGP(k.batched_MGGP_RBF(n_groups=ng), dim=2, M=M, n_groups=ng), y, L=L),
+        "SVGP(batched_RBF)": g.SVGP(k.batched_RBF(), dim=2, M=M),
+        "SVGP(batched_Matern32)": g.SVGP(k.batched_Matern32(), dim=2, M=M),
+    }
+    return zoo
+
+
+def state_dict_shapes(ns=None):
+    ns = load_reference() if ns is None else ns
+    return {name: {key: list(v.shape) for key, v in m.state_dict().items()} for name, m in model_zoo(ns).items()}

@@ -64,3 +64,47 @@ def test_abi_version_and_new_entry_points(lib):
     rows = [lib.gpz_svgp_predict_h_stat_row(i) for i in range(5)]
     assert len(set(rows)) == 5 and min(rows) >= 0                       # five distinct rows of the stats block
     assert lib.gpz_svgp_predict_h_stat_row(99) == -1
+
+
+def test_state_dict_keys_and_shapes_match_reference():
+    """Every model family has the reference's state_dict keys and shapes (golden written from the unmodified reference by
+    oracle/gen_golden.py; compared live as well when /root/reference is present).  Module construction needs no GPU."""
+    import json
+    import os
+    import types
+    import gpzoo_b200 as gz
+    from oracle import ref_loader, ref_runner
+    from tests.helpers import GOLDEN
+    golden = json.load(open(os.path.join(GOLDEN, "state_dict_shapes.json")))
+    ours = ref_runner.state_dict_shapes(types.SimpleNamespace(kernels=gz.kernels, gp=gz.gp, likelihoods=gz.likelihoods))
+    assert set(ours) == set(golden)
+    for name in golden:
+        assert ours[name] == golden[name], (name, ours[name], golden[name])
+    if ref_loader.available():
+        assert ref_runner.state_dict_shapes() == golden
+
+
+def test_reference_utility_names_importable():
+    """`from gpzoo.utilities import ...` of every hot-path name keeps working after install_as_gpzoo()."""
+    import sys
+    import gpzoo_b200 as gz
+    saved = {k: v for k, v in sys.modules.items() if k == "gpzoo" or k.startswith("gpzoo.")}
+    gz.install_as_gpzoo()
+    try:
+        _check_reference_names()
+    finally:                                  # other tests import the real reference under the same name
+        for k in [k for k in sys.modules if k == "gpzoo" or k.startswith("gpzoo.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+def _check_reference_names():
+    from gpzoo.utilities import (_embed_distance_matrix, _squared_dist, _torch_sqrt, add_jitter, reshape_param, svgp_forward,  # noqa: F401
+                                 train, train_batched, train_closure_batched, train_hybrid, train_hybrid_batched, whitened_KL)
+    from gpzoo.gp import MGGP_WSVGP, WSVGP
+    from gpzoo.likelihoods import Hybrid_NSF2
+    assert hasattr(WSVGP, "forward_precomputed") and hasattr(MGGP_WSVGP, "forward_precomputed")
+    assert hasattr(Hybrid_NSF2, "forward_precomputed")
+    import torch
+    assert reshape_param(torch.zeros(2, 3, 4, 5)).shape == (6, 4, 5)
+    assert abs(float(_torch_sqrt(torch.zeros((), dtype=torch.float64), 1e-6)) - 1e-3) < 1e-15

@@ -471,3 +471,59 @@ def test_gemm_split_fp16_route(monkeypatch):
     ref = C0.double() - Lo.double() @ Lo.double().transpose(1, 2)
     assert relerr(torch.tril(acc), torch.tril(ref)) < 5e-6
     assert torch.equal(torch.triu(acc, 1).cpu(), torch.triu(C0, 1))
+
+
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_utilities_svgp_forward_and_squared_dist(dt):
+    """utilities.svgp_forward (utilities.py:382-397) and _squared_dist (:399-405) on the library's kernels against the oracle's
+    restatement, values and gradients."""
+    import gpzoo_b200 as gz
+    from oracle import gpzoo_oracle as O
+    g = torch.Generator().manual_seed(5)
+    L, N, M = 3, 70, 20
+    mk = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64)
+    Kxx, W, mu = mk(L, N).abs() + 2, 0.3 * mk(L, N, M), mk(L, M)
+    A, B = mk(L, M, M), mk(L, M, M)
+    S, Kzz = A @ A.transpose(-1, -2) / M, B @ B.transpose(-1, -2) / M
+    ref_in = [t.clone().requires_grad_(True) for t in (Kxx, Kzz, W, mu, S)]
+    rm, rc = O.svgp_forward(*ref_in)
+    (rm.sum() + (rc ** 2).sum()).backward()
+    our_in = [t.to(DEV, dt).requires_grad_(True) for t in (Kxx, Kzz, W, mu, S)]
+    m, c = gz.utilities.svgp_forward(*our_in)
+    assert m.shape == (L, N, 1) and c.shape == (L, N)
+    (m.sum() + (c ** 2).sum()).backward()
+    tol = 1e-10 if dt == torch.float64 else 1e-4
+    assert relerr(m, rm) < tol and relerr(c, rc) < tol
+    for a, b in zip(our_in, ref_in):
+        assert relerr(a.grad, b.grad) < tol
+    X, Z = mk(40, 2), mk(17, 2)
+    Xr, Zr = X.clone().requires_grad_(True), Z.clone().requires_grad_(True)
+    wgt = mk(40, 17)
+    (O.squared_dist(Xr, Zr) * wgt).sum().backward()
+    Xo, Zo = X.to(DEV, dt).requires_grad_(True), Z.to(DEV, dt).requires_grad_(True)
+    d2 = gz.utilities._squared_dist(Xo, Zo)
+    (d2 * wgt.to(DEV, dt)).sum().backward()
+    assert relerr(d2, O.squared_dist(X, Z)) < tol and relerr(Xo.grad, Xr.grad) < tol and relerr(Zo.grad, Zr.grad) < tol
+    assert float(gz.utilities._squared_dist(Xo.detach(), Xo.detach()).diagonal().abs().max()) == 0.0
+
+
+def test_kernel_build_rejects_mismatched_arguments():
+    """The C ABI takes raw pointers, so the Python boundary refuses what the kernels would misread: a float32 Z with float64 X,
+    group labels outside [0, n_groups), and a Matern kernel under VNNGP (whose fused neighbour kernel evaluates the RBF)."""
+    import gpzoo_b200 as gz
+    from gpzoo_b200 import _cabi
+    X = torch.rand(32, 2, dtype=torch.float64, device=DEV)
+    Z = torch.rand(8, 2, dtype=torch.float32, device=DEV)
+    k = gz.kernels.NSF_RBF(L=2).to(DEV)
+    with pytest.raises(_cabi.GpzError):
+        k(X, Z)
+    mk = gz.kernels.MGGP_NSF_RBF(L=2, n_groups=3).to(DEV)
+    gX = torch.randint(0, 3, (32,), device=DEV)
+    gZ = torch.tensor([0, 1, 2, 3, 0, 1, 2, 0], device=DEV)                    # 3 is out of range
+    with pytest.raises(IndexError):
+        mk(X, Z.double(), gX, gZ)
+    out = mk(X, Z.double(), gX.int(), (gZ % 3).int())                           # int32 labels are converted, not reinterpreted
+    assert out.shape == (2, 32, 8)
+    v = gz.gp.VNNGP(gz.kernels.batched_Matern32(), dim=2, M=8, K=3).to(DEV).double()
+    with pytest.raises(NotImplementedError):
+        v(X)
