@@ -728,6 +728,9 @@ static int chol_inv_tc(float* W, float* Lc, float* X, float* tmp, float* lo_ws, 
   GPZ_CUDA(cudaMemsetAsync(Lc, 0, sizeof(float) * tot, st));
   GPZ_CUDA(cudaMemsetAsync(X, 0, sizeof(float) * tot, st));
   float* Wlo = lo_ws; float* Llo = lo_ws + tot; float* Xlo = lo_ws + 2 * tot; float* Tlo = lo_ws + 3 * tot;
+  // the triangular GEMMs read whole k-blocks of Lc / X, i.e. also entries above the diagonal of a diagonal block's row: those
+  // are zero in Lc / X (memset above) and must be zero in their lo planes too (only the lower blocks are ever written)
+  GPZ_CUDA(cudaMemsetAsync(Llo, 0, sizeof(float) * 2 * tot, st));
   int rc = gpz_tf32_lo_f32(W, Wlo, tot, (void*)st);
   if (rc) return rc;
   return chol_inv_rec_tc(W, Lc, X, tmp, Wlo, Llo, Xlo, Tlo, M, L, 0, M, info, st);

@@ -627,8 +627,9 @@ def test_state_dict_load_from_reference_layout():
     # notebooks overwrite the scalar-GP parameters with L-batched ones before saving; do the same before loading
     model.prior.mu = torch.nn.Parameter(torch.zeros(L, M))
     model.prior.Lu = torch.nn.Parameter(torch.zeros(L, M, M))
+    model = model.double()                    # (load_state_dict copies into the existing parameters' dtype)
     model.load_state_dict(ckpt, strict=True)
-    model = model.to(DEV).double()
+    model = model.to(DEV)
     elbo = model.elbo(inp["X"].to(DEV), inp["y"].to(DEV), E=inp["eps"].shape[0], eps=inp["eps"].to(DEV))
     assert relerr(elbo, gout["elbo"]) < 1e-10
     again = {k: v.cpu() for k, v in model.state_dict().items()}
