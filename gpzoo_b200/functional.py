@@ -26,6 +26,7 @@ USE_TENSOR_CORES = True      # fp32: route large contractions through the tcgen0
 TENSOR_CORE_ARITH = os.environ.get("GPZ_TC_ARITH", "fp16x3")
 # fp32 models: up to this many inducing points the O(M^3) chain runs in fp64 (gp.py `_chain_dtype`); GPZ_CHAIN_FP64_MAX_M=0 turns it off
 CHAIN_FP64_MAX_M = int(os.environ.get("GPZ_CHAIN_FP64_MAX_M", "256"))
+FUSED_CHAIN = os.environ.get("GPZ_FUSED_CHAIN", "1") != "0"       # csrc/chain.cu instead of the Function-per-op chain
 CHOL_TC_MIN_M = 1536         # above this size the fp32 Cholesky + inverse runs its O(M^3) products on the tensor cores
 _pending_info = []
 # build Kzx on a side stream, concurrently with the Cholesky chain of Kzz (gp.py moments); GPZ_OVERLAP=0 turns it off
@@ -400,6 +401,60 @@ class CholeskyInverse(Function):
         t1 = gemm(Linv, P, ta=True, a_tri=2, b_tri=1)                          # Linv^T Phi
         t2 = gemm(t1, Linv, b_tri=1)                                           # ... Linv
         return tri_op(t2, 1)                                                   # symmetrise
+
+
+def chain_ok(dtype, M):
+    """fp32 chains large enough for the fused two-call implementation (csrc/chain.cu)."""
+    return (USE_TENSOR_CORES and FUSED_CHAIN and dtype == torch.float32
+            and bool(_cabi.lib().gpz_svgp_chain_supported(c_i(int(M)))))
+
+
+class SvgpChain(Function):
+    """Everything between the jittered Kzz and the whitened operands of the predictive kernels, as ONE forward and ONE backward
+    C-ABI call (csrc/chain.cu): (Lc, Linv) = chol_inv(Kzz), Lu = lower_cholesky(raw), T = Linv Lu, q = Linv mu and
+    kl = KL(N(mu, Lu Lu^T) || N(0, Lc Lc^T)) per factor.  Replaces CholeskyInverse + LowerCholesky + Whiten + MvnKL (and the
+    ATen gradient accumulation between them) for fp32 models with M >= 128.  `consume`: Kzz may be overwritten."""
+
+    @staticmethod
+    def forward(ctx, Kzz, Lu_raw, mu, consume):
+        L, M, _ = Kzz.shape
+        dt = Kzz.dtype
+        dev = Kzz.device
+        W = _c(Kzz.detach())
+        if W.data_ptr() == Kzz.data_ptr() and not consume:
+            W = W.clone()
+        Lu_raw, mu = _c(Lu_raw.detach()), _c(mu.detach())
+        chol_tc = int(M > CHOL_TC_MIN_M)
+        Lc, Linv, Lu, T = (torch.empty((L, M, M), dtype=dt, device=dev) for _ in range(4))
+        q = torch.empty((L, M), dtype=dt, device=dev)
+        kl = torch.empty(L, dtype=dt, device=dev)
+        aux = torch.empty((6, L, M, M), dtype=dt, device=dev)
+        ws = torch.empty(((5 if chol_tc else 1) * L * M * M + 4 * L,), dtype=dt, device=dev)
+        info = torch.empty(L, dtype=torch.int32, device=dev)
+        call("svgp_chain_fwd", dt, ptr(W), ptr(Lu_raw), ptr(mu), ptr(Lc), ptr(Linv), ptr(Lu), ptr(T), ptr(q), ptr(kl), ptr(aux),
+             ptr(ws), c_i(M), c_i(L), c_i(chol_tc), ptr(info))
+        _pending_info.append(info)
+        if SYNC_CHECKS:
+            check_cholesky_info()
+        ctx.save_for_backward(Lc, Linv, Lu, T, q, mu, aux)
+        ctx.set_materialize_grads(False)
+        return Lc, Linv, Lu, T, q, kl
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gLc, gLinv, gLu, gT, gq, gkl):
+        Lc, Linv, Lu, T, q, mu, aux = ctx.saved_tensors
+        L, M, _ = Lc.shape
+        dt, dev = Lc.dtype, Lc.device
+        cc = lambda t: None if t is None else _c(t)
+        gLc, gLinv, gLu, gT, gq, gkl = cc(gLc), cc(gLinv), cc(gLu), cc(gT), cc(gq), cc(gkl)
+        gKzz = torch.empty((L, M, M), dtype=dt, device=dev)
+        gLu_raw = torch.empty_like(gKzz)
+        gmu = torch.empty((L, M), dtype=dt, device=dev)
+        ws = torch.empty((12 * L * M * M + 2 * L * M,), dtype=dt, device=dev)
+        call("svgp_chain_bwd", dt, ptr(Lc), ptr(Linv), ptr(Lu), ptr(T), ptr(q), ptr(mu), ptr(aux), ptr(gLc), ptr(gLinv), ptr(gLu),
+             ptr(gT), ptr(gq), ptr(gkl), ptr(gKzz), ptr(gLu_raw), ptr(gmu), ptr(ws), c_i(M), c_i(L))
+        return gKzz, gLu_raw, gmu, None
 
 
 class LowerCholesky(Function):

@@ -25,7 +25,7 @@ class VariationalMVN(distributions.MultivariateNormal):
 
     def __init__(self, loc, scale_tril, gpz_state):
         super().__init__(loc, scale_tril=scale_tril, validate_args=False)
-        self._gpz_state = gpz_state          # (T, q, Lc, Lu) L-batched tensors, batched flag
+        self._gpz_state = gpz_state          # (T, q, Lc, Lu) L-batched tensors, batched flag, per-factor KL if already computed
 
 
 class PriorMVN(distributions.MultivariateNormal):
@@ -37,8 +37,8 @@ class PriorMVN(distributions.MultivariateNormal):
 
 @register_kl(VariationalMVN, PriorMVN)
 def _kl_variational_prior(qU, pU):
-    T, q, Lc, Lu, batched = qU._gpz_state
-    kl = F.MvnKL.apply(T, q, Lc, Lu).to(qU.loc.dtype)
+    T, q, Lc, Lu, batched, kl = qU._gpz_state
+    kl = (kl if kl is not None else F.MvnKL.apply(T, q, Lc, Lu)).to(qU.loc.dtype)
     return kl if batched else kl[0]
 
 
@@ -78,12 +78,19 @@ class _SparseGPBase(nn.Module):
                 Kzz = self.kernel(self.Z, self.Z, _jitter=self.jitter)
         return Kxx, Kzx, Kzz
 
-    def _whitened(self, Kzz):
-        """Lc, Linv, Lu, T, q with a common leading L."""
+    def _whitened(self, Kzz, consume=False):
+        """Lc, Linv, Lu, T, q with a common leading L.  consume: Kzz is a temporary of the caller and may be overwritten.
+        Leaves the per-factor KL in `self._chain_kl` when the fused chain computed it (None otherwise)."""
         Kzz = _as3(Kzz)
         mu = self.mu if self.mu.dim() == 2 else self.mu.unsqueeze(0)
         Lu_raw = _as3(self.Lu)
         L = max(Kzz.shape[0], mu.shape[0], Lu_raw.shape[0])
+        self._chain_kl = None
+        if Kzz.shape[0] == L and F.chain_ok(Kzz.dtype, Kzz.shape[-1]):
+            ex = lambda t: t if t.shape[0] == L else t.expand(L, *t.shape[1:])
+            Lc, Linv, Lu, T, q, kl = F.SvgpChain.apply(Kzz, ex(Lu_raw.to(Kzz.dtype)), ex(mu.to(Kzz.dtype)), bool(consume))
+            self._chain_kl = kl
+            return Lc, Linv, Lu, T, q, L
         Lc, Linv = F.CholeskyInverse.apply(Kzz)
         if Lc.shape[0] != L:
             Lc, Linv = Lc.expand(L, -1, -1), Linv.expand(L, -1, -1)
@@ -132,13 +139,15 @@ class _SparseGPBase(nn.Module):
             side = F.side_stream(X.device)
             with F.launch_on(side):
                 Kxx, Kzx, _ = self._kernel_matrices(X, groupsX, want_lo, want_h, skip_kzz=True)
-            Lc, Linv, Lu, T, q, L = self._whitened(self._kzz(X, groupsX, cdt))
+            Lc, Linv, Lu, T, q, L = self._whitened(self._kzz(X, groupsX, cdt), consume=True)
             torch.cuda.current_stream().wait_stream(side)
         else:
             Kxx, Kzx, _ = self._kernel_matrices(X, groupsX, want_lo, want_h, skip_kzz=True)
-            Lc, Linv, Lu, T, q, L = self._whitened(self._kzz(X, groupsX, cdt))
+            Lc, Linv, Lu, T, q, L = self._whitened(self._kzz(X, groupsX, cdt), consume=True)
         chain = (Lc, Linv, Lu, T, q, L)
         out = dict(T=T, q=q, Lc=Lc, Lu=Lu, _chain=chain)
+        if _chain is None and getattr(self, "_chain_kl", None) is not None:
+            out["kl"] = self._chain_kl                  # per-factor KL(qU || pU), already computed by the fused chain
         Linv, T, q = Linv.to(dt), T.to(dt), q.to(dt)            # the N-proportional kernels run in the model's dtype
         Kxx = Kxx if Kxx.dim() == 2 else Kxx.unsqueeze(0)
         if Kxx.shape[0] != L:
@@ -189,7 +198,7 @@ class _SparseGPBase(nn.Module):
         Lu, Lc = Lu.to(mean.dtype), Lc.to(mean.dtype)            # (the KL below still uses the chain's own precision)
         qF = distributions.Normal(mean, torch.clamp(var, min=self.clamp_min) ** 0.5, validate_args=False)
         mu = self.mu.to(Lu.dtype)
-        qU = VariationalMVN(mu, Lu, (m["T"], m["q"], m["Lc"], m["Lu"], b))
+        qU = VariationalMVN(mu, Lu, (m["T"], m["q"], m["Lc"], m["Lu"], b, m.get("kl")))
         pU = PriorMVN(torch.zeros_like(mu), Lc)
         return qF, qU, pU
 
@@ -256,7 +265,8 @@ class WSVGP(_SparseGPBase):
     def forward_kernels(self, X, **args):
         return self._kernel_matrices(X, args.get("groupsX"))
 
-    def _whitened(self, Kzz):
+    def _whitened(self, Kzz, consume=False):
+        self._chain_kl = None
         Kzz = _as3(Kzz)
         mu = self.mu if self.mu.dim() == 2 else self.mu.unsqueeze(0)
         Lu_raw = _as3(self.Lu)

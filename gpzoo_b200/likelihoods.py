@@ -25,6 +25,11 @@ def _sample(qF, E, eps=None):
     return qF.loc + eps * qF.scale
 
 
+def _kl_of(m):
+    """Per-factor KL(qU || pU) of a `moments` result: the fused chain's own output when it ran, else the KL kernel."""
+    return m["kl"] if m.get("kl") is not None else F.MvnKL.apply(m["T"], m["q"], m["Lc"], m["Lu"])
+
+
 def _gp_call(gp, X, verbose, kwargs):
     # keywords, as the reference calls its priors (likelihoods.py:81, 111): MGGP_SVGP.forward(X, groupsX, verbose) and
     # MGGP_WSVGP.forward(X, verbose, **args) both take groupsX by name
@@ -118,7 +123,7 @@ class _FusedPoissonMixin:
         W = self.W.to(mean.dtype)
         ll = F.PoissonLL.apply(y, idx, W, self.V.to(mean.dtype), mean, var, eps, mean.shape[0], gp.clamp_min,
                                self._w_softplus, with_lgamma)
-        kl = F.MvnKL.apply(m["T"], m["q"], m["Lc"], m["Lu"]).to(mean.dtype)
+        kl = _kl_of(m).to(mean.dtype)
         out = ll - kl_weight * kl.sum()
         if return_parts:
             return out, dict(ll=ll, kl=kl, mean=mean, var=var)
@@ -258,7 +263,7 @@ class Hybrid_NSF2(nn.Module):
         W = torch.cat((self.sf.W, self.cf.W), dim=1).to(dt)
         ll = F.PoissonLL.apply(y, idx, W, self.V.to(dt), mean, spread, torch.cat((eps, eps2), 1), L, gp.clamp_min,
                                True, with_lgamma)
-        kl = F.MvnKL.apply(m["T"], m["q"], m["Lc"], m["Lu"]).to(dt)
+        kl = _kl_of(m).to(dt)
         return ll - kl_weight * kl.sum() - distributions.kl_divergence(qF2, pF2).sum()
 
 
@@ -323,5 +328,5 @@ class Hybrid_NSF(NSF):
         ll = F.PoissonLL.apply(y, idx, W, self.V.to(dt), torch.cat((mean1, qF2.loc.to(dt)), 0),
                                torch.cat((var1, qF2.scale.to(dt)), 0), torch.cat((eps, eps2), 1), L, gp.clamp_min, False,
                                with_lgamma)
-        kl = F.MvnKL.apply(m["T"], m["q"], m["Lc"], m["Lu"]).to(dt)
+        kl = _kl_of(m).to(dt)
         return ll - kl_weight * kl.sum() - distributions.kl_divergence(qF2, pF2).sum()

@@ -83,6 +83,21 @@ int gpz_gemm_f64(int ta, int tb, int m, int n, int k, double alpha, const double
  * trans == 0: out[l,i] = sum_k A[l,i,k] v[l,k];  trans != 0: out[l,j] = sum_k A[l,k,j] v[l,k];  A is L x rows x cols */
 int gpz_gemv_f32(int trans, const float* A, const float* v, float* out, int rows, int cols, int L, void* stream);
 int gpz_gemv_f64(int trans, const double* A, const double* v, double* out, int rows, int cols, int L, void* stream);
+/* The whole O(M^3) chain of one SVGP step in two calls (fp32, M >= 128, M % 4 == 0; csrc/chain.cu).  Replaces gp.py:208-221
+ * (add_jitter is fused upstream, torch.linalg.cholesky, transform_to(lower_cholesky)), the solve_triangular calls inside
+ * kl_divergence(qU, pU) (utilities.py:481,616 -> torch kl.py) and the autograd of all of them.
+ *   fwd: Kzz (L x M x M, jittered, DESTROYED) -> Lc, Linv = Lc^-1, Lu, T = Linv Lu, q = Linv mu, kl[L];
+ *        aux: 6 L M M floats kept for the backward; ws: L M M floats (5 L M M with chol_tc != 0) scratch; info[L] as LAPACK.
+ *   bwd: incoming gradients of (Lc, Linv, Lu, T, q, kl) (any may be NULL; triangular ones are read in their lower triangle)
+ *        -> gKzz (L x M x M, NOT symmetrised: contract it with a symmetric dKzz), gLu_raw, gmu; ws: 12 L M M + 2 L M floats. */
+int gpz_svgp_chain_supported(int M);
+int gpz_svgp_chain_fwd_f32(float* Kzz, const float* Lu_raw, const float* mu, float* Lc, float* Linv, float* Lu, float* T, float* q,
+                           float* kl, float* aux, float* ws, int M, int L, int chol_tc, int* info, void* stream);
+int gpz_svgp_chain_bwd_f32(const float* Lc, const float* Linv, const float* Lu, const float* T, const float* q, const float* mu,
+                           const float* aux, const float* gLc_in, const float* gLinv_in, const float* gLu_in, const float* gT_in,
+                           const float* gq_in, const float* gkl_in, float* gKzz, float* gLu_raw, float* gmu, float* ws, int M,
+                           int L, void* stream);
+
 /* gp.py:220 transform_to(lower_cholesky): out = tril(raw,-1) + diag(exp(diag raw)), and its backward */
 int gpz_lower_cholesky_fwd_f32(const float* raw, float* out, int M, int L, void* stream);
 int gpz_lower_cholesky_fwd_f64(const double* raw, double* out, int M, int L, void* stream);

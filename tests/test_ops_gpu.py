@@ -527,3 +527,57 @@ def test_kernel_build_rejects_mismatched_arguments():
     v = gz.gp.VNNGP(gz.kernels.batched_Matern32(), dim=2, M=8, K=3).to(DEV).double()
     with pytest.raises(NotImplementedError):
         v(X)
+
+
+@pytest.mark.parametrize("M", [128, 320, 1024, 1600])
+def test_fused_chain_matches_generic_fp64(M):
+    """csrc/chain.cu (one forward + one backward call, tcgen05 split-TF32 M^3 products) against the Function-per-op chain in
+    fp64: every output and, for random incoming gradients of every output, every input gradient.  gKzz is compared after
+    symmetrisation (the fused chain returns the un-symmetrised representative)."""
+    from gpzoo_b200 import functional as F
+    g = torch.Generator().manual_seed(M)
+    L = 3
+    Q = torch.randn(L, M, M, generator=g, dtype=torch.float64)
+    K = (Q @ Q.transpose(1, 2) / M + torch.eye(M, dtype=torch.float64)).to(DEV)
+    raw = (0.3 * torch.randn(L, M, M, generator=g, dtype=torch.float64)).to(DEV)
+    mu = torch.randn(L, M, generator=g, dtype=torch.float64).to(DEV)
+    w = [torch.randn(L, M, M, generator=g, dtype=torch.float64).tril().to(DEV) for _ in range(4)]
+    wq, wk = torch.randn(L, M, generator=g, dtype=torch.float64).to(DEV), torch.randn(L, generator=g, dtype=torch.float64).to(DEV)
+
+    def loss(Lc, Linv, Lu, T, q, kl, dt):
+        c = lambda t: t.to(dt)
+        return ((Lc * c(w[0])).sum() + (Linv * c(w[1])).sum() + (Lu * c(w[2])).sum() + (T * c(w[3])).sum() + (q * c(wq)).sum()
+                + (kl * c(wk)).sum())
+    # generic fp64
+    K64, r64, m64 = (t.clone().requires_grad_(True) for t in (K, raw, mu))
+    Lc, Linv = F.CholeskyInverse.apply(K64)
+    Lu = F.LowerCholesky.apply(r64)
+    T, q = F.Whiten.apply(Linv, Lu, m64)
+    kl = F.MvnKL.apply(T, q, Lc, Lu)
+    ref = (Lc, Linv, Lu, T, q, kl)
+    loss(*ref, torch.float64).backward()
+    # fused fp32
+    assert F.chain_ok(torch.float32, M)
+    K32, r32, m32 = (t.float().requires_grad_(True) for t in (K, raw, mu))
+    out = F.SvgpChain.apply(K32, r32, m32, False)
+    loss(*out, torch.float32).backward()
+    for name, a, b in zip(("Lc", "Linv", "Lu", "T", "q", "kl"), out, ref):
+        assert relerr(a, b) < 2e-5, (name, relerr(a, b))
+    sym = lambda t: 0.5 * (t + t.transpose(1, 2))
+    assert relerr(sym(K32.grad), sym(K64.grad)) < 1e-4, relerr(sym(K32.grad), sym(K64.grad))
+    assert relerr(r32.grad, r64.grad) < 1e-4 and relerr(m32.grad, m64.grad) < 1e-4
+    assert torch.equal(K32.detach(), K.float())                                 # consume=False: the input survives
+    assert torch.equal(r32.grad.triu(1), torch.zeros_like(r32.grad))
+    # partial incoming gradients (None for the rest) and a second backward over the same graph
+    K32b = K.float().requires_grad_(True)
+    o2 = F.SvgpChain.apply(K32b, raw.float(), mu.float(), False)
+    o2[5].sum().backward(retain_graph=True)
+    g1 = K32b.grad.clone()
+    K32b.grad = None
+    o2[5].sum().backward()
+    assert relerr(K32b.grad, g1) < 1e-6
+    K64b = K.clone().requires_grad_(True)
+    Lcb, Linvb = F.CholeskyInverse.apply(K64b)
+    Tb, qb = F.Whiten.apply(Linvb, F.LowerCholesky.apply(raw), mu)
+    F.MvnKL.apply(Tb, qb, Lcb, F.LowerCholesky.apply(raw)).sum().backward()
+    assert relerr(sym(g1), sym(K64b.grad)) < 1e-4

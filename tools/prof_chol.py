@@ -1,11 +1,49 @@
-import sys, torch
+"""Cholesky + inverse timing at the benchmark size: cluster kernel (with its phase clocks) vs the tensor-core recursion,
+for L = 10 factors and for the 1-2 factors a rank would own if the chain were sharded by factor."""
+import ctypes, sys, torch
 sys.path.insert(0, '.')
-from gpzoo_b200 import functional as F
+from gpzoo_b200 import functional as F, _cabi
 F.set_sync_checks(False)
 torch.manual_seed(0)
-L, M = 10, 1024
-Q = torch.randn(L, M, M, device='cuda')
-K = Q @ Q.transpose(1, 2) / M + torch.eye(M, device='cuda')
-for _ in range(3):
-    Lc, Linv = F.CholeskyInverse.apply(K)
-torch.cuda.synchronize()
+
+
+def timeit(fn, n=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+for M in [int(a) for a in sys.argv[1:]] or [1024]:
+    for L in (10, 2, 1):
+        Q = torch.randn(L, M, M, device='cuda')
+        K = Q @ Q.transpose(1, 2) / M + torch.eye(M, device='cuda')
+        ref = torch.linalg.cholesky(K.double())
+        out = {}
+        for name, thr in (("cluster", 1 << 30), ("tc", 0)):
+            F.CHOL_TC_MIN_M = thr
+            if name == "cluster" and M > 1536:
+                continue
+            t = timeit(lambda: F.CholeskyInverse.apply(K))
+            Lc, Linv = F.CholeskyInverse.apply(K)
+            err = float((Lc.double() - ref).norm() / ref.norm())
+            erri = float((Linv.double() @ ref - torch.eye(M, device='cuda', dtype=torch.float64)).norm() / M ** 0.5)
+            out[name] = (t, err, erri)
+        tt = timeit(lambda: torch.linalg.cholesky(K))
+        line = f"M={M} L={L}: " + "  ".join(f"{k} {v[0]:.3f} ms (Lc err {v[1]:.1e}, |Linv Lc - I| {v[2]:.1e})" for k, v in out.items())
+        print(line + f"  torch.linalg.cholesky alone {tt:.3f} ms")
+    if M <= 1536:
+        F.CHOL_TC_MIN_M = 1 << 30
+        dbg = torch.zeros(4, dtype=torch.int64, device='cuda')
+        _cabi.lib().gpz_chol_debug_(ctypes.c_void_p(dbg.data_ptr()))
+        F.CholeskyInverse.apply(K)
+        torch.cuda.synchronize()
+        _cabi.lib().gpz_chol_debug_(ctypes.c_void_p(0))
+        c = dbg.cpu().tolist()
+        print(f"  cluster phases (clock64 of CTA 0, L={L}): leaf {c[0]} panel {c[1]} trail+leaf {c[2]} inverse {c[3]}  total {sum(c)}")
