@@ -47,3 +47,17 @@ for M in [int(a) for a in sys.argv[1:]] or [1024]:
         _cabi.lib().gpz_chol_debug_(ctypes.c_void_p(0))
         c = dbg.cpu().tolist()
         print(f"  cluster phases (clock64 of CTA 0, L={L}): leaf {c[0]} panel {c[1]} trail+leaf {c[2]} inverse {c[3]}  total {sum(c)}")
+
+# does the time depend on the VALUES?  config 2's Kzz is 1.1 I plus mostly tiny (many denormal) entries
+from gpzoo_b200 import synthetic
+import gpzoo_b200 as gz
+pr = synthetic.nsf_problem(N=64, M=1024, L=10, G=4, E=1, seed=1, coord_scale=100.0, lengthscale=1.7, jitter=1e-1, dtype=torch.float32, device='cuda')
+kern = gz.kernels.NSF_RBF(L=10)
+kern.sigma, kern.lengthscale = torch.nn.Parameter(pr["sigma"]), torch.nn.Parameter(pr["lengthscale"])
+with torch.no_grad():
+    Kzz = kern(pr["Z"], pr["Z"], _jitter=0.1)
+F.CHOL_TC_MIN_M = 1 << 30
+den = float(((Kzz != 0) & (Kzz.abs() < 1.2e-38)).float().mean())
+print(f"config-2 Kzz: cluster {timeit(lambda: F.CholeskyInverse.apply(Kzz)):.3f} ms   (fraction of denormal entries {den:.3f}, zeros {float((Kzz == 0).float().mean()):.3f})")
+Kz2 = torch.where(Kzz.abs() < 1e-30, torch.zeros_like(Kzz), Kzz)
+print(f"config-2 Kzz, tiny entries flushed to 0: cluster {timeit(lambda: F.CholeskyInverse.apply(Kz2)):.3f} ms")
