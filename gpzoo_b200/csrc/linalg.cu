@@ -10,6 +10,7 @@
 #include <cooperative_groups.h>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "gemm_simt.cuh"
 #include "gpzoo_b200.h"
@@ -172,128 +173,166 @@ template <typename T> int trtri(const T* Lc, T* X, T* tmp, int M, int L, cudaStr
 // (Lc, X = Lc^-1) by divide and conquer: for A = [A11 .; A21 A22]
 //     (L11, X11) = rec(A11);  L21 = A21 X11^T;  A22 -= L21 L21^T;  (L22, X22) = rec(A22);  X21 = -X22 (L21 X11)
 // so all O(M^3) work is GEMMs (4 per internal node) and the only sequential kernel is the 64 x 64 leaf below, which
-// factors AND inverts its block in shared memory with 16-wide sub-blocking (a dozen block barriers instead of 128).
-// Factor and invert the n x n (n <= 64) diagonal block at (r0, r0) of one factor: W (input, lower), Lm and X (outputs).
-// `a`, `x`: two [NB][NB+1] shared-memory tiles.  256 threads; contains block barriers.
+// factors AND inverts its block.
+// Factor and invert the n x n (n <= 64) diagonal block at (r0, r0) of one factor: W (input, lower), Lm and X (outputs), all with
+// row stride ld.  `a`, `x`: two [NB][NB+1] shared-memory tiles.  256 threads; contains block barriers.
+//
+// The 64 x 64 block is handled as 2 x 2 blocks of 32: each 32 x 32 diagonal block is factored AND inverted by ONE warp entirely
+// in registers (lane = row, the pivot column travels by shuffles; no shared memory and no barrier inside the 32 columns), the
+// three 32^3 products between them (L21 = A21 X11^T, A22 -= L21 L21^T, X21 = -X22 L21 X11) are spread over all 8 warps.
+// This is the serial part of the whole Cholesky (16 leaves at M = 1024), so its latency is what matters, not its flops.
+template <typename T> __device__ __forceinline__ T shfl_t(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// A 32 x 32 diagonal block is FACTORED by one warp in registers (lane = row) and INVERTED by all eight warps (4 columns each).
+// In: a[k] = A[lane][k] (only k <= lane matters).  Rolled loops whose bodies have only compile-time register indices (a fully
+// unrolled version is 20 000 instructions of straight-line code that runs once and was bound by instruction fetch):
+// the remaining part of the row lives at a[0..31-j]; the update writes entry k into slot k-1, so the active column is always
+// slot 0 and the pivot is lane j's slot 0 (slots past the end of the row carry harmless garbage).  After 16 columns the row
+// has 16 entries left and a second loop with half the slots takes over.
+// Out: column j of L to Ls[lane][j], 1 / L[j][j] to rd[j].
+// No division ever sees a zero numerator (an IEEE division resolves 0 / x through FCHK + a slow-path call, which makes the warp
+// diverge in the middle of the shuffle sequence; the previous leaf lost 25 % on config 2's mostly-zero Kzz to exactly that).
+template <typename T, int LDS>
+__device__ __forceinline__ void warp_chol32(T (&a)[32], T* __restrict__ Ls, T* __restrict__ rd, int lane, int* __restrict__ info_l,
+                                            int base) {
+  int bad = 0;                                       // first non-positive pivot (uniform)
+  auto column = [&](int j, auto nslots) {
+    constexpr int NS = decltype(nslots)::value;
+    const T d = shfl_t(a[0], j);                     // pivot, uniform over the warp
+    bad = (bad == 0 && !(d > T(0))) ? base + j + 1 : bad;           // not positive definite (also catches NaN)
+    const T s = Num<T>::sqrt(d);
+    const T r = T(1) / s;
+    const T lij = lane > j ? a[0] * r : (lane == j ? s : T(0));     // L[lane][j]
+    Ls[lane * LDS + j] = lij;
+    if (lane == 0) rd[j] = r;
+    const T lsub = lane > j ? lij : T(0);
+#pragma unroll
+    for (int k = 1; k < NS; ++k) a[k - 1] = fma(-lsub, shfl_t(lij, (j + k) & 31), a[k]);
+  };
+#pragma unroll 1
+  for (int j = 0; j < 16; ++j) column(j, std::integral_constant<int, 32>{});
+#pragma unroll 1
+  for (int j = 16; j < 32; ++j) column(j, std::integral_constant<int, 16>{});
+  if (bad != 0 && lane == 0 && *info_l == 0) *info_l = bad;
+}
+
+// X = L^-1 of the 32 x 32 block by forward substitution on the identity, row-oriented (lane = row): once row j of X is final
+// (scaled by 1 / L[j][j]) every later row subtracts L[i][j] times it.  Warp w owns columns 4w .. 4w+3 (rows above them are zero,
+// so its sweep starts at j = 4w).  Reads Ls / rd written by warp_chol32, writes Xs[lane][c].
+template <typename T, int LDS>
+__device__ __forceinline__ void warps_trinv32(const T* __restrict__ Ls, const T* __restrict__ rd, T* __restrict__ Xs, int warp, int lane) {
+  const int c0 = warp * 4;
+  T v[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) v[u] = (c0 + u == lane) ? T(1) : T(0);
+#pragma unroll 2
+  for (int j = c0; j < 32; ++j) {
+    const T r = rd[j];
+    const T lsub = lane > j ? Ls[lane * LDS + j] : T(0);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const T xj = shfl_t(v[u], j) * r;              // X[j][c], final
+      v[u] = lane == j ? xj : fma(-lsub, xj, v[u]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) Xs[lane * LDS + c0 + u] = (c0 + u <= lane) ? v[u] : T(0);
+}
+
 template <typename T>
-__device__ void leaf_body(T (*a)[NB + 1], T (*x)[NB + 1], const T* __restrict__ W, T* __restrict__ Lm, T* __restrict__ X, int M,
-                          int r0, int n, int* __restrict__ info_l) {
-  constexpr int SB = 16;
-  __shared__ T sbuf[SB][SB + 1];
-  __shared__ T rsd[SB];
-  const int tid = threadIdx.x;
+__device__ void leaf_body(T (*a)[NB + 1], T (*x)[NB + 1], const T* __restrict__ W, T* __restrict__ Lm, T* __restrict__ X, int64_t ld,
+                          int r0, int n, int* __restrict__ info_l, int info_off = 0, long long* __restrict__ dbg = nullptr) {
+  constexpr int H = 32;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  long long tc0 = clock64();
+  auto mark = [&](int slot) { if (dbg != nullptr && tid == 0) { const long long t = clock64(); dbg[slot] = t - tc0; tc0 = t; } };
+  // identity padding beyond n keeps the routine free of size tests; the padding never reaches global memory
   for (int e = tid; e < NB * NB; e += 256) {
-    const int i = e / NB, j = e % NB;
-    a[i][j] = (i < n && j <= i) ? W[(int64_t)(r0 + i) * M + r0 + j] : T(0);
+    const int i = e >> 6, j = e & (NB - 1);
+    a[i][j] = (i < n && j <= i) ? W[(int64_t)(r0 + i) * ld + r0 + j] : ((i == j && i >= n) ? T(1) : T(0));
     x[i][j] = T(0);
   }
   __syncthreads();
-  // ---- Cholesky ----
-  for (int j0 = 0; j0 < n; j0 += SB) {
-    const int jn = min(SB, n - j0);
-    {
-      // (a) diagonal 16 x 16 block: thread (ti, tk) owns entry (ti, tk); one barrier per column.  Column j is left
-      //     un-scaled while it is used (the update divides by the pivot instead) and scaled once at the end.
-      const int ti = tid >> 4, tk = tid & 15;
-      for (int j = 0; j < jn; ++j) {
-        const T d = a[j0 + j][j0 + j];
-        if (tid == 0) {
-          if (!(d > T(0)) && *info_l == 0) *info_l = r0 + j0 + j + 1;
-          rsd[j] = Num<T>::rsqrt(d);
-        }
-        if (ti < jn && tk > j && tk <= ti)
-          a[j0 + ti][j0 + tk] -= a[j0 + ti][j0 + j] * a[j0 + tk][j0 + j] / d;
-        __syncthreads();
-      }
-      if (ti < jn && tk <= ti) {
-        const T v = a[j0 + ti][j0 + tk] * rsd[tk];          // diagonal: d * rsqrt(d) = sqrt(d)
-        a[j0 + ti][j0 + tk] = v;
-      }
+  mark(0);
+  __shared__ T rdiag[H];
+  auto diag_block = [&](int o) {                     // factor (warp 0) + invert (all warps) the 32 x 32 block at (o, o)
+    if (warp == 0) {
+      T ar[H];
+#pragma unroll
+      for (int k = 0; k < H; ++k) ar[k] = a[o + lane][o + k];
+      warp_chol32<T, NB + 1>(ar, &a[o][o], rdiag, lane, info_l, info_off + r0 + o);
     }
     __syncthreads();
-    const int rest0 = j0 + jn;
-    if (rest0 < n) {
-      // (b) panel rows below: one thread per row, the 16-wide row segment lives in registers
-      if (tid < n - rest0) {
-        const int i = rest0 + tid;
-        T seg[SB];
+    warps_trinv32<T, NB + 1>(&a[o][o], rdiag, &x[o][o], warp, lane);
+    __syncthreads();
+  };
+  diag_block(0);
+  mark(1);
+  if (n > H) {
+    const int i = H + (tid >> 3), j0 = (tid & 7) * 4;      // 4 outputs (i, j0..j0+3) per thread in every 32^3 product
+    T acc[4];
+    // L21 = A21 X11^T      (X11 lower: x[j][t] = 0 for t > j)
 #pragma unroll
-        for (int c = 0; c < SB; ++c) seg[c] = c < jn ? a[i][j0 + c] : T(0);
+    for (int u = 0; u < 4; ++u) acc[u] = T(0);
+#pragma unroll 8
+    for (int t = 0; t < H; ++t) {
+      const T av = a[i][t];
 #pragma unroll
-        for (int c = 0; c < SB; ++c) {
-          if (c < jn) {
-            T v = seg[c];
-#pragma unroll
-            for (int t = 0; t < c; ++t) v -= seg[t] * a[j0 + c][j0 + t];
-            seg[c] = v / a[j0 + c][j0 + c];
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < SB; ++c) if (c < jn) a[i][j0 + c] = seg[c];
-      }
-      __syncthreads();
-      // (c) trailing update of the lower triangle
-      for (int i = rest0 + (tid >> 4); i < n; i += 16) {
-        for (int k = rest0 + (tid & 15); k <= i; k += 16) {
-          T v = a[i][k];
-#pragma unroll 4
-          for (int t = 0; t < jn; ++t) v -= a[i][j0 + t] * a[k][j0 + t];
-          a[i][k] = v;
-        }
-      }
-      __syncthreads();
+      for (int u = 0; u < 4; ++u) acc[u] = fma(av, x[j0 + u][t], acc[u]);
     }
-  }
-  // ---- inverse, 16-blocked:  diagonal blocks by substitution (thread = column, column kept in registers), then the
-  //      block diagonals d = 1, 2, 3 ----
-  if (tid < n) {
-    const int c = tid, b0 = (c / SB) * SB, b1 = min(b0 + SB, n);
-    T xc[SB];
+    __syncthreads();                                       // A21 has been read by everyone: overwrite it with L21
 #pragma unroll
-    for (int u = 0; u < SB; ++u) xc[u] = T(0);
+    for (int u = 0; u < 4; ++u) a[i][j0 + u] = acc[u];
+    __syncthreads();
+    // A22 -= L21 L21^T
 #pragma unroll
-    for (int u = 0; u < SB; ++u) {
-      const int r = b0 + u;
-      if (r < b1 && r >= c) {
-        T v = (r == c) ? T(1) : T(0);
+    for (int u = 0; u < 4; ++u) acc[u] = T(0);
+#pragma unroll 8
+    for (int t = 0; t < H; ++t) {
+      const T av = a[i][t];
 #pragma unroll
-        for (int w = 0; w < u; ++w) v -= a[r][b0 + w] * xc[w];       // xc[w] = 0 for rows above c
-        xc[u] = v / a[r][r];
-        x[r][c] = xc[u];
-      }
+      for (int u = 0; u < 4; ++u) acc[u] = fma(av, a[H + j0 + u][t], acc[u]);
     }
-  }
-  __syncthreads();
-  const int nblk = (n + SB - 1) / SB;
-  for (int d = 1; d < nblk; ++d) {
-    for (int bi = d; bi < nblk; ++bi) {
-      const int bj = bi - d;
-      // S = sum_{k=bj}^{bi-1} L[bi,k] X[k,bj]   (16 x 16), thread = one entry
-      const int ii = bi * SB + tid / SB, jj = bj * SB + tid % SB;
-      T sacc = T(0);
-      if (ii < n) {
-        for (int t = bj * SB; t < bi * SB; ++t) sacc += a[ii][t] * x[t][jj];
-      }
-      __syncthreads();                 // every thread finished reading x before the block below is written
-      // X[bi,bj] = -X[bi,bi] S : stage S in the (still zero) upper part? no - use registers via shared scratch row
-      sbuf[tid / SB][tid % SB] = sacc;
-      __syncthreads();
-      if (ii < n) {
-        T v = T(0);
-        const int li = tid / SB;
-        for (int t = 0; t <= li; ++t) v -= x[bi * SB + li][bi * SB + t] * sbuf[t][tid % SB];
-        x[ii][jj] = v;
-      }
-      __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) a[i][H + j0 + u] -= acc[u];
+    __syncthreads();
+    mark(2);
+    diag_block(H);
+    mark(3);
+    // tmp = L21 X11  (into the still empty X21), then X21 = -X22 tmp
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[u] = T(0);
+#pragma unroll 8
+    for (int t = 0; t < H; ++t) {
+      const T av = a[i][t];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] = fma(av, x[t][j0 + u], acc[u]);
     }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) x[i][j0 + u] = acc[u];
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc[u] = T(0);
+#pragma unroll 8
+    for (int t = 0; t < H; ++t) {
+      const T xv = x[i][H + t];                            // X22[i][t] (0 for t > i - 32)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] = fma(xv, x[H + t][j0 + u], acc[u]);
+    }
+    __syncthreads();                                       // tmp has been read by everyone
+#pragma unroll
+    for (int u = 0; u < 4; ++u) x[i][j0 + u] = -acc[u];
+    __syncthreads();
+    mark(4);
   }
   for (int e = tid; e < NB * NB; e += 256) {
-    const int i = e / NB, j = e % NB;
+    const int i = e >> 6, j = e & (NB - 1);
     if (i < n && j < n) {
-      Lm[(int64_t)(r0 + i) * M + r0 + j] = j <= i ? a[i][j] : T(0);
-      X[(int64_t)(r0 + i) * M + r0 + j] = j <= i ? x[i][j] : T(0);
+      Lm[(int64_t)(r0 + i) * ld + r0 + j] = j <= i ? a[i][j] : T(0);
+      X[(int64_t)(r0 + i) * ld + r0 + j] = j <= i ? x[i][j] : T(0);
     }
   }
+  mark(5);
 }
 
 template <typename T>
@@ -304,7 +343,7 @@ __global__ void __launch_bounds__(256) chol_inv_leaf_kernel(const T* __restrict_
   Row* a = reinterpret_cast<Row*>(leaf_smem);
   Row* x = a + NB;
   const int64_t off = (int64_t)blockIdx.x * M * M;
-  leaf_body<T>(a, x, Wall + off, Lall + off, Xall + off, M, r0, n, info + blockIdx.x);
+  leaf_body<T>(a, x, Wall + off, Lall + off, Xall + off, (int64_t)M, r0, n, info + blockIdx.x);
 }
 
 // ---- the whole Cholesky + inverse of one factor in ONE kernel: a thread-block cluster of 8 CTAs per factor --------
@@ -377,9 +416,10 @@ constexpr int MAX_STEPS = 192;
 
 template <typename T>
 __device__ void run_steps(T (*tA)[TLD], T (*tB)[TLD], const int4* __restrict__ steps, int nsteps, const T* __restrict__ MA,
-                          const T* __restrict__ MB, T* __restrict__ MO, bool b_tr, T alpha, T beta, int M) {
+                          const T* __restrict__ MB, T* __restrict__ MO, bool b_tr, T alpha, T beta, int M, int nsz) {
+  // M: row stride of the matrices; nsz: size of the (sub-)matrix the block coordinates refer to
   const int tid = threadIdx.x;
-  auto bsz = [&](int b) { return min(NB, M - b * NB); };
+  auto bsz = [&](int b) { return min(NB, nsz - b * NB); };
   T ra[16], rb[16], rc[4][4];
   const int ty = tid >> 4, tx = tid & 15;
   auto fetch = [&](int sidx) {
@@ -451,8 +491,10 @@ __device__ void run_steps(T (*tA)[TLD], T (*tB)[TLD], const int4* __restrict__ s
 
 template <typename T>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(256)
-chol_inv_cluster_kernel(T* __restrict__ Wall, T* __restrict__ Lall, T* __restrict__ Xall, T* __restrict__ Tall, int M,
-                        int* __restrict__ info, long long* __restrict__ dbg) {
+chol_inv_cluster_kernel(T* __restrict__ Wall, T* __restrict__ Lall, T* __restrict__ Xall, T* __restrict__ Tall, int M, int blk0,
+                        int nsz, int* __restrict__ info, long long* __restrict__ dbg) {
+  // factors + inverts the nsz x nsz diagonal block starting at row / column blk0 of every M x M matrix (blk0 = 0, nsz = M: all
+  // of it); block coordinates below are relative to that block, M is the row stride
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) unsigned char cl_smem[];
@@ -465,15 +507,15 @@ chol_inv_cluster_kernel(T* __restrict__ Wall, T* __restrict__ Lall, T* __restric
   __shared__ int4 steps[MAX_STEPS];
   __shared__ int nsteps_s, q_next_s;
   const int l = blockIdx.x / CL, rank = (int)cluster.block_rank();
-  const int64_t off = (int64_t)l * M * M;
+  const int64_t off = (int64_t)l * M * M + (int64_t)blk0 * M + blk0;
   T* W = Wall + off; T* Lm = Lall + off; T* X = Xall + off; T* Tm = Tall + off;
-  const int nblk = (M + NB - 1) / NB;
-  auto bsz = [&](int b) { return min(NB, M - b * NB); };
+  const int nblk = (nsz + NB - 1) / NB;
+  auto bsz = [&](int b) { return min(NB, nsz - b * NB); };
 
   long long t_leaf = 0, t_panel = 0, t_trail = 0, t_inv = 0, t0 = clock64(), t1;
   // ---- factorisation, with look-ahead: while CTAs 1..7 apply the trailing update of step k, CTA 0 updates the next
   //      diagonal tile first and immediately factors / inverts it (the leaf is the serial part of the chain) ----
-  if (rank == 0) leaf_body<T>(la, lx, W, Lm, X, M, 0, bsz(0), info + l);
+  if (rank == 0) leaf_body<T>(la, lx, W, Lm, X, (int64_t)M, 0, bsz(0), info + l, blk0, (dbg != nullptr && blockIdx.x == 0) ? dbg + 4 : nullptr);
   cluster.sync();
   t1 = clock64(); t_leaf += t1 - t0; t0 = t1;
   for (int k = 0; k < nblk - 1; ++k) {
@@ -485,7 +527,7 @@ chol_inv_cluster_kernel(T* __restrict__ Wall, T* __restrict__ Lall, T* __restric
       nsteps_s = ns;
     }
     __syncthreads();
-    run_steps<T>(tA, tB, steps, nsteps_s, W, X, Lm, false, T(1), T(0), M);
+    run_steps<T>(tA, tB, steps, nsteps_s, W, X, Lm, false, T(1), T(0), M, nsz);
     cluster.sync();
     t1 = clock64(); t_panel += t1 - t0; t0 = t1;
     // trailing update of the lower triangle: W[gi][gj] -= Lc[gi][k] Lc[gj][k]^T   (in rounds of at most MAX_STEPS tiles).
@@ -505,11 +547,11 @@ chol_inv_cluster_kernel(T* __restrict__ Wall, T* __restrict__ Lall, T* __restric
       }
       __syncthreads();
       const int ns = nsteps_s, qn = q_next_s;
-      run_steps<T>(tA, tB, steps, ns, Lm, Lm, W, false, T(-1), T(1), M);
+      run_steps<T>(tA, tB, steps, ns, Lm, Lm, W, false, T(-1), T(1), M, nsz);
       __syncthreads();
       q_start = qn;
     }
-    if (rank == 0) leaf_body<T>(la, lx, W, Lm, X, M, (k + 1) * NB, bsz(k + 1), info + l);
+    if (rank == 0) leaf_body<T>(la, lx, W, Lm, X, (int64_t)M, (k + 1) * NB, bsz(k + 1), info + l, blk0);
     cluster.sync();
     t1 = clock64(); t_trail += t1 - t0; t0 = t1;
   }
@@ -543,8 +585,8 @@ chol_inv_cluster_kernel(T* __restrict__ Wall, T* __restrict__ Lall, T* __restric
         }
         __syncthreads();
         const int ns = nsteps_s, qn = q_next_s;
-        if (stage == 0) run_steps<T>(tA, tB, steps, ns, Lm, X, Tm, true, T(1), T(0), M);
-        else run_steps<T>(tA, tB, steps, ns, X, Tm, X, true, T(-1), T(0), M);
+        if (stage == 0) run_steps<T>(tA, tB, steps, ns, Lm, X, Tm, true, T(1), T(0), M, nsz);
+        else run_steps<T>(tA, tB, steps, ns, X, Tm, X, true, T(-1), T(0), M, nsz);
         __syncthreads();
         q_start = qn;
       }
@@ -617,7 +659,7 @@ template <typename T> int chol_inv(T* W, T* Lc, T* X, T* tmp, int M, int L, int*
   if (use_cluster && M <= 1536) {
     constexpr int csmem = (int)(2 * NB * TLD * sizeof(T));
     GPZ_CUDA(cudaFuncSetAttribute(chol_inv_cluster_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, csmem));
-    chol_inv_cluster_kernel<T><<<L * CL, 256, csmem, st>>>(W, Lc, X, tmp, M, info, g_chol_dbg);
+    chol_inv_cluster_kernel<T><<<L * CL, 256, csmem, st>>>(W, Lc, X, tmp, M, 0, M, info, g_chol_dbg);
     GPZ_CHECK_LAUNCH();
     return GPZ_OK;
   }
@@ -734,6 +776,67 @@ static int chol_inv_tc(float* W, float* Lc, float* X, float* tmp, float* lo_ws, 
   int rc = gpz_tf32_lo_f32(W, Wlo, tot, (void*)st);
   if (rc) return rc;
   return chol_inv_rec_tc(W, Lc, X, tmp, Wlo, Llo, Xlo, Tlo, M, L, 0, M, info, st);
+}
+
+// ---- hybrid: right-looking with 256-wide panels; diagonal blocks on the cluster kernel, everything else on tcgen05 -------------
+// The cluster kernel above is bound by its serial chain of 64 x 64 leaves and by CUDA-core tile products; here it only factors
+// and inverts the nbo x nbo (256) diagonal blocks (4 leaves each), and every product that involves more than one such block is
+// one batched tcgen05 split-TF32 GEMM on sub-blocks in place:
+//     for each panel k:   (L11, X11) = cluster(W11);   L21 = W21 X11^T;   W22 -= L21 L21^T        (trailing update, lower)
+//     then X = Lc^-1 by recursive doubling over the panels:   X21 = -X22 (L21 X11)
+// 12 GEMM launches at M = 1024.  lo planes as in chol_inv_rec_tc.
+static int hyb_nb() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GPZ_CHOL_HYB_NB"); v = e ? atoi(e) : 256; if (v < 64) v = 64; v = (v / 64) * 64; }
+  return v;
+}
+
+static int chol_inv_hybrid(float* W, float* Lc, float* X, float* tmp, float* lo_ws, int M, int L, int* info, cudaStream_t st) {
+  const int64_t sL = (int64_t)M * M, tot = sL * L;
+  float* Wlo = lo_ws; float* Llo = lo_ws + tot; float* Xlo = lo_ws + 2 * tot; float* Tlo = lo_ws + 3 * tot;
+  GPZ_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * L, st));
+  GPZ_CUDA(cudaMemsetAsync(Lc, 0, sizeof(float) * tot, st));
+  GPZ_CUDA(cudaMemsetAsync(X, 0, sizeof(float) * tot, st));
+  GPZ_CUDA(cudaMemsetAsync(Llo, 0, sizeof(float) * 2 * tot, st));       // Llo, Xlo: zero above the diagonal like Lc, X
+  int rc = gpz_tf32_lo_f32(W, Wlo, tot, (void*)st);
+  if (rc) return rc;
+  constexpr int csmem = (int)(2 * NB * TLD * sizeof(float));
+  GPZ_CUDA(cudaFuncSetAttribute(chol_inv_cluster_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, csmem));
+  const int nbo = hyb_nb();
+  for (int r0 = 0; r0 < M; r0 += nbo) {
+    const int n = min(nbo, M - r0), rem = M - r0 - n;
+    const int64_t o11 = (int64_t)r0 * M + r0, o21 = (int64_t)(r0 + n) * M + r0, o22 = (int64_t)(r0 + n) * M + r0 + n;
+    chol_inv_cluster_kernel<float><<<L * CL, 256, csmem, st>>>(W, Lc, X, tmp, M, r0, n, info, nullptr);
+    GPZ_CHECK_LAUNCH();
+    rc = lo_block(Lc + o11, Llo + o11, n, M, L, st);
+    if (rc) return rc;
+    rc = lo_block(X + o11, Xlo + o11, n, M, L, st);
+    if (rc) return rc;
+    if (rem > 0) {
+      // L21 = W21 X11^T            (B = X11 stored n x k: K-major; op(B) = X11^T is upper triangular)
+      rc = umma_gemm_ex(1, rem, n, n, 1.0f, W + o21, Wlo + o21, M, sL, X + o11, Xlo + o11, M, sL, nullptr, Lc + o21, Llo + o21, M, sL,
+                        L, 0, 2, 0, 1, 3, nullptr, (void*)st);
+      if (rc) return rc;
+      // W22 -= L21 L21^T  (lower triangle, in place): the trailing update
+      rc = umma_gemm_ex(1, rem, rem, n, -1.0f, Lc + o21, Llo + o21, M, sL, Lc + o21, Llo + o21, M, sL, W + o22, W + o22, Wlo + o22, M,
+                        sL, L, 0, 0, 1, 1, 3, nullptr, (void*)st);
+      if (rc) return rc;
+    }
+  }
+  for (int b = nbo; b < M; b *= 2) {
+    for (int f0 = 0; f0 + b < M; f0 += 2 * b) {
+      const int n1 = b, n2 = min(b, M - f0 - b);
+      const int64_t o11 = (int64_t)f0 * M + f0, o21 = (int64_t)(f0 + b) * M + f0, o22 = (int64_t)(f0 + b) * M + f0 + b;
+      // tmp21 = L21 X11  (X11 lower triangular, stored k x n) ;  X21 = -X22 tmp21  (X22 lower triangular)
+      rc = umma_gemm_ex(0, n2, n1, n1, 1.0f, Lc + o21, Llo + o21, M, sL, X + o11, Xlo + o11, M, sL, nullptr, tmp + o21, Tlo + o21, M, sL,
+                        L, 0, 1, 0, 1, 3, nullptr, (void*)st);
+      if (rc) return rc;
+      rc = umma_gemm_ex(0, n2, n1, n2, -1.0f, X + o22, Xlo + o22, M, sL, tmp + o21, Tlo + o21, M, sL, nullptr, X + o21, Xlo + o21, M, sL,
+                        L, 1, 0, 0, 1, 3, nullptr, (void*)st);
+      if (rc) return rc;
+    }
+  }
+  return GPZ_OK;
 }
 
 // ---- element-wise O(M^2) helpers -------------------------------------------------------------------
@@ -889,5 +992,8 @@ GPZ_LINALG_IMPL(f64, double)
 extern "C" int gpz_chol_inv_tc_f32(float* W, float* Lc, float* X, float* tmp, float* lo_ws, int M, int L, int* info, void* stream) {
   if (M <= 0 || L <= 0) return GPZ_ERR_BADARG;
   if (M % 4) return GPZ_ERR_UNSUPPORTED;
-  return chol_inv_tc(W, Lc, X, tmp, lo_ws, M, L, info, ST(stream));
+  static int mode = -1;                 // GPZ_CHOL_TC_MODE=rec: the divide-and-conquer recursion instead of the panel hybrid
+  if (mode < 0) { const char* e = getenv("GPZ_CHOL_TC_MODE"); mode = (e && e[0] == 'r') ? 1 : 0; }
+  if (mode == 1) return chol_inv_tc(W, Lc, X, tmp, lo_ws, M, L, info, ST(stream));
+  return chol_inv_hybrid(W, Lc, X, tmp, lo_ws, M, L, info, ST(stream));
 }

@@ -27,7 +27,9 @@ TENSOR_CORE_ARITH = os.environ.get("GPZ_TC_ARITH", "fp16x3")
 # fp32 models: up to this many inducing points the O(M^3) chain runs in fp64 (gp.py `_chain_dtype`); GPZ_CHAIN_FP64_MAX_M=0 turns it off
 CHAIN_FP64_MAX_M = int(os.environ.get("GPZ_CHAIN_FP64_MAX_M", "256"))
 FUSED_CHAIN = os.environ.get("GPZ_FUSED_CHAIN", "1") != "0"       # csrc/chain.cu instead of the Function-per-op chain
-CHOL_TC_MIN_M = 1536         # above this size the fp32 Cholesky + inverse runs its O(M^3) products on the tensor cores
+CHOL_TC_MIN_M = int(os.environ.get("GPZ_CHOL_TC_MIN_M", "768"))   # above this size the fp32 Cholesky + inverse is the panel hybrid:
+# 256-wide diagonal blocks on the cluster kernel, trailing updates and the inverse's doubling on tcgen05 (measured, L = 10:
+# M = 512 0.42 vs 0.51 ms, M = 1024 1.30 vs 1.18 ms, M = 1536 3.41 vs 2.02 ms, cluster vs hybrid)
 _pending_info = []
 # build Kzx on a side stream, concurrently with the Cholesky chain of Kzz (gp.py moments); GPZ_OVERLAP=0 turns it off
 OVERLAP_KERNEL_BUILD = os.environ.get("GPZ_OVERLAP", "1") != "0"

@@ -346,7 +346,10 @@ class VNNGP(_SparseGPBase):
         Kzz = _as3(self.kernel(self.Z, self.Z, _jitter=self.jitter))                 # first jitter (gp.py:55)
         Kxx = self.kernel(X, X, diag=True)
         Kxx = Kxx if Kxx.dim() == 2 else Kxx.unsqueeze(0)
-        Lc, Linv, Lu, T, q, L = self._whitened(Kzz)
+        # the full-M chain only feeds KL(qU || pU) (gp.py:119-120) and Lu; it runs in the chain's dtype (fp64 up to M = 256)
+        cdt = self._chain_dtype(dt)
+        Lc, Linv, Lu_c, T, q, L = self._whitened(Kzz if cdt == dt else self._kzz(X, None, cdt))
+        Lu = Lu_c.to(dt)
         if Kzz.shape[0] != L:
             Kzz, Kxx = Kzz.expand(L, -1, -1), Kxx.expand(L, -1)
         S = F.OuterLower.apply(Lu)
@@ -358,7 +361,7 @@ class VNNGP(_SparseGPBase):
             sigma, ls = sigma.expand(L), ls.expand(L)
         nn_idx = self.neighbors(X)
         mean, var = F.VnngpPredict.apply(X, self.Z.to(dt), sigma, ls, Kzz, S, mu, Kxx, nn_idx, float(self.jitter))
-        return dict(mean=mean, var=var, T=T, q=q, Lc=Lc, Lu=Lu, nn=nn_idx)
+        return dict(mean=mean, var=var, T=T, q=q, Lc=Lc, Lu=Lu_c, nn=nn_idx, kl=getattr(self, "_chain_kl", None))
 
     def forward(self, X, verbose=False):
         return self._distributions(self.moments(X))

@@ -40,13 +40,13 @@ for M in [int(a) for a in sys.argv[1:]] or [1024]:
         print(line + f"  torch.linalg.cholesky alone {tt:.3f} ms")
     if M <= 1536:
         F.CHOL_TC_MIN_M = 1 << 30
-        dbg = torch.zeros(4, dtype=torch.int64, device='cuda')
+        dbg = torch.zeros(10, dtype=torch.int64, device='cuda')
         _cabi.lib().gpz_chol_debug_(ctypes.c_void_p(dbg.data_ptr()))
         F.CholeskyInverse.apply(K)
         torch.cuda.synchronize()
         _cabi.lib().gpz_chol_debug_(ctypes.c_void_p(0))
         c = dbg.cpu().tolist()
-        print(f"  cluster phases (clock64 of CTA 0, L={L}): leaf {c[0]} panel {c[1]} trail+leaf {c[2]} inverse {c[3]}  total {sum(c)}")
+        print(f"  cluster phases (clock64 of CTA 0, L={L}): leaf {c[0]} panel {c[1]} trail+leaf {c[2]} inverse {c[3]}  total {sum(c[:4])}; first leaf: load {c[4]} diag0 {c[5]} products {c[6]} diag1 {c[7]} X21 {c[8]} store {c[9]}")
 
 # does the time depend on the VALUES?  config 2's Kzz is 1.1 I plus mostly tiny (many denormal) entries
 from gpzoo_b200 import synthetic
