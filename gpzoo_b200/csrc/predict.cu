@@ -263,15 +263,16 @@ static int predict_bwd_tc(const float* Kzx, const float* Kzx_lo, const float* Li
 // of its output directly:
 //   Kzx  : |K| <= sigma^2                                   (kernel_build.cu writes the planes and sK)
 //   A    : |A[:,n]|_2^2 = k_n^T (Kzz + jitter I)^-1 k_n <= Kxx[n]   (Schur complement of a PSD kernel)  ->  bound 2 sqrt(max Kxx)
-//   gC   : 2 max|C| max|gv|                                 (max|C| is tracked exactly by the epilogue that produced C)
-//   gA   : |T|_inf bound(gC) + 2 max|A| max|gv| + max|q| max|gm|
+//   C    : |C[m,n]| <= |T[:,m]|_2 |A[:,n]|_2 <= sqrt(M) max|T| sqrt(max Kxx)      (bound x 2; max|C| is also tracked exactly)
+//   A diag(2 gv) : 2 max|A| max|gv|                          (written by the gA epilogue, feeds gT)
+//   gA   : |T|_inf 2 max|C| max|gv| + 2 max|A| max|gv| + max|q| max|gm|
 //   Linv, T (M x M): exact max from a reduction pass.
 // A bound that is 2^10 too loose still leaves the fp16 subnormal floor 2^-30 below the largest entry, i.e. below fp32 epsilon
 // relative to the matrix norm; a violated bound produces inf/NaN (never a silently saturated value).
 // ws_h (halfs): [Linv_h | Linv_l | LinvT_h | LinvT_l | T_h | T_l | TT_h | TT_l], each L*M*M.
 // ws_f (floats): [sumA2 (L*N) | sumC2 (L*N) | stats (16 slots of L)], slots:
-enum { ST_S_LINV = 0, ST_S_T, ST_S_A, ST_S_GC, ST_S_GA, ST_AMAX_LINV, ST_AMAX_T, ST_AMAX_A, ST_AMAX_C, ST_TINF, ST_AMAX_GV,
-       ST_AMAX_GM, ST_AMAX_Q, ST_AMAX_KXX, ST_AMAX_GA, ST_SPARE, ST_SLOTS };
+enum { ST_S_LINV = 0, ST_S_T, ST_S_A, ST_S_AW, ST_S_GA, ST_AMAX_LINV, ST_AMAX_T, ST_AMAX_A, ST_AMAX_C, ST_TINF, ST_AMAX_GV,
+       ST_AMAX_GM, ST_AMAX_Q, ST_AMAX_KXX, ST_AMAX_GA, ST_S_C, ST_SLOTS };
 
 // max |x[l,:]| of up to three L x n arrays in one launch: grid (chunks, L, arrays), atomicMax on the float bits
 struct Amax3 { const float* x[3]; int n[3]; unsigned int* out[3]; };
@@ -285,10 +286,13 @@ __global__ void __launch_bounds__(256) amax3_kernel(const Amax3 a) {
   if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(a.out[w] + l, __float_as_uint(m));
 }
 
-// sA[l] from max Kxx[l,:]
-__global__ void predict_h_fwd_scales_kernel(float* __restrict__ stats, int L) {
+// sA[l] from max Kxx[l,:], sC[l] from max|T| as well
+__global__ void predict_h_fwd_scales_kernel(float* __restrict__ stats, int L, int M) {
   const int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l < L) stats[ST_S_A * L + l] = gpz_pow2_scale(2.f * sqrtf(stats[ST_AMAX_KXX * L + l]));
+  if (l >= L) return;
+  const float rk = sqrtf(stats[ST_AMAX_KXX * L + l]);
+  stats[ST_S_A * L + l] = gpz_pow2_scale(2.f * rk);
+  stats[ST_S_C * L + l] = gpz_pow2_scale(2.f * sqrtf((float)M) * stats[ST_AMAX_T * L + l] * rk);
 }
 
 // max_i sum_j |T[l,i,j]|: one warp per row
@@ -308,41 +312,10 @@ __global__ void predict_h_bwd_scales_kernel(float* __restrict__ stats, int L) {
   if (l >= L) return;
   const float a_A = stats[ST_AMAX_A * L + l], a_C = stats[ST_AMAX_C * L + l], tinf = stats[ST_TINF * L + l];
   const float a_gv = stats[ST_AMAX_GV * L + l], a_gm = stats[ST_AMAX_GM * L + l], a_q = stats[ST_AMAX_Q * L + l];
-  const float b_gC = 2.f * a_C * a_gv;
+  const float b_gC = 2.f * a_C * a_gv;                      // |C diag(2 gv)|
   const float b_gA = tinf * b_gC + 2.f * a_A * a_gv + a_q * a_gm;
-  stats[ST_S_GC * L + l] = gpz_pow2_scale(b_gC);
+  stats[ST_S_AW * L + l] = gpz_pow2_scale(2.f * a_A * a_gv);  // A diag(2 gv)
   stats[ST_S_GA * L + l] = gpz_pow2_scale(b_gA);
-}
-
-// gC = 2 C gv written as fp16 planes of gC * s[l]
-__global__ void __launch_bounds__(256) predict_h_scale_kernel(const float* __restrict__ C, const float* __restrict__ gv,
-                                                               const float* __restrict__ s_gc, __half* __restrict__ gCh,
-                                                               __half* __restrict__ gCl, int M, int N) {
-  const int l = blockIdx.z;
-  const int n8 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
-  if (n8 >= N) return;
-  const float sc = 2.f * s_gc[l];
-  const float4 g0 = *reinterpret_cast<const float4*>(gv + (int64_t)l * N + n8);
-  const float4 g1 = *reinterpret_cast<const float4*>(gv + (int64_t)l * N + n8 + 4);
-  const float w[8] = {g0.x * sc, g0.y * sc, g0.z * sc, g0.w * sc, g1.x * sc, g1.y * sc, g1.z * sc, g1.w * sc};
-  const int m0 = blockIdx.y * 16, m1 = min(m0 + 16, M);
-  for (int m = m0; m < m1; ++m) {
-    const int64_t e = ((int64_t)l * M + m) * N + n8;
-    const float4 c0 = __ldcs(reinterpret_cast<const float4*>(C + e));
-    const float4 c1 = __ldcs(reinterpret_cast<const float4*>(C + e + 4));
-    const float v[8] = {c0.x * w[0], c0.y * w[1], c0.z * w[2], c0.w * w[3], c1.x * w[4], c1.y * w[5], c1.z * w[6], c1.w * w[7]};
-    uint32_t h[4], lo[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const __half2 hh = __floats2half2_rn(v[2 * u], v[2 * u + 1]);
-      const float2 f = __half22float2(hh);
-      const __half2 ll = __floats2half2_rn(v[2 * u] - f.x, v[2 * u + 1] - f.y);
-      h[u] = *reinterpret_cast<const uint32_t*>(&hh);
-      lo[u] = *reinterpret_cast<const uint32_t*>(&ll);
-    }
-    *reinterpret_cast<uint4*>(gCh + e) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(gCl + e) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-  }
 }
 
 static Umma16Args h_args(int bk, int m, int n, int k, const __half* Ah, const __half* Al, int64_t lda, int64_t sA, const float* sa,
@@ -357,8 +330,8 @@ static Umma16Args h_args(int bk, int m, int n, int k, const __half* Ah, const __
 }
 
 static int predict_fwd_h(const __half* Kh, const __half* Kl, const float* sK, const float* Linv, const float* Tm, const float* q,
-                         const float* kxx, __half* Ah, __half* Al, float* C, float* mean, float* var, __half* ws_h, float* ws_f,
-                         int M, int N, int L, cudaStream_t st) {
+                         const float* kxx, __half* Ah, __half* Al, __half* Ch, __half* Cl, float* mean, float* var, __half* ws_h,
+                         float* ws_f, int M, int N, int L, cudaStream_t st) {
   const int64_t sMM = (int64_t)M * M, sMN = (int64_t)M * N, W = sMM * L, LN = (int64_t)L * N;
   __half* Linv_h = ws_h; __half* Linv_l = ws_h + W;
   __half* LinvT_h = ws_h + 2 * W; __half* LinvT_l = ws_h + 3 * W;
@@ -377,7 +350,7 @@ static int predict_fwd_h(const __half* Kh, const __half* Kl, const float* sK, co
   if (rc) return rc;
   rc = split16_amax(kxx, N, L, ustats + ST_AMAX_KXX * L, (void*)st);
   if (rc) return rc;
-  predict_h_fwd_scales_kernel<<<(unsigned)cdiv(L, 64), 64, 0, st>>>(stats, L);
+  predict_h_fwd_scales_kernel<<<(unsigned)cdiv(L, 64), 64, 0, st>>>(stats, L, M);
   GPZ_CHECK_LAUNCH();
   // A = Linv Kzx  (lower-triangular product == TRSM Lc A = Kzx); epilogue: sum_m A^2, mean = sum_m q_m A, max |A|
   UmmaEpilogue e1{1, nullptr, q, nullptr, nullptr, sA2, mean, nullptr};
@@ -385,10 +358,10 @@ static int predict_fwd_h(const __half* Kh, const __half* Kl, const float* sK, co
   g1.Dh = Ah; g1.Dl = Al; g1.sd = stats + ST_S_A * L; g1.amax = ustats + ST_AMAX_A * L; g1.epi = &e1;
   rc = umma_gemm16_ex(g1, (void*)st);
   if (rc) return rc;
-  // C = T^T A     (upper-triangular product); epilogue: sum_m C^2, max |C|
+  // C = T^T A     (upper-triangular product), kept as fp16 planes for the backward; epilogue: sum_m C^2, max |C|
   UmmaEpilogue e2{2, nullptr, nullptr, nullptr, nullptr, sC2, nullptr, nullptr};
   Umma16Args g2 = h_args(0, M, N, M, TT_h, TT_l, M, sMM, stats + ST_S_T * L, Ah, Al, N, sMN, stats + ST_S_A * L, N, sMN, L, 2, 0, 1);
-  g2.D = C; g2.amax = ustats + ST_AMAX_C * L; g2.epi = &e2;
+  g2.Dh = Ch; g2.Dl = Cl; g2.sd = stats + ST_S_C * L; g2.amax = ustats + ST_AMAX_C * L; g2.epi = &e2;
   rc = umma_gemm16_ex(g2, (void*)st);
   if (rc) return rc;
   predict_var_kernel<<<(unsigned)cdiv(LN, 256), 256, 0, st>>>(kxx, sA2, sC2, var, LN);
@@ -397,15 +370,16 @@ static int predict_fwd_h(const __half* Kh, const __half* Kl, const float* sK, co
 }
 
 static int predict_bwd_h(const __half* Kh, const __half* Kl, const float* sK, const float* Tm, const float* q, const __half* Ah,
-                         const __half* Al, const float* C, const float* gm, const float* gv, __half* gCh, __half* gCl, __half* gAh,
-                         __half* gAl, float* gKzx, float* gLinv, float* gT, float* gq, __half* ws_h, float* ws_f, int M, int N, int L,
-                         cudaStream_t st) {
+                         const __half* Al, const __half* Ch, const __half* Cl, const float* gm, const float* gv, __half* AWh,
+                         __half* AWl, __half* gAh, __half* gAl, float* gKzx, float* gLinv, float* gT, float* gq, __half* ws_h,
+                         float* ws_f, int M, int N, int L, cudaStream_t st) {
   const int64_t sMM = (int64_t)M * M, sMN = (int64_t)M * N, W = sMM * L, LN = (int64_t)L * N;
   __half* LinvT_h = ws_h + 2 * W; __half* LinvT_l = ws_h + 3 * W;
   __half* T_h = ws_h + 4 * W; __half* T_l = ws_h + 5 * W;
   float* stats = ws_f + 2 * LN;
   unsigned int* ustats = reinterpret_cast<unsigned int*>(stats);
-  const float* sA = stats + ST_S_A * L; const float* sgC = stats + ST_S_GC * L; const float* sgA = stats + ST_S_GA * L;
+  const float* sA = stats + ST_S_A * L; const float* sAW = stats + ST_S_AW * L; const float* sgA = stats + ST_S_GA * L;
+  const float* sC = stats + ST_S_C * L;
   // (the backward may run more than once on the same forward state: reset the maxima it accumulates)
   GPZ_CUDA(cudaMemsetAsync(ustats + ST_TINF * L, 0, sizeof(unsigned int) * 4 * (size_t)L, st));      // TINF, GV, GM, Q are adjacent
   GPZ_CUDA(cudaMemsetAsync(ustats + ST_AMAX_GA * L, 0, sizeof(unsigned int) * (size_t)L, st));
@@ -416,24 +390,25 @@ static int predict_bwd_h(const __half* Kh, const __half* Kl, const float* sK, co
   GPZ_CHECK_LAUNCH();
   predict_h_bwd_scales_kernel<<<(unsigned)cdiv(L, 64), 64, 0, st>>>(stats, L);
   GPZ_CHECK_LAUNCH();
-  predict_h_scale_kernel<<<dim3((unsigned)cdiv(N, 2048), (unsigned)cdiv(M, 16), L), 256, 0, st>>>(C, gv, sgC, gCh, gCl, M, N);
-  GPZ_CHECK_LAUNCH();
   GPZ_CUDA(cudaMemsetAsync(gq, 0, sizeof(float) * (size_t)L * M, st));
   int splitk = 1;
   {
     const int64_t tiles = cdiv(M, 128) * cdiv(M, 256) * L / 2 + 1;
     while (splitk < 32 && tiles * splitk < 148 * 2 && N / (splitk * 2) >= 1024) splitk *= 2;
   }
-  // gT = tril(A gC^T)   (reduction over the N spots, both operands K-major)
-  Umma16Args g4 = h_args(1, M, M, N, Ah, Al, N, sMN, sA, gCh, gCl, N, sMN, sgC, M, sMM, L, 0, 1, splitk);
-  g4.D = gT;
-  int rc = umma_gemm16_ex(g4, (void*)st);
-  if (rc) return rc;
-  // gA = T gC - 2 A gv + q gm^T ;  gq = A gm     (both in the epilogue, which reads the A planes once)
-  UmmaEpilogue e3{3, nullptr, q, gv, gm, nullptr, nullptr, gq};
-  Umma16Args g3 = h_args(0, M, N, M, T_h, T_l, M, sMM, stats + ST_S_T * L, gCh, gCl, N, sMN, sgC, N, sMN, L, 1, 0, 1);
+  // gA = T C diag(2 gv) - A diag(2 gv) + q gm^T = 2 gv o (T C - A) + q gm^T  straight from the unweighted C planes (the column
+  // weights commute out of the product); the same epilogue, which reads the A planes once, also gives gq = A gm and writes
+  // AW = A diag(2 gv) as planes for the reduction below
+  UmmaEpilogue e3{4, nullptr, q, gv, gm, nullptr, nullptr, gq};
+  Umma16Args g3 = h_args(0, M, N, M, T_h, T_l, M, sMM, stats + ST_S_T * L, Ch, Cl, N, sMN, sC, N, sMN, L, 1, 0, 1);
   g3.Dh = gAh; g3.Dl = gAl; g3.sd = sgA; g3.amax = ustats + ST_AMAX_GA * L; g3.epi = &e3; g3.AuxH = Ah; g3.AuxL = Al; g3.saux = sA;
-  rc = umma_gemm16_ex(g3, (void*)st);
+  g3.D2h = AWh; g3.D2l = AWl; g3.sd2 = sAW;
+  int rc = umma_gemm16_ex(g3, (void*)st);
+  if (rc) return rc;
+  // gT = tril(A diag(2 gv) C^T)   (reduction over the N spots, both operands K-major)
+  Umma16Args g4 = h_args(1, M, M, N, AWh, AWl, N, sMN, sAW, Ch, Cl, N, sMN, sC, M, sMM, L, 0, 1, splitk);
+  g4.D = gT;
+  rc = umma_gemm16_ex(g4, (void*)st);
   if (rc) return rc;
   // gKzx = Linv^T gA
   Umma16Args g5 = h_args(0, M, N, M, LinvT_h, LinvT_l, M, sMM, stats + ST_S_LINV * L, gAh, gAl, N, sMN, sgA, N, sMN, L, 2, 0, 1);
@@ -469,7 +444,7 @@ extern "C" int gpz_svgp_predict_bwd_tc_f32(const float* Kzx, const float* Kzx_lo
 
 // split-FP16 tensor-core variant (see predict_fwd_h): planes are fp16, ws_h holds 8 L*M*M halfs, ws_f 2 L*N + 16 L floats
 // row of the stats block (L floats each, starting at ws_f + 2 L N) holding: 0 scale of A, 1 max|A|, 2 max|C|, 3 scale of gA,
-// 4 max|gA|  (read by the host-side overflow guard); -1 for an unknown id
+// 4 max|gA|, 5 scale of C  (read by the host-side overflow guard); -1 for an unknown id
 extern "C" int gpz_svgp_predict_h_stat_row(int which) {
   switch (which) {
     case 0: return ST_S_A;
@@ -477,25 +452,26 @@ extern "C" int gpz_svgp_predict_h_stat_row(int which) {
     case 2: return ST_AMAX_C;
     case 3: return ST_S_GA;
     case 4: return ST_AMAX_GA;
+    case 5: return ST_S_C;
     default: return -1;
   }
 }
 extern "C" int gpz_svgp_predict_h_supported(int M, int N) { return (M % 8 == 0 && N % 8 == 0 && M >= 64 && N >= 256) ? 1 : 0; }
 extern "C" int gpz_svgp_predict_fwd_h_f32(const void* Kh, const void* Kl, const float* sK, const float* Linv, const float* T,
-                                          const float* q, const float* kxx, void* Ah, void* Al, float* C, float* mean, float* var,
-                                          void* ws_h, float* ws_f, int M, int N, int L, void* stream) {
+                                          const float* q, const float* kxx, void* Ah, void* Al, void* Ch, void* Cl, float* mean,
+                                          float* var, void* ws_h, float* ws_f, int M, int N, int L, void* stream) {
   if (!gpz_svgp_predict_h_supported(M, N) || L <= 0) return GPZ_ERR_UNSUPPORTED;
-  return predict_fwd_h((const __half*)Kh, (const __half*)Kl, sK, Linv, T, q, kxx, (__half*)Ah, (__half*)Al, C, mean, var,
-                       (__half*)ws_h, ws_f, M, N, L, (cudaStream_t)stream);
+  return predict_fwd_h((const __half*)Kh, (const __half*)Kl, sK, Linv, T, q, kxx, (__half*)Ah, (__half*)Al, (__half*)Ch, (__half*)Cl,
+                       mean, var, (__half*)ws_h, ws_f, M, N, L, (cudaStream_t)stream);
 }
 extern "C" int gpz_svgp_predict_bwd_h_f32(const void* Kh, const void* Kl, const float* sK, const float* T, const float* q,
-                                          const void* Ah, const void* Al, const float* C, const float* gm, const float* gv,
-                                          void* gCh, void* gCl, void* gAh, void* gAl, float* gKzx, float* gLinv, float* gT,
-                                          float* gq, void* ws_h, float* ws_f, int M, int N, int L, void* stream) {
+                                          const void* Ah, const void* Al, const void* Ch, const void* Cl, const float* gm,
+                                          const float* gv, void* AWh, void* AWl, void* gAh, void* gAl, float* gKzx, float* gLinv,
+                                          float* gT, float* gq, void* ws_h, float* ws_f, int M, int N, int L, void* stream) {
   if (!gpz_svgp_predict_h_supported(M, N) || L <= 0) return GPZ_ERR_UNSUPPORTED;
-  return predict_bwd_h((const __half*)Kh, (const __half*)Kl, sK, T, q, (const __half*)Ah, (const __half*)Al, C, gm, gv,
-                       (__half*)gCh, (__half*)gCl, (__half*)gAh, (__half*)gAl, gKzx, gLinv, gT, gq, (__half*)ws_h, ws_f, M, N, L,
-                       (cudaStream_t)stream);
+  return predict_bwd_h((const __half*)Kh, (const __half*)Kl, sK, T, q, (const __half*)Ah, (const __half*)Al, (const __half*)Ch,
+                       (const __half*)Cl, gm, gv, (__half*)AWh, (__half*)AWl, (__half*)gAh, (__half*)gAl, gKzx, gLinv, gT, gq,
+                       (__half*)ws_h, ws_f, M, N, L, (cudaStream_t)stream);
 }
 
 #define GPZ_PREDICT_IMPL(SUF, T)                                                                                      \

@@ -59,6 +59,8 @@ struct Params {
   //   1: col1[n] += sum_i D[i,n]^2 ; col2[n] += sum_i rowv[i] D[i,n]                     (A = Linv Kzx: sum A^2 and mean)
   //   2: col1[n] += sum_i D[i,n]^2                                                        (C = T^T A: sum C^2)
   //   3: D = acc - 2 Aux[i,n] colv1[n] + rowv[i] colv2[n] ; rowacc[i] += sum_n Aux[i,n] colv2[n]   (gA and gq = A gm)
+  //   4: D = 2 colv1[n] (acc - Aux[i,n]) + rowv[i] colv2[n] ; rowacc as 3 ; D2 = 2 colv1[n] Aux[i,n]  (fp16 planes D2h/D2l * sd2)
+  //      (gA from the UNweighted C planes: the column weights 2 gv commute out of T C diag(2 gv); D2 = A diag(2 gv) feeds gT)
   int epi_mode;
   const float* Aux; const float* rowv; const float* colv1; const float* colv2;
   float* col1; float* col2; float* rowacc;
@@ -68,7 +70,8 @@ struct Params {
   const float* sa; const float* sb;       // operand scales (nullptr = 1): the accumulator is multiplied by 1/(sa[b] sb[b])
   __half* Dh; __half* Dl; const float* sd;   // optional (hi, lo) fp16 output planes of D * sd[b]  (same ldd / sD as D)
   unsigned int* amax;                     // optional per-batch max |D| (float bits, atomicMax)
-  const __half* AuxH; const __half* AuxL; const float* saux;   // epi_mode 3: Aux given as fp16 planes instead of fp32
+  const __half* AuxH; const __half* AuxL; const float* saux;   // epi_mode 3 / 4: Aux given as fp16 planes instead of fp32
+  __half* D2h; __half* D2l; const float* sd2;                 // epi_mode 4: second output (same ldd / sD as D)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -194,7 +197,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 template <int MODE, bool OUT_D, bool OUT_H>
 __device__ __forceinline__ void epilogue_tile_fast(const Params& p, int b, int i0, int j0, int q, int lane, int c_begin,
                                                    uint32_t tmem_acc, float* epi, float alpha_b, float sd_b, float inv_saux,
-                                                   float& amx) {
+                                                   float& amx, float sd2_b = 1.0f) {
   const int lr = lane >> 3, cq = (lane & 7) * 4;
   const int row0 = i0 + q * 32;
   const int64_t ld4 = 4 * p.ldd;
@@ -202,7 +205,7 @@ __device__ __forceinline__ void epilogue_tile_fast(const Params& p, int b, int i
   const int64_t colbase = (int64_t)b * p.n + j0 + c_begin * 32 + cq;
   float racc[8];
   const float* qrow = p.rowv + (int64_t)b * p.m + row0 + lr;      // rowv of row (4 itr + lr): re-read per use (L1), saves 8 registers
-  if (MODE == 3) {
+  if (MODE == 3 || MODE == 4) {
 #pragma unroll
     for (int u = 0; u < 8; ++u) racc[u] = 0.f;
   }
@@ -214,7 +217,7 @@ __device__ __forceinline__ void epilogue_tile_fast(const Params& p, int b, int i
     uint32_t r[32];
     tmem_ld32_nowait(tmem_acc + (uint32_t)((c_begin + cc) * 32), r);
     float4 cv1, cv2;
-    if (MODE == 3) {
+    if (MODE == 3 || MODE == 4) {
       cv1 = __ldg(reinterpret_cast<const float4*>(p.colv1 + colbase + cc * 32));
       cv2 = __ldg(reinterpret_cast<const float4*>(p.colv2 + colbase + cc * 32));
       // (the whole Aux region of this warp was prefetched into L2 when the tile was handed out; rows 0..3 of the later chunks
@@ -240,7 +243,7 @@ __device__ __forceinline__ void epilogue_tile_fast(const Params& p, int b, int i
       float4 v = lds128(srd + itr * 512 + ((((lane & 7) ^ ((4 * (itr & 1) + lr) & 7))) << 4));
       v.x *= alpha_b; v.y *= alpha_b; v.z *= alpha_b; v.w *= alpha_b;
       const int64_t o = o_chunk + itr * ld4;
-      if (MODE == 3) {
+      if (MODE == 3 || MODE == 4) {
         const uint2 hh = axh[itr & 3], ll = axl[itr & 3];
         if (itr < 4) {                                 // this slot is free again: fetch row itr + 4
           axh[itr] = __ldcs(reinterpret_cast<const uint2*>(p.AuxH + o_chunk + (itr + 4) * ld4));
@@ -253,10 +256,23 @@ __device__ __forceinline__ void epilogue_tile_fast(const Params& p, int b, int i
         ax.x = unpack_sum(hh.x, ll.x, 0) * inv_saux; ax.y = unpack_sum(hh.x, ll.x, 1) * inv_saux;
         ax.z = unpack_sum(hh.y, ll.y, 0) * inv_saux; ax.w = unpack_sum(hh.y, ll.y, 1) * inv_saux;
         const float qv = __ldg(qrow + itr * 4);
-        v.x += fmaf(qv, cv2.x, -2.f * ax.x * cv1.x);
-        v.y += fmaf(qv, cv2.y, -2.f * ax.y * cv1.y);
-        v.z += fmaf(qv, cv2.z, -2.f * ax.z * cv1.z);
-        v.w += fmaf(qv, cv2.w, -2.f * ax.w * cv1.w);
+        if (MODE == 3) {
+          v.x += fmaf(qv, cv2.x, -2.f * ax.x * cv1.x);
+          v.y += fmaf(qv, cv2.y, -2.f * ax.y * cv1.y);
+          v.z += fmaf(qv, cv2.z, -2.f * ax.z * cv1.z);
+          v.w += fmaf(qv, cv2.w, -2.f * ax.w * cv1.w);
+        } else {
+          const float4 w = make_float4(2.f * cv1.x, 2.f * cv1.y, 2.f * cv1.z, 2.f * cv1.w);
+          v.x = fmaf(w.x, v.x - ax.x, qv * cv2.x);
+          v.y = fmaf(w.y, v.y - ax.y, qv * cv2.y);
+          v.z = fmaf(w.z, v.z - ax.z, qv * cv2.z);
+          v.w = fmaf(w.w, v.w - ax.w, qv * cv2.w);
+          uint2 qh, ql;                                 // D2 = A diag(2 gv)
+          split_half2(w.x * ax.x * sd2_b, w.y * ax.y * sd2_b, qh.x, ql.x);
+          split_half2(w.z * ax.z * sd2_b, w.w * ax.w * sd2_b, qh.y, ql.y);
+          *reinterpret_cast<uint2*>(p.D2h + o) = qh;
+          *reinterpret_cast<uint2*>(p.D2l + o) = ql;
+        }
         racc[itr] += ax.x * cv2.x + ax.y * cv2.y + ax.z * cv2.z + ax.w * cv2.w;     // reduced over the lanes once per tile
       } else if (MODE != 0) {
         cs1.x = fmaf(v.x, v.x, cs1.x); cs1.y = fmaf(v.y, v.y, cs1.y); cs1.z = fmaf(v.z, v.z, cs1.z); cs1.w = fmaf(v.w, v.w, cs1.w);
@@ -297,7 +313,7 @@ __device__ __forceinline__ void epilogue_tile_fast(const Params& p, int b, int i
     __syncwarp();
     o_chunk += 32;
   }
-  if (MODE == 3) {
+  if (MODE == 3 || MODE == 4) {
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       float rp = racc[u];
@@ -533,7 +549,8 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         (!p.Dlo || (reinterpret_cast<uintptr_t>(p.Dlo) & 15) == 0) &&
                         (!p.Cin || (reinterpret_cast<uintptr_t>(p.Cin) & 15) == 0) && ((p.sD % 4) == 0) &&
                         (!p.Dh || ((reinterpret_cast<uintptr_t>(p.Dh) & 7) == 0 && (reinterpret_cast<uintptr_t>(p.Dl) & 7) == 0)) &&
-                        (!p.AuxH || ((reinterpret_cast<uintptr_t>(p.AuxH) & 7) == 0 && (reinterpret_cast<uintptr_t>(p.AuxL) & 7) == 0));
+                        (!p.AuxH || ((reinterpret_cast<uintptr_t>(p.AuxH) & 7) == 0 && (reinterpret_cast<uintptr_t>(p.AuxL) & 7) == 0)) &&
+                        (!p.D2h || ((reinterpret_cast<uintptr_t>(p.D2h) & 7) == 0 && (reinterpret_cast<uintptr_t>(p.D2l) & 7) == 0));
     float* epi = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 2) * 32 * 32;
     uint32_t acc_iter = 0;
     for (uint32_t iter = 0;; ++iter) {
@@ -547,7 +564,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const bool has_acc = ti.nkb > 0;
       if (!has_acc && !ti.zero) continue;
       const uint32_t as = acc_iter & 1u;
-      if (F16 && p.epi_mode == 3 && p.AuxH && has_acc && ti.i0 + BM <= p.m && ti.j0 + BN <= p.n) {
+      if (F16 && (p.epi_mode == 3 || p.epi_mode == 4) && p.AuxH && has_acc && ti.i0 + BM <= p.m && ti.j0 + BN <= p.n) {
         // while the MMAs of this tile run: pull this warp's part of the Aux planes (32 rows x 128 columns x 2 planes) into L2
         const __half* ah = p.AuxH + (int64_t)ti.b * p.sD + (int64_t)(ti.i0 + q * 32 + lane) * p.ldd + ti.j0 + c_begin * 32;
         const __half* al = p.AuxL + (int64_t)ti.b * p.sD + (int64_t)(ti.i0 + q * 32 + lane) * p.ldd + ti.j0 + c_begin * 32;
@@ -566,6 +583,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       if (p.sb) alpha_b *= 1.0f / p.sb[ti.b];
       const float sd_b = (p.Dh && p.sd) ? p.sd[ti.b] : 1.0f;
       const float inv_saux = (p.AuxH && p.saux) ? 1.0f / p.saux[ti.b] : 1.0f;
+      const float sd2_b = (p.D2h && p.sd2) ? p.sd2[ti.b] : 1.0f;
       float amx = 0.f;
       if (F16 && has_acc && vec_ok && p.splitk == 1 && p.d_tri == 0 && !p.Cin && !p.Dlo && ti.i0 + BM <= p.m && ti.j0 + BN <= p.n) {
         // tile completely inside the matrix: specialised, branch-free inner loops
@@ -573,7 +591,9 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         bool done = true;
         if (p.epi_mode == 1 && p.Dh && !p.D) epilogue_tile_fast<1, false, true>(p, ti.b, ti.i0, ti.j0, q, lane, c_begin, tacc, epi, alpha_b, sd_b, inv_saux, amx);
         else if (p.epi_mode == 2 && p.D && !p.Dh) epilogue_tile_fast<2, true, false>(p, ti.b, ti.i0, ti.j0, q, lane, c_begin, tacc, epi, alpha_b, sd_b, inv_saux, amx);
+        else if (p.epi_mode == 2 && p.Dh && !p.D) epilogue_tile_fast<2, false, true>(p, ti.b, ti.i0, ti.j0, q, lane, c_begin, tacc, epi, alpha_b, sd_b, inv_saux, amx);
         else if (p.epi_mode == 3 && p.AuxH && p.Dh && !p.D) epilogue_tile_fast<3, false, true>(p, ti.b, ti.i0, ti.j0, q, lane, c_begin, tacc, epi, alpha_b, sd_b, inv_saux, amx);
+        else if (p.epi_mode == 4 && p.AuxH && p.Dh && !p.D && p.D2h) epilogue_tile_fast<4, false, true>(p, ti.b, ti.i0, ti.j0, q, lane, c_begin, tacc, epi, alpha_b, sd_b, inv_saux, amx, sd2_b);
         else if (p.epi_mode == 0 && p.D && !p.Dh) epilogue_tile_fast<0, true, false>(p, ti.b, ti.i0, ti.j0, q, lane, c_begin, tacc, epi, alpha_b, sd_b, inv_saux, amx);
         else if (p.epi_mode == 0 && p.Dh && !p.D) epilogue_tile_fast<0, false, true>(p, ti.b, ti.i0, ti.j0, q, lane, c_begin, tacc, epi, alpha_b, sd_b, inv_saux, amx);
         else done = false;
@@ -637,7 +657,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           const int cq = (lane & 7) * 4;
           float4 cs1 = make_float4(0.f, 0.f, 0.f, 0.f), cs2 = make_float4(0.f, 0.f, 0.f, 0.f);
           float4 cv1 = cs1, cv2 = cs1;
-          if (p.epi_mode == 3) {
+          if (p.epi_mode == 3 || p.epi_mode == 4) {
             cv1 = *reinterpret_cast<const float4*>(p.colv1 + (int64_t)ti.b * p.n + gj0 + cq);
             cv2 = *reinterpret_cast<const float4*>(p.colv2 + (int64_t)ti.b * p.n + gj0 + cq);
           }
@@ -651,7 +671,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
               const float4 cc = *reinterpret_cast<const float4*>(p.Cin + o);
               v.x += cc.x; v.y += cc.y; v.z += cc.z; v.w += cc.w;
             }
-            if (p.epi_mode == 3) {
+            if (p.epi_mode == 3 || p.epi_mode == 4) {
               float4 ax;
               if (p.AuxH) {
                 const uint2 hh = *reinterpret_cast<const uint2*>(p.AuxH + o);
@@ -662,10 +682,24 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 ax = *reinterpret_cast<const float4*>(p.Aux + o);
               }
               const float qv = qreg[itr];
-              v.x += fmaf(qv, cv2.x, -2.f * ax.x * cv1.x);
-              v.y += fmaf(qv, cv2.y, -2.f * ax.y * cv1.y);
-              v.z += fmaf(qv, cv2.z, -2.f * ax.z * cv1.z);
-              v.w += fmaf(qv, cv2.w, -2.f * ax.w * cv1.w);
+              if (p.epi_mode == 3) {
+                v.x += fmaf(qv, cv2.x, -2.f * ax.x * cv1.x);
+                v.y += fmaf(qv, cv2.y, -2.f * ax.y * cv1.y);
+                v.z += fmaf(qv, cv2.z, -2.f * ax.z * cv1.z);
+                v.w += fmaf(qv, cv2.w, -2.f * ax.w * cv1.w);
+              } else {
+                v.x = fmaf(2.f * cv1.x, v.x - ax.x, qv * cv2.x);
+                v.y = fmaf(2.f * cv1.y, v.y - ax.y, qv * cv2.y);
+                v.z = fmaf(2.f * cv1.z, v.z - ax.z, qv * cv2.z);
+                v.w = fmaf(2.f * cv1.w, v.w - ax.w, qv * cv2.w);
+                if (p.D2h) {
+                  uint2 qh, ql;
+                  split_half2(2.f * cv1.x * ax.x * sd2_b, 2.f * cv1.y * ax.y * sd2_b, qh.x, ql.x);
+                  split_half2(2.f * cv1.z * ax.z * sd2_b, 2.f * cv1.w * ax.w * sd2_b, qh.y, ql.y);
+                  *reinterpret_cast<uint2*>(p.D2h + o) = qh;
+                  *reinterpret_cast<uint2*>(p.D2l + o) = ql;
+                }
+              }
               float rp = ax.x * cv2.x + ax.y * cv2.y + ax.z * cv2.z + ax.w * cv2.w;
               rp += __shfl_xor_sync(0xffffffffu, rp, 1);
               rp += __shfl_xor_sync(0xffffffffu, rp, 2);
@@ -724,11 +758,22 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             if ((p.d_tri == 1 && gj > gi) || (p.d_tri == 2 && gj < gi)) continue;
             float v = alpha_b * __uint_as_float(r[u]);
             if (p.Cin) v += p.Cin[row_off + gj];
-            if (p.epi_mode == 3) {
+            if (p.epi_mode == 3 || p.epi_mode == 4) {
               const float ax = p.AuxH ? (__half2float(p.AuxH[row_off + gj]) + __half2float(p.AuxL[row_off + gj])) * inv_saux
                                       : p.Aux[row_off + gj];
               const float g2 = p.colv2[(int64_t)ti.b * p.n + gj];
-              v += fmaf(q_s, g2, -2.f * ax * p.colv1[(int64_t)ti.b * p.n + gj]);
+              const float g1 = p.colv1[(int64_t)ti.b * p.n + gj];
+              if (p.epi_mode == 3) {
+                v += fmaf(q_s, g2, -2.f * ax * g1);
+              } else {
+                v = fmaf(2.f * g1, v - ax, q_s * g2);
+                if (p.D2h) {
+                  __half h2, l2;
+                  split_half(2.f * g1 * ax * sd2_b, h2, l2);
+                  p.D2h[row_off + gj] = h2;
+                  p.D2l[row_off + gj] = l2;
+                }
+              }
               racc_s = fmaf(ax, g2, racc_s);
             } else if (p.epi_mode != 0) {
               atomicAdd(p.col1 + (int64_t)ti.b * p.n + gj, v * v);
@@ -746,7 +791,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           }
         }
       }
-      if (p.epi_mode == 3) {
+      if (p.epi_mode == 3 || p.epi_mode == 4) {
         if ((lane & 7) == 0) {
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
@@ -989,7 +1034,8 @@ int umma_gemm_ex(int b_kmajor, int m, int n, int k, float alpha, const float* A,
   p.D = D; p.Dlo = Dlo; p.Cin = Cin; p.m = m; p.n = n; p.k = k; p.ldd = ldd; p.sD = sD; p.batch = batch; p.splitk = splitk;
   p.a_tri = a_tri; p.b_tri = b_tri; p.d_tri = d_tri; p.n_terms = n_terms; p.alpha = alpha;
   p.bk = BK; p.sa = nullptr; p.sb = nullptr; p.Dh = nullptr; p.Dl = nullptr; p.sd = nullptr; p.amax = nullptr;
-  p.AuxH = nullptr; p.AuxL = nullptr; p.saux = nullptr;
+  p.AuxH = nullptr; p.AuxL = nullptr; p.saux = nullptr; p.D2h = nullptr; p.D2l = nullptr; p.sd2 = nullptr;
+  if (p.epi_mode == 4) return GPZ_ERR_BADARG;            // split-FP16 only
   return launch_gemm(b_kmajor != 0, false, mA, mAlo, mB, mBlo, p, (cudaStream_t)stream);
 }
 
@@ -1039,7 +1085,8 @@ int umma_gemm16_ex(const Umma16Args& g, void* stream) {
   p.D = g.D; p.Dlo = nullptr; p.Cin = g.Cin; p.m = g.m; p.n = g.n; p.k = g.k; p.ldd = g.ldd; p.sD = g.sD; p.batch = g.batch;
   p.splitk = splitk; p.a_tri = g.a_tri; p.b_tri = g.b_tri; p.d_tri = g.d_tri; p.n_terms = g.n_terms == 1 ? 1 : 3; p.alpha = g.alpha;
   p.bk = BK16; p.sa = g.sa; p.sb = g.sb; p.Dh = g.Dh; p.Dl = g.Dl; p.sd = g.sd; p.amax = g.amax;
-  p.AuxH = g.AuxH; p.AuxL = g.AuxL; p.saux = g.saux;
+  p.AuxH = g.AuxH; p.AuxL = g.AuxL; p.saux = g.saux; p.D2h = g.D2h; p.D2l = g.D2l; p.sd2 = g.sd2;
+  if (p.epi_mode == 4 && (!p.AuxH || !p.D2h || !p.D2l)) return GPZ_ERR_BADARG;
   return launch_gemm(g.b_kmajor != 0, true, mA, mAlo, mB, mBlo, p, (cudaStream_t)stream);
 }
 

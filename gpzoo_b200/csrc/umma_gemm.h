@@ -29,6 +29,7 @@ struct Umma16Args {
   int batch, a_tri, d_tri, splitk, n_terms;
   const UmmaEpilogue* epi;                                                  // fused epilogue (mode 3 may use AuxH/AuxL)
   const __half* AuxH; const __half* AuxL; const float* saux;
+  __half* D2h; __half* D2l; const float* sd2;                               // epilogue mode 4: second fp16-plane output
 };
 int umma_gemm16_ex(const Umma16Args& args, void* stream);
 

@@ -595,19 +595,18 @@ class PredictH(Function):
         dt = Linv.dtype
         L, M, N = Kh.shape
         dev = Kh.device
-        Ah, Al = torch.empty_like(Kh), torch.empty_like(Kh)
-        C = torch.empty((L, M, N), dtype=dt, device=dev)
+        Ah, Al, Ch, Cl = (torch.empty_like(Kh) for _ in range(4))
         mean = torch.empty((L, N), dtype=dt, device=dev)
         var = torch.empty_like(mean)
         ws_h = torch.empty(8 * L * M * M, dtype=torch.float16, device=dev)
         ws_f = torch.empty(2 * L * N + 16 * L, dtype=dt, device=dev)
-        call("svgp_predict_fwd_h", dt, ptr(Kh), ptr(Kl), ptr(sK), ptr(Linv), ptr(T), ptr(q), ptr(Kxx), ptr(Ah), ptr(Al), ptr(C),
-             ptr(mean), ptr(var), ptr(ws_h), ptr(ws_f), c_i(M), c_i(N), c_i(L))
-        ctx.save_for_backward(Kh, Kl, sK, Linv, T, q, Ah, Al, C, ws_h, ws_f)
+        call("svgp_predict_fwd_h", dt, ptr(Kh), ptr(Kl), ptr(sK), ptr(Linv), ptr(T), ptr(q), ptr(Kxx), ptr(Ah), ptr(Al), ptr(Ch),
+             ptr(Cl), ptr(mean), ptr(var), ptr(ws_h), ptr(ws_f), c_i(M), c_i(N), c_i(L))
+        ctx.save_for_backward(Kh, Kl, sK, Linv, T, q, Ah, Al, Ch, Cl, ws_h, ws_f)
         # tracked max |A|, max |C| (slots 7, 8 of the stats block, csrc/predict.cu): examined lazily with the Cholesky info
         st = ws_f[2 * L * N:].view(-1, L)
-        r_sA, r_aA, r_aC = (_stat_row(i) for i in (0, 1, 2))
-        _pending_amax.append((torch.stack((st[r_aA], st[r_aC])), torch.stack((st[r_sA], torch.ones_like(st[r_sA]))), ("A", "C")))
+        r_sA, r_aA, r_aC, r_sC = (_stat_row(i) for i in (0, 1, 2, 5))
+        _pending_amax.append((torch.stack((st[r_aA], st[r_aC])), torch.stack((st[r_sA], st[r_sC])), ("A", "C")))
         if len(_pending_amax) > 64:
             _fold_pending_amax()
         if SYNC_CHECKS:
@@ -617,19 +616,19 @@ class PredictH(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, gm, gv):
-        Kh, Kl, sK, Linv, T, q, Ah, Al, C, ws_h, ws_f = ctx.saved_tensors
+        Kh, Kl, sK, Linv, T, q, Ah, Al, Ch, Cl, ws_h, ws_f = ctx.saved_tensors
         dt = Linv.dtype
         L, M, N = Kh.shape
         dev = Kh.device
         gm = _c(gm) if gm is not None else torch.zeros((L, N), dtype=dt, device=dev)
         gv = _c(gv) if gv is not None else torch.zeros((L, N), dtype=dt, device=dev)
-        gCh, gCl, gAh, gAl = (torch.empty_like(Kh) for _ in range(4))
+        AWh, AWl, gAh, gAl = (torch.empty_like(Kh) for _ in range(4))
         gKzx = torch.empty((L, M, N), dtype=dt, device=dev)
         gLinv = torch.zeros_like(Linv)
         gT = torch.zeros_like(T)
         gq = torch.empty_like(q)
-        call("svgp_predict_bwd_h", dt, ptr(Kh), ptr(Kl), ptr(sK), ptr(T), ptr(q), ptr(Ah), ptr(Al), ptr(C), ptr(gm), ptr(gv),
-             ptr(gCh), ptr(gCl), ptr(gAh), ptr(gAl), ptr(gKzx), ptr(gLinv), ptr(gT), ptr(gq), ptr(ws_h), ptr(ws_f),
+        call("svgp_predict_bwd_h", dt, ptr(Kh), ptr(Kl), ptr(sK), ptr(T), ptr(q), ptr(Ah), ptr(Al), ptr(Ch), ptr(Cl), ptr(gm), ptr(gv),
+             ptr(AWh), ptr(AWl), ptr(gAh), ptr(gAl), ptr(gKzx), ptr(gLinv), ptr(gT), ptr(gq), ptr(ws_h), ptr(ws_f),
              c_i(M), c_i(N), c_i(L))
         st = ws_f[2 * L * N:].view(-1, L)
         _pending_amax.append((st[_stat_row(4)].unsqueeze(0), st[_stat_row(3)].unsqueeze(0), ("dL/dA",)))   # max |gA| vs its scale

@@ -215,22 +215,24 @@ int gpz_umma_gemm16_f32(int b_kmajor, int m, int n, int k, float alpha, const vo
 /* split-FP16 K1 forward and SVGP predictive op (the default fp32 hot path; csrc/kernel_build.cu, csrc/predict.cu):
  *      kernel_build_fwd_h writes K as fp16 planes (out_h + out_l ~= K * out_scale[l], 4 bytes per entry) instead of fp32;
  *      predict_fwd_h / predict_bwd_h are gpz_svgp_predict_fwd/bwd (gp.py:218-225, utilities.py:382-397 and their autograd)
- *      on those planes: A, gC, gA travel as fp16 planes as well, C, gKzx, gLinv, gT, gq, mean, var are fp32.
+ *      on those planes: A, C, gA and AW = A diag(2 gv) (scratch of the backward) travel as fp16 planes as well; gKzx, gLinv, gT,
+ *      gq, mean, var are fp32.  The backward never forms gC = C diag(2 gv): gA = 2 gv o (T C - A) + q gm^T comes straight from
+ *      the unweighted C planes (column weights commute out of the product), gT = tril(AW C^T).
  *      ws_h: 8 L M M halfs, ws_f: 2 L N + 16 L floats, both written by fwd and read by bwd; gT and gLinv zero-initialised. */
 int gpz_kernel_build_fwd_h_f32(const float* x1, const float* x2, const float* sigma, const float* ls, const float* a,
                                const float* r2, const int64_t* g1, const int64_t* g2, int n1, int n2, int D, int L, int ng, int kind,
                                float p_half, float jitter, void* out_h, void* out_l, float* out_scale, void* stream);
 int gpz_svgp_predict_h_supported(int M, int N);
-/* row (of L floats, counted from ws_f + 2 L N) of: 0 scale of A, 1 max|A|, 2 max|C|, 3 scale of gA, 4 max|gA| — what the
- * host-side overflow guard of the fp16 planes reads */
+/* row (of L floats, counted from ws_f + 2 L N) of: 0 scale of A, 1 max|A|, 2 max|C|, 3 scale of gA, 4 max|gA|, 5 scale of C —
+ * what the host-side overflow guard of the fp16 planes reads */
 int gpz_svgp_predict_h_stat_row(int which);
 int gpz_svgp_predict_fwd_h_f32(const void* Kh, const void* Kl, const float* sK, const float* Linv, const float* T, const float* q,
-                               const float* kxx, void* Ah, void* Al, float* C, float* mean, float* var, void* ws_h, float* ws_f,
-                               int M, int N, int L, void* stream);
+                               const float* kxx, void* Ah, void* Al, void* Ch, void* Cl, float* mean, float* var, void* ws_h,
+                               float* ws_f, int M, int N, int L, void* stream);
 int gpz_svgp_predict_bwd_h_f32(const void* Kh, const void* Kl, const float* sK, const float* T, const float* q, const void* Ah,
-                               const void* Al, const float* C, const float* gm, const float* gv, void* gCh, void* gCl, void* gAh,
-                               void* gAl, float* gKzx, float* gLinv, float* gT, float* gq, void* ws_h, float* ws_f, int M, int N,
-                               int L, void* stream);
+                               const void* Al, const void* Ch, const void* Cl, const float* gm, const float* gv, void* AWh, void* AWl,
+                               void* gAh, void* gAl, float* gKzx, float* gLinv, float* gT, float* gq, void* ws_h, float* ws_f, int M,
+                               int N, int L, void* stream);
 
 /* ---- training-step update: multi-tensor Adam in one launch (torch.optim.Adam without weight decay /
  *      amsgrad; utilities.py:621 optimizer.step()) with the reference's post-step clamp W.clamp_(min=0) (utilities.py:623) fused in
