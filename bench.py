@@ -381,6 +381,8 @@ def run_ours(args):
             errs = {n: rel(g, p.grad) for n, g, p in zip(names, got, sh1)}
             errs["elbo"] = rel(total, e1.detach())
             dp_parity = dict(rel_err_vs_1gpu=errs, tol=1e-4, ok=bool(max(errs.values()) < 1e-4))
+            if not dp_parity["ok"]:
+                dp_parity["norms"] = {n: (float(g.norm()), float(p.grad.norm())) for n, g, p in zip(names, got, sh1)}
             del m1, sh1, e1
             assert dp_parity["ok"], dp_parity
 
@@ -389,6 +391,10 @@ def run_ours(args):
     # training loop); every upload and every read-back lies inside the timed region: n steps = n uploads + n read-backs.
     ms_e2e, h2d = None, 0
     if not args.no_e2e and not minibatched:     # (configs 4/5 keep their shard resident and index minibatches on the device)
+        # The landing buffers below are written on the copy stream; the allocator hands them out in main-stream order, so they
+        # may be memory that still-queued main-stream work (a rank that runs ahead of its peers has whole steps queued behind an
+        # all-reduce) has not finished with.  Drain everything first.
+        barrier()
         copy_stream = torch.cuda.Stream(device=dev)
         hX, hy = st["hX"], st["hy"]
         dbuf = [(torch.empty_like(st["X"]), torch.empty_like(st["y"])) for _ in range(2)]
