@@ -266,6 +266,9 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     functional.set_sync_checks(False)          # Cholesky info / overflow guards are checked once, after the timed region
+    shard_chain = world > 1 and not args.no_chain_shard
+    if shard_chain:                            # the replicated O(M^3) chain's backward runs factor-sharded over the ranks
+        functional.set_chain_sharding(dist.group.WORLD)
     dt = torch.float32
     c = CONFIGS[args.config]
     kind = c["kind"]
@@ -373,9 +376,12 @@ def run_ours(args):
         got = [p.grad.detach().clone() for p in st["shared"]]
         if rank == 0:
             full = dict(st["prob"])
+            functional.set_chain_sharding(None)          # the reference step is computed by this rank alone
             m1, sh1 = build_model(c, full, dt, dev)
             e1 = m1.elbo(full["X"].to(dev), full["y"].to(dev), E=c["E"], eps=full["eps"].to(dev))
             (-e1).backward()
+            if shard_chain:
+                functional.set_chain_sharding(dist.group.WORLD)
             rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-300))
             names = ["Z", "sigma", "lengthscale", "mu", "Lu", "W"]
             errs = {n: rel(g, p.grad) for n, g, p in zip(names, got, sh1)}
@@ -512,7 +518,8 @@ def run_ours(args):
                 warmup=warm, ms_per_step=ms, higher_is_better=True, scaling=main_mode, vs_baseline=None, dtype="f32", data="synthetic",
                 config=cfg,
                 run=dict(spots_per_gpu=n_loc, global_spots_per_step=spots, spots_per_s=spots * 1e3 / ms,
-                         parallelism=f"dp{world} over spots, 1 NCCL all-reduce/step",
+                         parallelism=f"dp{world} over spots, 1 NCCL all-reduce/step" + (
+                             "; backward of the replicated O(M^3) chain sharded by factor (1 all-to-all)" if shard_chain else ""),
                          l2="inputs larger than L2 (y %.0f MB, Kzx planes %.2f GB per GPU)" % (4e-6 * G * n_loc, 4e-9 * L * M * n_loc),
                          e2e="per step: X, y of the rank's spots uploaded from pinned host memory on a copy stream (double buffered) + "
                              "loss read back to the host with one-step lag"),
@@ -577,6 +584,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling leg")
+    ap.add_argument("--no-chain-shard", action="store_true", help="N > 1: every rank runs the whole O(M^3) backward (A/B)")
     ap.add_argument("--N", type=int, default=None, help="override the number of spots of config 2 (debugging only)")
     args = ap.parse_args()
     if args.N:

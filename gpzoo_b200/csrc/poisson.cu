@@ -421,6 +421,265 @@ __global__ void __launch_bounds__(P2_THREADS, sizeof(T) == 4 ? 4 : 1) poisson_ke
   if (tid == 0) a.ll_part[blockIdx.y * gridDim.x + blockIdx.x] = tot;
 }
 
+// ---- v3 (fp32): the v2 scheme on packed fp32x2 FMAs -------------------------------------------------------------------------
+// The kernel is bound by instruction issue, not by HBM (v2: 113 instructions per (gene, spot) element, 232 M warp instructions
+// per launch at config 2).  Blackwell issues one 3-register FFMA per two cycles and scheduler, but FFMA2 (fma.rn.f32x2) does
+// two fp32 FMAs per instruction, so the three F-long contractions per element (rate, d/dF, d/dW) run on pairs of factors:
+// F = 10 -> 5 FFMA2 each, no padding to 12.  On top of that
+//   * ef' = softplus(V_n) exp(F) is formed once per spot, so the rate is the contraction itself and t' = (y / r - 1) / E;
+//   * sum_g r (for the log-likelihood and for d/dV) is sum_f ef'_f * (sum_g w_gf): one short contraction per 32-gene chunk
+//     instead of two adds per element;
+//   * log(y!) comes from a 64-entry table for integer counts (anything else takes the exact lgamma).
+// Same outputs, workspace layout and grid as v2.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                     rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+
+template <int FP>       // FP = pairs of factors held per thread (F <= 2 FP)
+__global__ void __launch_bounds__(P2_THREADS, 4) poisson_kernel3(const PoissonArgs<float> a) {
+  constexpr int FPP = (FP + 1) & ~1;      // pairs per shared-memory row, padded to 16-byte multiples
+  extern __shared__ __align__(16) unsigned char pz_smem[];
+  typedef float RowT[P2_SPOTS + 1];
+  typedef float2 RowP[FPP];
+  RowT* tS = reinterpret_cast<RowT*>(pz_smem);                                           // [PZ_GCH][P2_SPOTS+1]  t' = (y/r - 1)/E
+  RowP* efS = reinterpret_cast<RowP*>(pz_smem + ((sizeof(float) * PZ_GCH * (P2_SPOTS + 1) + 15) / 16) * 16);   // [P2_SPOTS][FPP]
+  RowP* sW = efS + P2_SPOTS;                                                             // [PZ_GCH][FPP]
+  RowP* sAcc = sW + PZ_GCH;                                                              // [4 * PZ_GCH][FPP]
+  float2* sWsum = reinterpret_cast<float2*>(sAcc + 4 * PZ_GCH);                          // [FPP]  sum over the chunk's genes
+  __shared__ double red[32];
+  __shared__ float lfact[64];                   // log(y!) for integer counts y < 64
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 64) lfact[tid] = lgammaf((float)(tid + 1));
+  const int n0 = blockIdx.x * P2_SPOTS;
+  int nn[2]; bool act[2]; int64_t col[2]; float spV[2], vraw[2], ysum[2], rsum[2];
+#pragma unroll
+  for (int s2 = 0; s2 < 2; ++s2) {
+    nn[s2] = n0 + s2 * P2_THREADS + tid;
+    act[s2] = nn[s2] < a.B;
+    col[s2] = act[s2] ? (a.idx ? a.idx[nn[s2]] : (int64_t)nn[s2]) : 0;
+    vraw[s2] = act[s2] ? a.V[col[s2]] : 0.f;
+    spV[s2] = act[s2] ? softplus(vraw[s2]) : 0.f;
+    ysum[s2] = 0.f; rsum[s2] = 0.f;
+  }
+  const bool block_full = n0 + P2_SPOTS <= a.B;
+  const float invE = 1.f / (float)a.E;
+  const int g_begin = blockIdx.y * a.genes_per_cta;
+  const int g_end = min(a.G, g_begin + a.genes_per_cta);
+  double ll = 0.0;
+  constexpr float LN2 = 0.69314718055994530942f;
+
+  float ynext[PZ_GRP][2];
+  auto prefetch = [&](int gfirst) {
+#pragma unroll
+    for (int u = 0; u < PZ_GRP; ++u)
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2)
+        ynext[u][s2] = (act[s2] && gfirst + u < g_end) ? __ldcs(a.y + (int64_t)(gfirst + u) * a.y_ld + col[s2]) : 0.f;
+  };
+  prefetch(g_begin);
+
+  for (int e = 0; e < a.E; ++e) {
+    float2 ef[2][FP], pg[2][FP];
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+      for (int fp = 0; fp < FP; ++fp) {
+        pg[s2][fp] = make_float2(0.f, 0.f);
+        float v[2] = {0.f, 0.f};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int f = 2 * fp + h;
+          if (f < a.F && act[s2]) {
+            const int64_t o = (int64_t)f * a.B + nn[s2];
+            const float sp = a.spread[o];
+            const float sd = f < a.n_var ? sqrtf(sp > a.clamp_min ? sp : a.clamp_min) : sp;
+            v[h] = spV[s2] * expf(fmaf(a.eps[((int64_t)e * a.F + f) * a.B + nn[s2]], sd, a.mean[o]));
+          }
+        }
+        ef[s2][fp] = make_float2(v[0], v[1]);
+      }
+    __syncthreads();                               // phase B of the previous sample finished with efS
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2) {
+#pragma unroll
+      for (int fp = 0; fp < FP; ++fp) efS[s2 * P2_THREADS + tid][fp] = ef[s2][fp];
+      if (FPP > FP) efS[s2 * P2_THREADS + tid][FPP - 1] = make_float2(0.f, 0.f);
+    }
+
+    for (int g0 = g_begin; g0 < g_end; g0 += PZ_GCH) {
+      __syncthreads();                             // previous chunk's phase B / flush finished with sW, tS, sAcc
+      for (int i = tid; i < PZ_GCH * FPP; i += P2_THREADS) {
+        const int gi = i / FPP, fp = i % FPP;
+        float w[2] = {0.f, 0.f};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int f = 2 * fp + h;
+          if (g0 + gi < g_end && f < a.F) {
+            w[h] = a.W[(int64_t)(g0 + gi) * a.F + f];
+            if (a.w_softplus) w[h] = softplus(w[h]);
+          }
+        }
+        sW[gi][fp] = make_float2(w[0], w[1]);
+      }
+      __syncthreads();
+      if (tid < FPP) {                             // column sums of the chunk's loadings
+        float2 sacc = make_float2(0.f, 0.f);
+        for (int gi = 0; gi < PZ_GCH; ++gi) { const float2 w = sW[gi][tid]; sacc.x += w.x; sacc.y += w.y; }
+        sWsum[tid] = sacc;
+      }
+      // ---- phase A: thread = two spots ----
+      float llc = 0.f;
+#pragma unroll 1
+      for (int gb = 0; gb < PZ_GCH; gb += PZ_GRP) {
+        float yv[PZ_GRP][2];
+#pragma unroll
+        for (int u = 0; u < PZ_GRP; ++u) { yv[u][0] = ynext[u][0]; yv[u][1] = ynext[u][1]; }
+        {
+          int gn = g0 + gb + PZ_GRP;               // first gene of the next group in (sample, chunk, group) order
+          if (gb + PZ_GRP == PZ_GCH && g0 + PZ_GCH >= g_end) gn = (e + 1 < a.E) ? g_begin : g_end;
+          prefetch(gn);
+        }
+        auto body = [&](auto guard, int u) {
+          constexpr bool GUARD = decltype(guard)::value;
+          const int gi = gb + u;
+          float2 wrow[FPP];
+#pragma unroll
+          for (int i = 0; i < FPP / 2; ++i) {
+            const float4 v = reinterpret_cast<const float4*>(&sW[gi][0])[i];
+            wrow[2 * i] = make_float2(v.x, v.y); wrow[2 * i + 1] = make_float2(v.z, v.w);
+          }
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2) {
+            float t = 0.f;
+            if (!GUARD || (act[s2] && g0 + gi < g_end)) {
+              const float y = yv[u][s2];
+              float2 z = make_float2(0.f, 0.f);
+#pragma unroll
+              for (int fp = 0; fp < FP; ++fp) z = ffma2(wrow[fp], ef[s2][fp], z);
+              const float r = z.x + z.y;                                  // rate (softplus(V) is inside ef)
+              const float ylog = (y * LN2) * __log2f(r);
+              float lp = y == 0.f ? 0.f : ylog;
+              if (a.with_lgamma) {
+                const int yi = (int)y;
+                lp -= (yi >= 0 && yi < 64 && (float)yi == y) ? lfact[yi] : lgammaf(y + 1.f);
+              }
+              llc += lp;
+              ysum[s2] += y;
+              t = fmaf(y * invE, __frcp_rn(r), -invE);                    // (y / r - 1) / E
+              const float2 t2 = make_float2(t, t);
+#pragma unroll
+              for (int fp = 0; fp < FP; ++fp) pg[s2][fp] = ffma2(wrow[fp], t2, pg[s2][fp]);
+            }
+            tS[gi][s2 * P2_THREADS + tid] = t;
+          }
+        };
+        if (block_full && g0 + PZ_GCH <= g_end) {
+#pragma unroll
+          for (int u = 0; u < PZ_GRP; ++u) body(std::false_type{}, u);
+        } else {
+#pragma unroll 1
+          for (int u = 0; u < PZ_GRP; ++u) body(std::true_type{}, u);
+        }
+      }
+      __syncthreads();
+      // sum over the chunk's genes of the rate, per spot: sum_f ef'_f * Wsum_f
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        float2 z = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int fp = 0; fp < FP; ++fp) z = ffma2(sWsum[fp], ef[s2][fp], z);
+        rsum[s2] += z.x + z.y;
+        llc -= act[s2] ? (z.x + z.y) : 0.f;
+      }
+      ll += (double)(llc * invE);
+      // ---- phase B: lane = gene, warp = a quarter (64) of the spots ----
+      float2 acc[FP];
+#pragma unroll
+      for (int fp = 0; fp < FP; ++fp) acc[fp] = make_float2(0.f, 0.f);
+      const int nb = warp * 64;
+#pragma unroll 4
+      for (int k = 0; k < 64; ++k) {
+        const float t = tS[lane][nb + k];
+        const float2 t2 = make_float2(t, t);
+        float2 erow[FPP];
+#pragma unroll
+        for (int i = 0; i < FPP / 2; ++i) {
+          const float4 v = reinterpret_cast<const float4*>(&efS[nb + k][0])[i];
+          erow[2 * i] = make_float2(v.x, v.y); erow[2 * i + 1] = make_float2(v.z, v.w);
+        }
+#pragma unroll
+        for (int fp = 0; fp < FP; ++fp) acc[fp] = ffma2(t2, erow[fp], acc[fp]);
+      }
+#pragma unroll
+      for (int fp = 0; fp < FP; ++fp) sAcc[warp * PZ_GCH + lane][fp] = acc[fp];
+      __syncthreads();
+      for (int i = tid; i < PZ_GCH * a.F; i += P2_THREADS) {
+        const int gi = i / a.F, f = i % a.F;
+        if (g0 + gi < g_end) {
+          float* dst = a.gW_part + ((int64_t)blockIdx.x * a.G + g0 + gi) * a.F + f;
+          float v = 0.f;
+#pragma unroll
+          for (int w4 = 0; w4 < 4; ++w4) {
+            const float2 pr = sAcc[w4 * PZ_GCH + gi][f >> 1];
+            v += (f & 1) ? pr.y : pr.x;
+          }
+          *dst = e == 0 ? v : *dst + v;
+        }
+      }
+    }
+    // ---- per-sample epilogue: d ll / d mean, d ll / d spread ----
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2) {
+      if (!act[s2]) continue;
+#pragma unroll
+      for (int fp = 0; fp < FP; ++fp) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int f = 2 * fp + h;
+          if (f < a.F) {
+            const int64_t o = (int64_t)f * a.B + nn[s2];
+            const float gF = h ? ef[s2][fp].y * pg[s2][fp].y : ef[s2][fp].x * pg[s2][fp].x;
+            float gsp = gF * a.eps[((int64_t)e * a.F + f) * a.B + nn[s2]];
+            if (f < a.n_var) {                       // spread is a variance: d sd / d var = 1 / (2 sd) where not clamped
+              const float sp = a.spread[o];
+              gsp = sp >= a.clamp_min ? gsp / (2.f * sqrtf(sp)) : 0.f;
+            }
+            if (a.atomic_out) { atomicAdd(a.gmean + o, gF); atomicAdd(a.gspread + o, gsp); }
+            else if (e == 0) { a.gmean[o] = gF; a.gspread[o] = gsp; }
+            else { a.gmean[o] += gF; a.gspread[o] += gsp; }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int s2 = 0; s2 < 2; ++s2) {
+    if (act[s2]) {
+      // d ll / d V = softplus'(V) / softplus(V) * mean_e sum_g (y - r);  ysum was accumulated once per sample
+      const float gv = softplus_grad(vraw[s2]) * (ysum[s2] - rsum[s2]) * invE / spV[s2];
+      if (a.atomic_out) atomicAdd(a.gV + nn[s2], gv); else a.gV[nn[s2]] = gv;
+    }
+  }
+  const double tot = block_sum<double>(ll, red);
+  if (tid == 0) a.ll_part[blockIdx.y * gridDim.x + blockIdx.x] = tot;
+}
+
+template <int FP> constexpr size_t poisson_smem3() {
+  constexpr int FPP = (FP + 1) & ~1;
+  return ((sizeof(float) * PZ_GCH * (P2_SPOTS + 1) + 15) / 16) * 16 + sizeof(float2) * FPP * (P2_SPOTS + PZ_GCH + 4 * PZ_GCH + 1);
+}
+template <int FP> int poisson_launch3(const PoissonArgs<float>& a, dim3 grid, cudaStream_t st) {
+  constexpr size_t smem = poisson_smem3<FP>();
+  GPZ_CUDA(cudaFuncSetAttribute(poisson_kernel3<FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  poisson_kernel3<FP><<<grid, P2_THREADS, smem, st>>>(a);
+  GPZ_CHECK_LAUNCH();
+  return GPZ_OK;
+}
+
 // gW[g,f] = (softplus'(W[g,f]) or 1) * sum_b gW_part[b,g,f]
 template <typename T>
 __global__ void poisson_gw_reduce_kernel(const T* __restrict__ part, const T* __restrict__ W, T* __restrict__ gW, int64_t GF, int nb,
@@ -446,13 +705,14 @@ template <typename T, int FMAX> constexpr size_t poisson_smem() {
 template <typename T, int FMAX> constexpr size_t poisson_smem2() {
   return ((sizeof(T) * PZ_GCH * (P2_SPOTS + 1) + 15) / 16) * 16 + sizeof(T) * (FMAX * P2_SPOTS + PZ_GCH * FMAX + 4 * PZ_GCH * FMAX);
 }
-static int poisson_version() {
+static int poisson_version() {          // GPZ_POISSON_V: 1 = thread-per-spot kernel, 2 = two spots per thread, 3 = 2 on packed fp32x2 FMAs (fp32 only; measured equal to 2: the kernel is bound by bookkeeping instructions, not by the FMAs)
   static int v = -1;
   if (v < 0) { const char* e = getenv("GPZ_POISSON_V"); v = e ? atoi(e) : 2; }
   return v;
 }
+static bool poisson_v2_forced() { return poisson_version() == 2; }
 template <typename T, int FMAX> int poisson_launch(const PoissonArgs<T>& a, dim3 grid, cudaStream_t st) {
-  if (poisson_version() == 2) {
+  if (poisson_version() >= 2) {
     constexpr size_t smem = poisson_smem2<T, FMAX>();
     GPZ_CUDA(cudaFuncSetAttribute(poisson_kernel2<T, FMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     poisson_kernel2<T, FMAX><<<grid, P2_THREADS, smem, st>>>(a);
@@ -466,7 +726,7 @@ template <typename T, int FMAX> int poisson_launch(const PoissonArgs<T>& a, dim3
 }
 
 static void poisson_grid(int G, int B, int* nbx, int* nby, int* gpc) {
-  *nbx = (int)cdiv(B, poisson_version() == 2 ? P2_SPOTS : PZ_SPOTS);
+  *nbx = (int)cdiv(B, poisson_version() >= 2 ? P2_SPOTS : PZ_SPOTS);
   const int chunks = (int)cdiv(G, PZ_GCH);
   int by = 1;
   if (*nbx < 1184) by = (int)min((int64_t)chunks, cdiv(1184, *nbx > 0 ? *nbx : 1));
@@ -498,6 +758,22 @@ int poisson_fwdbwd(PoissonArgs<T> a, T* gW, double* ll_out, void* ws, size_t ws_
   }
   dim3 grid(nbx, nby);
   int rc;
+  if constexpr (std::is_same<T, float>::value) {
+    if (poisson_version() >= 3) {          // fp32: the packed-FMA kernel
+      if (a.F <= 4) rc = poisson_launch3<2>(a, grid, st);
+      else if (a.F <= 10) rc = poisson_launch3<5>(a, grid, st);
+      else if (a.F <= 12) rc = poisson_launch3<6>(a, grid, st);
+      else if (a.F <= 20) rc = poisson_launch3<10>(a, grid, st);
+      else rc = poisson_launch3<16>(a, grid, st);
+      if (rc) return rc;
+      const int64_t GF3 = (int64_t)a.G * a.F;
+      poisson_gw_reduce_kernel<T><<<(unsigned)cdiv(GF3, 256), 256, 0, st>>>(a.gW_part, a.W, gW, GF3, nbx, a.w_softplus);
+      GPZ_CHECK_LAUNCH();
+      sum_double_kernel<<<1, 256, 0, st>>>(a.ll_part, nbx * nby, ll_out);
+      GPZ_CHECK_LAUNCH();
+      return GPZ_OK;
+    }
+  }
   if (a.F <= 4) rc = poisson_launch<T, 4>(a, grid, st);
   else if (a.F <= 12) rc = poisson_launch<T, 12>(a, grid, st);
   else if (a.F <= 20) rc = poisson_launch<T, 20>(a, grid, st);

@@ -36,15 +36,24 @@ namespace umma {
 
 // A stage holds 64 bytes of k per row: 16 fp32 (tf32 arithmetic) or 32 fp16 (split-FP16 arithmetic) elements, so the
 // byte geometry of the K-major tiles (and the stage size) is the same in both modes.
-constexpr int BM = 128, BN = 256, BK = 16, BK16 = 32, STAGES = 4;
+#ifndef GPZ_UMMA_STAGES
+#define GPZ_UMMA_STAGES 4
+#endif
+#ifndef GPZ_UMMA_EPI_WARPS
+#define GPZ_UMMA_EPI_WARPS 8
+#endif
+constexpr int BM = 128, BN = 256, BK = 16, BK16 = 32, STAGES = GPZ_UMMA_STAGES;
 constexpr int A_BYTES = BM * BK * 4;          // 8 KB   (128 rows x 64 B, SWIZZLE_64B)
 constexpr int B_BYTES = BN * BK * 4;          // 16 KB  (K-major: 256 rows x 64 B; MN-major tf32: 8 chunks x 16 k-rows x 128 B;
                                               //         MN-major fp16: 4 chunks x 32 k-rows x 128 B)
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // raw + lo of both operands = 48 KB
-constexpr int EPI_WARPS = 8;                  // two epilogue warps per TMEM lane quadrant, each owns half of the tile's columns
+constexpr int EPI_WARPS = GPZ_UMMA_EPI_WARPS;  // EPI_WARPS / 4 epilogue warps per TMEM lane quadrant, each owns an equal share of the tile's columns
+constexpr int EPI_CHUNKS = (BN / 32) / (EPI_WARPS / 4);      // 32-column chunks per epilogue warp
+static_assert(EPI_WARPS % 4 == 0 && (BN / 32) % (EPI_WARPS / 4) == 0, "epilogue warps must split the tile's column chunks evenly");
 constexpr int EPI_BYTES = EPI_WARPS * 32 * 32 * 4;  // per-warp 32 x 32 fp32 staging tile, XOR-swizzled 16-byte columns
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
 constexpr int NTHREADS = 64 + 32 * EPI_WARPS;
+static_assert(SMEM_BYTES <= 232448, "shared memory per CTA");
 constexpr uint32_t TMEM_COLS = 512;      // two 128 x 256 fp32 accumulators
 
 struct Params {
@@ -213,7 +222,7 @@ __device__ __forceinline__ void epilogue_tile_fast(const Params& p, int b, int i
   const uint32_t srd = smem_u32(epi) + lr * 128;     // staging read: row (4 itr + lr), 16-byte slot (lane & 7) ^ (row & 7)
   const uint32_t swr = smem_u32(epi) + lane * 128;   // staging write: row lane
 #pragma unroll 1
-  for (int cc = 0; cc < BN / 64; ++cc) {
+  for (int cc = 0; cc < EPI_CHUNKS; ++cc) {
     uint32_t r[32];
     tmem_ld32_nowait(tmem_acc + (uint32_t)((c_begin + cc) * 32), r);
     float4 cv1, cv2;
@@ -248,7 +257,7 @@ __device__ __forceinline__ void epilogue_tile_fast(const Params& p, int b, int i
         if (itr < 4) {                                 // this slot is free again: fetch row itr + 4
           axh[itr] = __ldcs(reinterpret_cast<const uint2*>(p.AuxH + o_chunk + (itr + 4) * ld4));
           axl[itr] = __ldcs(reinterpret_cast<const uint2*>(p.AuxL + o_chunk + (itr + 4) * ld4));
-        } else if (cc + 1 < BN / 64) {                 // ... and row itr - 4 of the next chunk
+        } else if (cc + 1 < EPI_CHUNKS) {              // ... and row itr - 4 of the next chunk
           axh[itr - 4] = __ldcs(reinterpret_cast<const uint2*>(p.AuxH + o_chunk + 32 + (itr - 4) * ld4));
           axl[itr - 4] = __ldcs(reinterpret_cast<const uint2*>(p.AuxL + o_chunk + 32 + (itr - 4) * ld4));
         }
@@ -544,7 +553,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   } else {
     // ===== epilogue: warps 2..9, TMEM lane quadrant = warp % 4; warps 2..5 take column chunks 0..3, warps 6..9 chunks 4..7 =====
     const int q = warp & 3;
-    const int c_begin = ((warp - 2) >> 2) * (BN / 64), c_end = c_begin + BN / 64;
+    const int c_begin = ((warp - 2) >> 2) * EPI_CHUNKS, c_end = c_begin + EPI_CHUNKS;
     const bool vec_ok = (p.ldd % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0) &&
                         (!p.Dlo || (reinterpret_cast<uintptr_t>(p.Dlo) & 15) == 0) &&
                         (!p.Cin || (reinterpret_cast<uintptr_t>(p.Cin) & 15) == 0) && ((p.sD % 4) == 0) &&
@@ -569,9 +578,11 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         const __half* ah = p.AuxH + (int64_t)ti.b * p.sD + (int64_t)(ti.i0 + q * 32 + lane) * p.ldd + ti.j0 + c_begin * 32;
         const __half* al = p.AuxL + (int64_t)ti.b * p.sD + (int64_t)(ti.i0 + q * 32 + lane) * p.ldd + ti.j0 + c_begin * 32;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(ah));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(ah + 64));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(al));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(al + 64));
+        if (EPI_CHUNKS > 2) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(ah + 64));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(al + 64));
+        }
       }
       if (has_acc) {
         mbar_wait(accum_full + as, (acc_iter >> 1) & 1u);

@@ -453,10 +453,74 @@ class SvgpChain(Function):
         gKzz = torch.empty((L, M, M), dtype=dt, device=dev)
         gLu_raw = torch.empty_like(gKzz)
         gmu = torch.empty((L, M), dtype=dt, device=dev)
+        grp = _chain_shard_group
+        if grp is not None and torch.distributed.get_world_size(grp) > 1 and gLc is None and gLu is None:
+            return SvgpChain._backward_sharded(grp, ctx.saved_tensors, gLinv, gT, gq, gkl, gKzz, gLu_raw, gmu) + (None,)
         ws = torch.empty((12 * L * M * M + 2 * L * M,), dtype=dt, device=dev)
         call("svgp_chain_bwd", dt, ptr(Lc), ptr(Linv), ptr(Lu), ptr(T), ptr(q), ptr(mu), ptr(aux), ptr(gLc), ptr(gLinv), ptr(gLu),
              ptr(gT), ptr(gq), ptr(gkl), ptr(gKzz), ptr(gLu_raw), ptr(gmu), ptr(ws), c_i(M), c_i(L))
         return gKzz, gLu_raw, gmu, None
+
+    @staticmethod
+    def _backward_sharded(grp, saved, gLinv, gT, gq, gkl, gKzz, gLu_raw, gmu):
+        """Data-parallel ranks hold PARTIAL gradients (sums over their own spots) of the replicated chain's outputs.  The chain's
+        backward is linear in them, so instead of every rank pushing its partials through all L factors (and the all-reduce
+        summing the results) the partials are summed FIRST, factor by factor onto the rank that owns the factor (one all-to-all
+        + a sum over the senders), and each rank runs the backward of its own factors only.  It returns zeros for the factors
+        it does not own; the step's gradient all-reduce then assembles the totals exactly as before.  The replicated O(M^3)
+        backward (7 GEMMs per factor) shrinks from L to ceil(L / world) factors per rank."""
+        import torch.distributed as dist
+        Lc, Linv, Lu, T, q, mu, aux = saved
+        L, M, _ = Lc.shape
+        dt, dev = Lc.dtype, Lc.device
+        world, rank = dist.get_world_size(grp), dist.get_rank(grp)
+        bounds = [(r * L) // world for r in range(world + 1)]              # contiguous blocks of factors, sizes differ by <= 1
+        l0, l1 = bounds[rank], bounds[rank + 1]
+        own = l1 - l0
+        zeros = lambda *shape: torch.zeros(shape, dtype=dt, device=dev)
+        gLinv = gLinv if gLinv is not None else zeros(L, M, M)
+        gT = gT if gT is not None else zeros(L, M, M)
+        gq = gq if gq is not None else zeros(L, M)
+        # one flat buffer per factor: [gLinv_l | gT_l | gq_l]
+        per = 2 * M * M + M
+        send = torch.empty((L, per), dtype=dt, device=dev)
+        send[:, :M * M] = gLinv.reshape(L, -1)
+        send[:, M * M:2 * M * M] = gT.reshape(L, -1)
+        send[:, 2 * M * M:] = gq
+        recv = torch.empty((world, own, per), dtype=dt, device=dev)
+        dist.all_to_all_single(recv.view(-1), send.view(-1), output_split_sizes=[own * per] * world,
+                               input_split_sizes=[(bounds[r + 1] - bounds[r]) * per for r in range(world)], group=grp)
+        gKzz.zero_(), gLu_raw.zero_(), gmu.zero_()
+        if own > 0:
+            tot = recv.sum(0)                                              # partials of every rank, own factors
+            gLinv_o = tot[:, :M * M].reshape(own, M, M).contiguous()
+            gT_o = tot[:, M * M:2 * M * M].reshape(own, M, M).contiguous()
+            gq_o = tot[:, 2 * M * M:].contiguous()
+            # every rank weighted the KL by 1 / world (kl_weight): the owner applies the full weight
+            gkl_o = (gkl[l0:l1] * world).contiguous() if gkl is not None else None
+            sl = lambda t: t[l0:l1].contiguous()
+            aux_o = aux[:, l0:l1].contiguous()
+            gK_o = torch.empty((own, M, M), dtype=dt, device=dev)
+            gLu_o = torch.empty_like(gK_o)
+            gmu_o = torch.empty((own, M), dtype=dt, device=dev)
+            ws = torch.empty((12 * own * M * M + 2 * own * M,), dtype=dt, device=dev)
+            call("svgp_chain_bwd", dt, ptr(sl(Lc)), ptr(sl(Linv)), ptr(sl(Lu)), ptr(sl(T)), ptr(sl(q)), ptr(sl(mu)), ptr(aux_o),
+                 ptr(None), ptr(gLinv_o), ptr(None), ptr(gT_o), ptr(gq_o), ptr(gkl_o), ptr(gK_o), ptr(gLu_o), ptr(gmu_o), ptr(ws),
+                 c_i(M), c_i(own))
+            gKzz[l0:l1], gLu_raw[l0:l1], gmu[l0:l1] = gK_o, gLu_o, gmu_o
+        return gKzz, gLu_raw, gmu
+
+
+_chain_shard_group = None
+
+
+def set_chain_sharding(group):
+    """Data-parallel training: shard the backward of the replicated O(M^3) chain by factor over `group` (a torch.distributed
+    process group; None turns it off).  Requires that every rank of the group calls the step with the same parameters and a
+    KL weight of 1 / world_size, and that the shared-parameter gradients are summed over the group afterwards
+    (`gpzoo_b200.distributed.FlatGradReducer`)."""
+    global _chain_shard_group
+    _chain_shard_group = group
 
 
 class LowerCholesky(Function):
