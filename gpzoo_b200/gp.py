@@ -133,14 +133,19 @@ class _SparseGPBase(nn.Module):
             Kxx, Kzx, _ = self._kernel_matrices(X, groupsX, want_lo, want_h, skip_kzz=True)
             Lc, Linv, Lu, T, q, L = _chain
         elif want_h and F.OVERLAP_KERNEL_BUILD:
-            # The Kzz chain (Cholesky + inverse: one 8-CTA cluster per factor, latency-bound, about half of the SMs) and the
-            # HBM-bound Kzx build are independent: the Kzx kernel is launched on a side stream (torch's current stream, and so
-            # the allocator's view of every tensor, stays the same) and joins before the predictive GEMMs.
-            side = F.side_stream(X.device)
-            with F.launch_on(side):
+            # The Kzz chain (Cholesky + inverse, latency-bound, about half of the SMs) and the HBM-bound Kzx build are
+            # independent: the Kzx kernel runs on a side stream and joins before the predictive GEMMs.  It runs under
+            # torch.cuda.stream(side), so autograd runs its BACKWARD on the side stream too (the engine replays every node on
+            # the stream of its forward and orders producers / consumers across streams): the issue-bound kernel-build
+            # backward of Kzx then overlaps the tensor-core-bound backward of the chain instead of queueing behind it.
+            side, main = F.side_stream(X.device), torch.cuda.current_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
                 Kxx, Kzx, _ = self._kernel_matrices(X, groupsX, want_lo, want_h, skip_kzz=True)
             Lc, Linv, Lu, T, q, L = self._whitened(self._kzz(X, groupsX, cdt), consume=True)
-            torch.cuda.current_stream().wait_stream(side)
+            main.wait_stream(side)
+            for t in (Kxx,) + tuple(Kzx):          # allocated in the side stream's pool, consumed on the main stream
+                t.record_stream(main)
         else:
             Kxx, Kzx, _ = self._kernel_matrices(X, groupsX, want_lo, want_h, skip_kzz=True)
             Lc, Linv, Lu, T, q, L = self._whitened(self._kzz(X, groupsX, cdt), consume=True)
