@@ -88,9 +88,11 @@ __global__ void __launch_bounds__(KB_THREADS) kbuild_fwd_kernel(const KBArgs<T> 
       for (int v = 0; v < KB_VEC; ++v) {
         T val;
         if (MG) {
+          // one reciprocal per entry (MUFU.RCP in fp32: the two IEEE divisions held the multi-group build at 20 % of HBM peak)
           const T den = fma(s_a[l], r2[v], T(1));
-          const T sc = a.p_half == T(1) ? T(1) / den : Num<T>::pow(den, -a.p_half);
-          val = s2 * Num<T>::exp(c * d2[v] / den) * sc;
+          const T idn = fast_div(T(1), den);
+          const T sc = a.p_half == T(1) ? idn : Num<T>::pow(den, -a.p_half);
+          val = s2 * Num<T>::exp(c * d2[v] * idn) * sc;
         } else if (MAT) {
           const T vv = c * Num<T>::sqrt(d2[v]);
           val = s2 * (T(1) + vv) * Num<T>::exp(-vv);
@@ -184,8 +186,9 @@ __global__ void __launch_bounds__(KB_THREADS) kbuild_fwd_h_kernel(const KBArgs<f
         float val;
         if (MG) {
           const float den = fmaf(s_a[l], r2[v], 1.f);
-          const float scd = a.p_half == 1.f ? 1.f / den : powf(den, -a.p_half);
-          val = s2 * expf(c * d2[v] / den) * scd;
+          const float idn = __fdividef(1.f, den);
+          const float scd = a.p_half == 1.f ? idn : powf(den, -a.p_half);
+          val = s2 * expf(c * d2[v] * idn) * scd;
         } else if (MAT) {
           const float vv = c * sqrtf(d2[v]);
           val = s2 * (1.f + vv) * expf(-vv);
@@ -309,7 +312,7 @@ __global__ void __launch_bounds__(KB_THREADS, (sizeof(T) == 4 && LMAX <= 12) ? 2
             T k0, idn, ee = T(0);
             if (MG) {
               const T den = fma(s_a[l], r2[v], T(1));
-              idn = T(1) / den;
+              idn = fast_div(T(1), den);
               const T sc = a.p_half == T(1) ? idn : Num<T>::pow(den, -a.p_half);
               k0 = s2 * fast_exp(c * d2[v] * idn) * sc;
             } else if (MAT) {
