@@ -121,6 +121,52 @@ __global__ void __launch_bounds__(256) chain_trifix_kernel(float* __restrict__ X
   }
 }
 
+// V = V0 + gkl T (lower) with its lo plane
+__global__ void __launch_bounds__(256) chain_v_kernel(float* __restrict__ V, float* __restrict__ V_lo, const float* __restrict__ T,
+                                                       const float* __restrict__ gkl, int M) {
+  const int i = blockIdx.x, l = blockIdx.y;
+  const int64_t row = ((int64_t)l * M + i) * M;
+  const float g = gkl ? gkl[l] : 0.f;
+  for (int j = threadIdx.x; j < M; j += blockDim.x) {
+    const float v = j <= i ? V[row + j] + g * T[row + j] : 0.f;      // (the product above wrote the lower triangle only)
+    V[row + j] = v;
+    V_lo[row + j] = tf32_lo_part(v);
+  }
+}
+
+// gq = gqp + gkl q
+__global__ void chain_gq_kernel(const float* __restrict__ gqp, const float* __restrict__ gkl, const float* __restrict__ q,
+                                float* __restrict__ gq, int M, int L) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < M * L) gq[e] = gqp[e] + (gkl ? gkl[e / M] : 0.f) * q[e];
+}
+
+// G2 = tril(YS + YS^T - S1 + gkl Y + q gqp^T) with its lo plane (zeros above the diagonal); 32 x 32 tiles through shared memory
+__global__ void __launch_bounds__(256) chain_g2_kernel(const float* __restrict__ YS, const float* __restrict__ S1, const float* __restrict__ Y,
+                                                        const float* __restrict__ q, const float* __restrict__ gqp,
+                                                        const float* __restrict__ gkl, float* __restrict__ G2, float* __restrict__ G2_lo,
+                                                        int M) {
+  __shared__ float t[32][33];
+  const int64_t mat = (int64_t)blockIdx.z * M * M;
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float g = gkl ? gkl[blockIdx.z] : 0.f;
+  for (int r = ty; r < 32; r += 8) {                          // t[r][c] = YS[bx + r][by + c]  (the transposed tile)
+    const int i = bx + r, j = by + tx;
+    t[r][tx] = (i < M && j < M) ? YS[mat + (int64_t)i * M + j] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int i = by + r, j = bx + tx;
+    if (i < M && j < M) {
+      const int64_t o = mat + (int64_t)i * M + j;
+      float v = 0.f;
+      if (j <= i) v = YS[o] + t[tx][r] - S1[o] + g * Y[o] + q[(int64_t)blockIdx.z * M + i] * gqp[(int64_t)blockIdx.z * M + j];
+      G2[o] = v;
+      G2_lo[o] = tf32_lo_part(v);
+    }
+  }
+}
+
 static int tcg(cudaStream_t st, int bk, int M, int L, float alpha, const float* A, const float* Alo, const float* B, const float* Blo,
                const float* Cin, float* D, float* Dlo, int a_tri, int b_tri, int d_tri) {
   const int64_t s = (int64_t)M * M;
@@ -191,6 +237,64 @@ extern "C" int gpz_svgp_chain_bwd_f32(const float* Lc, const float* Linv, const 
   rc = tcg(st, 1, M, L, -1.0f, t1, t1_lo, Linv, Linv_lo, nullptr, gLc, nullptr, 1, 2, 1);         // gLc0 = -tril(t1 Linv^T)
   if (rc) return rc;
   chain_trifix_kernel<<<rows, 256, 0, st>>>(gLc, gLc_lo, 0, gmu, q, gLc_in, gkl_in, Lc, M);
+  GPZ_CHECK_LAUNCH();
+  rc = tcg(st, 0, M, L, 1.0f, LcT, LcT_lo, gLc, gLc_lo, nullptr, P, nullptr, 2, 1, 1);            // P0 = tril(Lc^T gLc)
+  if (rc) return rc;
+  chain_trifix_kernel<<<rows, 256, 0, st>>>(P, P_lo, 1, nullptr, nullptr, nullptr, nullptr, nullptr, M);
+  GPZ_CHECK_LAUNCH();
+  rc = tcg(st, 0, M, L, 1.0f, LinvT, LinvT_lo, P, P_lo, nullptr, t2, t2_lo, 2, 1, 0);             // t2 = Linv^T P
+  if (rc) return rc;
+  return tcg(st, 0, M, L, 1.0f, t2, t2_lo, Linv, Linv_lo, nullptr, gKzz, nullptr, 0, 1, 0);        // gKzz = t2 Linv
+}
+
+// Merged backward of predict + chain (fp32): the predictive backward hands over S1 = A diag(2 gv) A^T (full symmetric, with its
+// lo plane) and gqp = A gm instead of gT and gLinv.  With C = T^T A, Kzx = Lc A and Lc^T Linv^T = I, Lu^T Linv^T = T^T:
+//     gq = gqp + gkl q ;  gmu = Linv^T gq
+//     Y = T T^T ;  V = (S1 + gkl I) T ;  gLu = tril(Linv^T V) - gkl / diag(Lu)  (+ incoming)
+//     G2 = Y S1 + S1 Y - S1 + gkl Y + q gqp^T
+//     gLc = gkl / diag(Lc) - tril(Linv^T G2) - tril(gmu q^T)  (+ incoming) ;  P = Phi(Lc^T gLc) ;  gKzz = Linv^T P Linv
+// i.e. 8 M x M x M products and ONE reduction over the spots, instead of 11 products and two reductions, and without the
+// multiply-by-Lc-then-by-Linv round trip of the un-merged regrouping (which costs accuracy on ill-conditioned Kzz).
+// ws: 13 L M M + 2 L M floats.
+extern "C" int gpz_svgp_chain_bwd_s1_f32(const float* Lc, const float* Linv, const float* Lu, const float* T, const float* q,
+                                         const float* mu, const float* aux, const float* S1, const float* S1_lo, const float* gqp,
+                                         const float* gkl_in, const float* gLc_in, const float* gLu_in, float* gKzz, float* gLu_raw,
+                                         float* gmu, float* ws, int M, int L, void* stream) {
+  if (!gpz_svgp_chain_supported(M) || L <= 0) return GPZ_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t W = (int64_t)M * M * L;
+  const float* Linv_lo = aux; const float* LinvT = aux + W; const float* LinvT_lo = aux + 2 * W; const float* LcT = aux + 3 * W;
+  const float* LcT_lo = aux + 4 * W;
+  float* T_lo = ws; float* Y = ws + W; float* Y_lo = ws + 2 * W; float* V = ws + 3 * W; float* V_lo = ws + 4 * W; float* U = ws + 5 * W;
+  float* YS = ws + 6 * W; float* G2 = ws + 7 * W; float* G2_lo = ws + 8 * W; float* gLc = ws + 9 * W; float* gLc_lo = ws + 10 * W;
+  float* P = ws + 11 * W; float* P_lo = ws + 12 * W; float* gq = ws + 13 * W;
+  float* t2 = YS; float* t2_lo = Y_lo;                   // YS / Y_lo are dead once G2 has been formed
+  (void)mu;
+  const dim3 rows(M, L);
+  const dim3 tiles((unsigned)cdiv(M, 32), (unsigned)cdiv(M, 32), L);
+  int rc = gpz_tf32_lo_f32(T, T_lo, W, stream);
+  if (rc) return rc;
+  chain_gq_kernel<<<(unsigned)cdiv((int64_t)M * L, 256), 256, 0, st>>>(gqp, gkl_in, q, gq, M, L);
+  GPZ_CHECK_LAUNCH();
+  rc = gpz_gemv_f32(1, Linv, gq, gmu, M, M, L, stream);                                           // gmu = Linv^T gq
+  if (rc) return rc;
+  rc = tcg(st, 1, M, L, 1.0f, T, T_lo, T, T_lo, nullptr, Y, Y_lo, 1, 2, 0);                        // Y = T T^T (op(B) = T^T)
+  if (rc) return rc;
+  rc = tcg(st, 0, M, L, 1.0f, S1, S1_lo, T, T_lo, nullptr, V, nullptr, 0, 1, 1);                   // V0 = tril(S1 T)
+  if (rc) return rc;
+  chain_v_kernel<<<rows, 256, 0, st>>>(V, V_lo, T, gkl_in, M);                                    // V = tril((S1 + gkl I) T)
+  GPZ_CHECK_LAUNCH();
+  rc = tcg(st, 0, M, L, 1.0f, LinvT, LinvT_lo, V, V_lo, nullptr, U, nullptr, 2, 1, 1);             // U = tril(Linv^T V)
+  if (rc) return rc;
+  chain_glu_kernel<<<rows, 256, 0, st>>>(U, gLu_in, gkl_in, Lu, gLu_raw, M);
+  GPZ_CHECK_LAUNCH();
+  rc = tcg(st, 0, M, L, 1.0f, Y, Y_lo, S1, S1_lo, nullptr, YS, nullptr, 0, 0, 0);                  // YS = Y S1 (full)
+  if (rc) return rc;
+  chain_g2_kernel<<<tiles, 256, 0, st>>>(YS, S1, Y, q, gqp, gkl_in, G2, G2_lo, M);
+  GPZ_CHECK_LAUNCH();
+  rc = tcg(st, 0, M, L, -1.0f, LinvT, LinvT_lo, G2, G2_lo, nullptr, gLc, nullptr, 2, 1, 1);        // gLc0 = -tril(Linv^T G2)
+  if (rc) return rc;
+  chain_trifix_kernel<<<rows, 256, 0, st>>>(gLc, gLc_lo, 0, gmu, q, gLc_in, gkl_in, Lc, M);       // - tril(gmu q^T) + gkl / diag(Lc) + incoming
   GPZ_CHECK_LAUNCH();
   rc = tcg(st, 0, M, L, 1.0f, LcT, LcT_lo, gLc, gLc_lo, nullptr, P, nullptr, 2, 1, 1);            // P0 = tril(Lc^T gLc)
   if (rc) return rc;

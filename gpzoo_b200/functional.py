@@ -26,7 +26,13 @@ USE_TENSOR_CORES = True      # fp32: route large contractions through the tcgen0
 TENSOR_CORE_ARITH = os.environ.get("GPZ_TC_ARITH", "fp16x3")
 # fp32 models: up to this many inducing points the O(M^3) chain runs in fp64 (gp.py `_chain_dtype`); GPZ_CHAIN_FP64_MAX_M=0 turns it off
 CHAIN_FP64_MAX_M = int(os.environ.get("GPZ_CHAIN_FP64_MAX_M", "256"))
-FUSED_CHAIN = os.environ.get("GPZ_FUSED_CHAIN", "1") != "0"       # csrc/chain.cu instead of the Function-per-op chain
+# two-node path only: split-FP16 predict backward with one N-reduction + four M^3 products instead of two N-reductions
+# (csrc/predict.cu).  Off by default: its multiply-by-Lc / multiply-by-Linv round trip costs accuracy on ill-conditioned Kzz
+# (d lengthscale 1.2e-4 instead of 4e-5 at cond 600); the one-node path (SvgpMomentsH) merges the algebra instead.
+REGROUP_PREDICT_BWD = os.environ.get("GPZ_REGROUP", "0") != "0"
+FUSED_CHAIN = os.environ.get("GPZ_FUSED_CHAIN", "1") != "0"
+# chain + predict as one autograd node with the merged backward (SvgpMomentsH); GPZ_FUSED_MOMENTS=0: the two-node path
+FUSED_MOMENTS = os.environ.get("GPZ_FUSED_MOMENTS", "1") != "0"       # csrc/chain.cu instead of the Function-per-op chain
 CHOL_TC_MIN_M = int(os.environ.get("GPZ_CHOL_TC_MIN_M", "768"))   # above this size the fp32 Cholesky + inverse is the panel hybrid:
 # 256-wide diagonal blocks on the cluster kernel, trailing updates and the inverse's doubling on tcgen05 (measured, L = 10:
 # M = 512 0.42 vs 0.51 ms, M = 1024 1.30 vs 1.18 ms, M = 1536 3.41 vs 2.02 ms, cluster vs hybrid)
@@ -523,6 +529,82 @@ def set_chain_sharding(group):
     _chain_shard_group = group
 
 
+def fused_moments_ok(dtype, M, N):
+    """fp32 problems that take the fused chain + split-FP16 predict Function with the merged backward."""
+    return FUSED_MOMENTS and chain_ok(dtype, M) and predict_h_ok(dtype, M, N)
+
+
+class SvgpMomentsH(Function):
+    """SvgpChain + PredictH as ONE autograd node (fp32): jittered Kzz, raw Lu, mu and the fp16 planes of Kzx ->
+    predictive mean / variance, per-factor KL, Lc and Lu.  Keeping Linv, T and q internal is what allows the MERGED backward
+    (csrc/chain.cu gpz_svgp_chain_bwd_s1): one reduction over the spots (S1 = A diag(2 gv) A^T) and 8 M x M x M products instead
+    of two reductions and 11 products."""
+
+    @staticmethod
+    def forward(ctx, Kzz, Lu_raw, mu, Kxx, Kzx, Kh, Kl, sK, consume):
+        L, M, _ = Kzz.shape
+        dt, dev = Kzz.dtype, Kzz.device
+        N = Kh.shape[-1]
+        W = _c(Kzz.detach())
+        if W.data_ptr() == Kzz.data_ptr() and not consume:
+            W = W.clone()
+        Lu_raw, mu, Kxx, Kh, Kl, sK = _c(Lu_raw.detach()), _c(mu.detach()), _c(Kxx.detach()), _c(Kh), _c(Kl), _c(sK)
+        chol_tc = int(M > CHOL_TC_MIN_M)
+        Lc, Linv, Lu, T = (torch.empty((L, M, M), dtype=dt, device=dev) for _ in range(4))
+        q = torch.empty((L, M), dtype=dt, device=dev)
+        kl = torch.empty(L, dtype=dt, device=dev)
+        aux = torch.empty((6, L, M, M), dtype=dt, device=dev)
+        ws = torch.empty(((5 if chol_tc else 1) * L * M * M + 4 * L,), dtype=dt, device=dev)
+        info = torch.empty(L, dtype=torch.int32, device=dev)
+        call("svgp_chain_fwd", dt, ptr(W), ptr(Lu_raw), ptr(mu), ptr(Lc), ptr(Linv), ptr(Lu), ptr(T), ptr(q), ptr(kl), ptr(aux),
+             ptr(ws), c_i(M), c_i(L), c_i(chol_tc), ptr(info))
+        _pending_info.append(info)
+        Ah, Al, Ch, Cl = (torch.empty_like(Kh) for _ in range(4))
+        mean = torch.empty((L, N), dtype=dt, device=dev)
+        var = torch.empty_like(mean)
+        ws_h = torch.empty(8 * L * M * M, dtype=torch.float16, device=dev)
+        ws_f = torch.empty(2 * L * N + 16 * L, dtype=dt, device=dev)
+        call("svgp_predict_fwd_h", dt, ptr(Kh), ptr(Kl), ptr(sK), ptr(Linv), ptr(T), ptr(q), ptr(Kxx), ptr(Ah), ptr(Al), ptr(Ch),
+             ptr(Cl), ptr(mean), ptr(var), ptr(ws_h), ptr(ws_f), c_i(M), c_i(N), c_i(L))
+        st = ws_f[2 * L * N:].view(-1, L)
+        r_sA, r_aA, r_aC, r_sC = (_stat_row(i) for i in (0, 1, 2, 5))
+        _pending_amax.append((torch.stack((st[r_aA], st[r_aC])), torch.stack((st[r_sA], st[r_sC])), ("A", "C")))
+        if len(_pending_amax) > 64:
+            _fold_pending_amax()
+        if SYNC_CHECKS:
+            check_cholesky_info()
+        ctx.save_for_backward(Lc, Linv, Lu, T, q, mu, aux, Kh, Kl, sK, Ah, Al, Ch, Cl, ws_h, ws_f)
+        ctx.set_materialize_grads(False)
+        return mean, var, kl, Lc, Lu
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gm, gv, gkl, gLc, gLu):
+        Lc, Linv, Lu, T, q, mu, aux, Kh, Kl, sK, Ah, Al, Ch, Cl, ws_h, ws_f = ctx.saved_tensors
+        L, M, N = Kh.shape
+        dt, dev = Lc.dtype, Lc.device
+        cc = lambda t: None if t is None else _c(t)
+        gm = _c(gm) if gm is not None else torch.zeros((L, N), dtype=dt, device=dev)
+        gv = _c(gv) if gv is not None else torch.zeros((L, N), dtype=dt, device=dev)
+        gkl, gLc, gLu = cc(gkl), cc(gLc), cc(gLu)
+        AWh, AWl, gAh, gAl = (torch.empty_like(Kh) for _ in range(4))
+        gKzx = torch.empty((L, M, N), dtype=dt, device=dev)
+        gqp = torch.empty((L, M), dtype=dt, device=dev)
+        S = torch.empty((2, L, M, M), dtype=dt, device=dev)                 # S1 and its lo plane
+        call("svgp_predict_bwd_h", dt, ptr(Kh), ptr(Kl), ptr(sK), ptr(T), ptr(q), ptr(Ah), ptr(Al), ptr(Ch), ptr(Cl), ptr(gm), ptr(gv),
+             ptr(AWh), ptr(AWl), ptr(gAh), ptr(gAl), ptr(gKzx), ptr(None), ptr(None), ptr(gqp), ptr(ws_h), ptr(ws_f), ptr(Lc), ptr(S),
+             c_i(M), c_i(N), c_i(L))
+        stt = ws_f[2 * L * N:].view(-1, L)
+        _pending_amax.append((stt[_stat_row(4)].unsqueeze(0), stt[_stat_row(3)].unsqueeze(0), ("dL/dA",)))
+        gKzz = torch.empty((L, M, M), dtype=dt, device=dev)
+        gLu_raw = torch.empty_like(gKzz)
+        gmu = torch.empty((L, M), dtype=dt, device=dev)
+        ws = torch.empty((13 * L * M * M + 2 * L * M,), dtype=dt, device=dev)
+        call("svgp_chain_bwd_s1", dt, ptr(Lc), ptr(Linv), ptr(Lu), ptr(T), ptr(q), ptr(mu), ptr(aux), ptr(S[0]), ptr(S[1]), ptr(gqp),
+             ptr(gkl), ptr(gLc), ptr(gLu), ptr(gKzz), ptr(gLu_raw), ptr(gmu), ptr(ws), c_i(M), c_i(L))
+        return gKzz, gLu_raw, gmu, gv, gKzx, None, None, None, None
+
+
 class LowerCholesky(Function):
     """transform_to(constraints.lower_cholesky) (gp.py:220): tril(raw,-1) + diag(exp(diag raw))."""
 
@@ -654,8 +736,10 @@ class PredictH(Function):
     `Kzx` is KernelBuildH's stand-in (it only routes dL/dKzx); (Kh, Kl, sK) are the planes it wrote."""
 
     @staticmethod
-    def forward(ctx, Kxx, Kzx, Linv, T, q, Kh, Kl, sK):
+    def forward(ctx, Kxx, Kzx, Linv, T, q, Kh, Kl, sK, Lc=None):
+        """Lc: the Cholesky factor whose inverse `Linv` is (a constant of the backward's regrouping Kzx = Lc A; optional)."""
         Kxx, Linv, T, q, Kh, Kl, sK = _c(Kxx), _c(Linv), _c(T), _c(q), _c(Kh), _c(Kl), _c(sK)
+        ctx.Lc = _c(Lc.detach()) if (Lc is not None and REGROUP_PREDICT_BWD) else None
         dt = Linv.dtype
         L, M, N = Kh.shape
         dev = Kh.device
@@ -691,12 +775,14 @@ class PredictH(Function):
         gLinv = torch.zeros_like(Linv)
         gT = torch.zeros_like(T)
         gq = torch.empty_like(q)
+        Lc = ctx.Lc
+        ws_m = torch.empty(8 * L * M * M, dtype=dt, device=dev) if Lc is not None else None
         call("svgp_predict_bwd_h", dt, ptr(Kh), ptr(Kl), ptr(sK), ptr(T), ptr(q), ptr(Ah), ptr(Al), ptr(Ch), ptr(Cl), ptr(gm), ptr(gv),
-             ptr(AWh), ptr(AWl), ptr(gAh), ptr(gAl), ptr(gKzx), ptr(gLinv), ptr(gT), ptr(gq), ptr(ws_h), ptr(ws_f),
+             ptr(AWh), ptr(AWl), ptr(gAh), ptr(gAl), ptr(gKzx), ptr(gLinv), ptr(gT), ptr(gq), ptr(ws_h), ptr(ws_f), ptr(Lc), ptr(ws_m),
              c_i(M), c_i(N), c_i(L))
         st = ws_f[2 * L * N:].view(-1, L)
         _pending_amax.append((st[_stat_row(4)].unsqueeze(0), st[_stat_row(3)].unsqueeze(0), ("dL/dA",)))   # max |gA| vs its scale
-        return gv, gKzx, gLinv, gT, gq, None, None, None
+        return gv, gKzx, gLinv, gT, gq, None, None, None, None
 
 
 def umma_gemm(A, B, b_kmajor, Alo=None, Blo=None, Cin=None, alpha=1.0, want_lo=False, a_tri=0, b_tri=0, d_tri=0, splitk=1,

@@ -119,6 +119,33 @@ class _SparseGPBase(nn.Module):
             return self.kernel(Zc, Zc, self.groupsZ, self.groupsZ, _jitter=self.jitter)
         return self.kernel(Zc, Zc, _jitter=self.jitter)
 
+    _fusable = True          # SVGP / MGGP_SVGP: chain + predict as ONE autograd node (functional.SvgpMomentsH)
+
+    def _fused_moments(self, X, groupsX, cdt, Kxx, Kzx, side, main):
+        """The one-node path (merged backward) when it applies: fp32 chain, M large enough for the fused chain, L-batched
+        kernel and variational parameters, autograd on.  Returns the `moments` dict or None."""
+        dt = X.dtype
+        M = self.Z.shape[0]
+        if not (self._fusable and torch.is_grad_enabled() and cdt == dt and F.fused_moments_ok(dt, M, X.shape[0])):
+            return None
+        mu = self.mu if self.mu.dim() == 2 else self.mu.unsqueeze(0)
+        Lu_raw = _as3(self.Lu)
+        handle, Kh, Kl, sK = Kzx
+        L = max(Kh.shape[0], mu.shape[0], Lu_raw.shape[0])
+        if not (Kh.shape[0] == L and mu.shape[0] == L and Lu_raw.shape[0] == L):
+            return None
+        Kzz = _as3(self._kzz(X, groupsX, cdt))
+        if Kzz.shape[0] != L:
+            return None
+        Kxx = Kxx if Kxx.dim() == 2 else Kxx.unsqueeze(0)
+        if Kxx.shape[0] != L:
+            Kxx = Kxx.expand(L, -1)
+        main.wait_stream(side)
+        for t in (Kxx, handle, Kh, Kl, sK):
+            t.record_stream(main)
+        mean, var, kl, Lc, Lu = F.SvgpMomentsH.apply(Kzz, Lu_raw.to(dt), mu.to(dt), Kxx, handle, Kh, Kl, sK, True)
+        return dict(mean=mean, var=var, kl=kl, Lc=Lc, Lu=Lu, T=None, q=None, _chain=None)
+
     def moments(self, X, groupsX=None, _chain=None):
         """Fused predictive moments: returns dict(mean, var (unclamped), T, q, Lc, Lu), all L-batched (T, q, Lc, Lu in the
         chain's dtype, see `_chain_dtype`).
@@ -136,12 +163,14 @@ class _SparseGPBase(nn.Module):
             # The Kzz chain (Cholesky + inverse, latency-bound, about half of the SMs) and the HBM-bound Kzx build are
             # independent: the Kzx kernel runs on a side stream and joins before the predictive GEMMs.  It runs under
             # torch.cuda.stream(side), so autograd runs its BACKWARD on the side stream too (the engine replays every node on
-            # the stream of its forward and orders producers / consumers across streams): the issue-bound kernel-build
-            # backward of Kzx then overlaps the tensor-core-bound backward of the chain instead of queueing behind it.
+            # the stream of its forward and orders producers / consumers across streams).
             side, main = F.side_stream(X.device), torch.cuda.current_stream()
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 Kxx, Kzx, _ = self._kernel_matrices(X, groupsX, want_lo, want_h, skip_kzz=True)
+            fused = self._fused_moments(X, groupsX, cdt, Kxx, Kzx, side, main)
+            if fused is not None:
+                return fused
             Lc, Linv, Lu, T, q, L = self._whitened(self._kzz(X, groupsX, cdt), consume=True)
             main.wait_stream(side)
             for t in (Kxx,) + tuple(Kzx):          # allocated in the side stream's pool, consumed on the main stream
@@ -161,7 +190,8 @@ class _SparseGPBase(nn.Module):
             Kzx, Kh, Kl, sK = Kzx
             if Kh.shape[0] != L:
                 Kzx, Kh, Kl, sK = Kzx.expand(L, -1, -1), Kh.expand(L, -1, -1), Kl.expand(L, -1, -1), sK.expand(L)
-            mean, var = F.PredictH.apply(Kxx, Kzx, Linv, T, q, Kh, Kl, sK)
+            Lc_true = getattr(self, "_true_Lc", None) if getattr(self, "_true_Lc", None) is not None else Lc
+            mean, var = F.PredictH.apply(Kxx, Kzx, Linv, T, q, Kh, Kl, sK, Lc_true.to(dt))
             return dict(out, mean=mean, var=var)
         Kzx_lo = None
         if want_lo:
@@ -259,6 +289,7 @@ class WSVGP(_SparseGPBase):
     the second term (gp.py:287) — a guard against round-off only (the term is >= 0 in exact arithmetic); here the sum is
     formed in one pass and clamped at 0 as a whole."""
     clamp_min = 0.0
+    _fusable = False         # T := Lu, q := mu and the KL is against the identity: the two-node path
 
     def __init__(self, kernel, dim=1, M=50, jitter=1e-4):
         super().__init__()
@@ -278,6 +309,7 @@ class WSVGP(_SparseGPBase):
         L = max(Kzz.shape[0], mu.shape[0], Lu_raw.shape[0])
         ex = lambda t: t if t.shape[0] == L else t.expand(L, *t.shape[1:])
         Lc, Linv = F.CholeskyInverse.apply(Kzz)
+        self._true_Lc = ex(Lc.detach())                                  # (the predictive backward regroups with Kzx = Lc A)
         Lu = ex(F.LowerCholesky.apply(Lu_raw.to(Kzz.dtype)))
         eye = torch.eye(Kzz.shape[-1], dtype=Kzz.dtype, device=Kzz.device).expand(L, -1, -1).contiguous()
         return eye, ex(Linv), Lu, Lu, ex(mu.to(Kzz.dtype)), L          # (Lc := I for the KL, Linv, Lu, T := Lu, q := mu)

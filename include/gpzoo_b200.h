@@ -98,6 +98,15 @@ int gpz_svgp_chain_bwd_f32(const float* Lc, const float* Linv, const float* Lu, 
                            const float* gq_in, const float* gkl_in, float* gKzz, float* gLu_raw, float* gmu, float* ws, int M,
                            int L, void* stream);
 
+/* Merged backward of the predictive op and the chain (fp32): gpz_svgp_predict_bwd_h_f32 called with gT = gLinv = NULL and
+ * ws_m = [S1 | S1_lo] (2 L M M floats) leaves S1 = A diag(2 gv) A^T (full symmetric) and gq = A gm; this call turns them, gkl and
+ * optional incoming gradients of Lc / Lu into gKzz (not symmetrised), gLu_raw, gmu with 8 M x M x M products (csrc/chain.cu).
+ * ws: 13 L M M + 2 L M floats. */
+int gpz_svgp_chain_bwd_s1_f32(const float* Lc, const float* Linv, const float* Lu, const float* T, const float* q, const float* mu,
+                              const float* aux, const float* S1, const float* S1_lo, const float* gqp, const float* gkl_in,
+                              const float* gLc_in, const float* gLu_in, float* gKzz, float* gLu_raw, float* gmu, float* ws, int M,
+                              int L, void* stream);
+
 /* gp.py:220 transform_to(lower_cholesky): out = tril(raw,-1) + diag(exp(diag raw)), and its backward */
 int gpz_lower_cholesky_fwd_f32(const float* raw, float* out, int M, int L, void* stream);
 int gpz_lower_cholesky_fwd_f64(const double* raw, double* out, int M, int L, void* stream);
@@ -231,8 +240,12 @@ int gpz_svgp_predict_fwd_h_f32(const void* Kh, const void* Kl, const float* sK, 
                                float* ws_f, int M, int N, int L, void* stream);
 int gpz_svgp_predict_bwd_h_f32(const void* Kh, const void* Kl, const float* sK, const float* T, const float* q, const void* Ah,
                                const void* Al, const void* Ch, const void* Cl, const float* gm, const float* gv, void* AWh, void* AWl,
-                               void* gAh, void* gAl, float* gKzx, float* gLinv, float* gT, float* gq, void* ws_h, float* ws_f, int M,
-                               int N, int L, void* stream);
+                               void* gAh, void* gAl, float* gKzx, float* gLinv, float* gT, float* gq, void* ws_h, float* ws_f,
+                               const float* Lc, float* ws_m, int M, int N, int L, void* stream);
+/*      Lc (the Cholesky factor whose inverse Linv is) + ws_m (8 L M M floats; may be NULL): with ws_m given the backward runs ONE
+ *      reduction over the N spots, S1 = A diag(2 gv) A^T, and gets gT = tril(S1 T) and gLinv = tril(((T T^T - I) S1 + q gq^T) Lc^T)
+ *      from four M x M x M products (C = T^T A and Kzx = Lc A); without them it runs the two reductions gT = tril(AW C^T),
+ *      gLinv = tril(gA Kzx^T). */
 
 /* ---- training-step update: multi-tensor Adam in one launch (torch.optim.Adam without weight decay /
  *      amsgrad; utilities.py:621 optimizer.step()) with the reference's post-step clamp W.clamp_(min=0) (utilities.py:623) fused in
