@@ -476,7 +476,9 @@ def run_ours(args):
     F = L + c.get("T", 0)
     algo = {   # per-call algorithmic work on ONE rank: ("hbm", bytes) or ("tensor", flops)
         "svgp_predict_fwd_h": ("tensor", 2.0 * L * M * M * N),
-        "svgp_predict_bwd_h": ("tensor", 4.0 * L * M * M * N),
+        # merged backward (SvgpMomentsH): gA, S1 = tril(AW A^T), gKzx, each one triangular M x M x N product; the two-node path
+        # has four (gA, gKzx, gT, gLinv)
+        "svgp_predict_bwd_h": ("tensor", (3.0 if "svgp_chain_bwd_s1" in prof else 4.0) * L * M * M * N),
         "kernel_build_fwd_h": ("hbm", 4.0 * L * M * N),    # Kzx written once as two fp16 planes
         "kernel_build_bwd": ("hbm", 4.0 * L * M * N),      # dL/dKzx read once (the largest of the two calls: the Kzx one)
         "poisson_fwdbwd": ("hbm", 4.0 * G * N + 4.0 * (3 * E * F * N + 2 * G * F + 2 * N)),

@@ -49,6 +49,11 @@ def side_stream(device):
     st = _side_streams.get(key)
     if st is None:
         st = _side_streams[key] = torch.cuda.Stream(device=key)
+        # the kernel-build backward runs on this stream by design; autograd orders it against the parameters' accumulation on the
+        # main stream (that synchronisation is wanted) and would otherwise print a one-off warning about the stream mismatch
+        mute = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+        if mute is not None:
+            mute(False)
     return st
 
 

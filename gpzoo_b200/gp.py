@@ -141,8 +141,6 @@ class _SparseGPBase(nn.Module):
         if Kxx.shape[0] != L:
             Kxx = Kxx.expand(L, -1)
         main.wait_stream(side)
-        for t in (Kxx, handle, Kh, Kl, sK):
-            t.record_stream(main)
         mean, var, kl, Lc, Lu = F.SvgpMomentsH.apply(Kzz, Lu_raw.to(dt), mu.to(dt), Kxx, handle, Kh, Kl, sK, True)
         return dict(mean=mean, var=var, kl=kl, Lc=Lc, Lu=Lu, T=None, q=None, _chain=None)
 
@@ -163,7 +161,10 @@ class _SparseGPBase(nn.Module):
             # The Kzz chain (Cholesky + inverse, latency-bound, about half of the SMs) and the HBM-bound Kzx build are
             # independent: the Kzx kernel runs on a side stream and joins before the predictive GEMMs.  It runs under
             # torch.cuda.stream(side), so autograd runs its BACKWARD on the side stream too (the engine replays every node on
-            # the stream of its forward and orders producers / consumers across streams).
+            # the stream of its forward and orders producers / consumers across streams).  The planes live in the side stream's
+            # allocator pool and are consumed on the main stream; no record_stream is needed (and it would make the allocator
+            # churn): a side-pool block is only ever reused by a later side-stream allocation, and the side stream's work of the
+            # next step starts with the wait below, i.e. after everything the main stream had queued when the block was freed.
             side, main = F.side_stream(X.device), torch.cuda.current_stream()
             side.wait_stream(main)
             with torch.cuda.stream(side):
@@ -173,8 +174,6 @@ class _SparseGPBase(nn.Module):
                 return fused
             Lc, Linv, Lu, T, q, L = self._whitened(self._kzz(X, groupsX, cdt), consume=True)
             main.wait_stream(side)
-            for t in (Kxx,) + tuple(Kzx):          # allocated in the side stream's pool, consumed on the main stream
-                t.record_stream(main)
         else:
             Kxx, Kzx, _ = self._kernel_matrices(X, groupsX, want_lo, want_h, skip_kzz=True)
             Lc, Linv, Lu, T, q, L = self._whitened(self._kzz(X, groupsX, cdt), consume=True)
