@@ -19,6 +19,7 @@ Prints ONE JSON line (rank 0).  `--impl reference` times the reference's CPU PyT
 instead, on the same config, and adds the stock PyTorch-eager time of the same op sequence on this GPU (`eager_gpu`).
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -317,6 +318,8 @@ def run_ours(args):
         st["reducer"] = FlatGradReducer(st["shared"], device=dev, dtype=dt)
         return st
 
+    DEBUG = os.environ.get("GPZ_BENCH_DEBUG") == "1"
+
     def step(st, Xd=None, yd=None, eps="given"):
         model = st["model"]
         for p in model.parameters():
@@ -329,21 +332,49 @@ def run_ours(args):
             kw["idx"] = st["idx"]
             if st["gX"] is not None:
                 kw["groupsX"] = st["gX"][st["idx"]]
+        if DEBUG:
+            _cabi.host_profile = {}
+            t0 = time.perf_counter()
         elbo = model.elbo(Xd, yd, **kw)
+        if DEBUG:
+            t1 = time.perf_counter()
         (-elbo).backward()
-        return st["reducer"].all_reduce(elbo)      # one NCCL all-reduce of the flat shared-gradient buffer (+ ELBO)
+        if DEBUG:
+            t2 = time.perf_counter()
+        out = st["reducer"].all_reduce(elbo)       # one NCCL all-reduce of the flat shared-gradient buffer (+ ELBO)
+        if DEBUG:
+            ms_ = torch.cuda.memory_stats()
+            na = ms_.get("num_device_alloc", 0), ms_.get("num_device_free", 0), ms_.get("num_alloc_retries", 0)
+            if na != st.get("_na"):
+                print("allocator: cudaMalloc/cudaFree/retries so far", na, "reserved GB %.2f" % (torch.cuda.memory_reserved() / 1e9),
+                      file=sys.stderr, flush=True)
+                st["_na"] = na
+        if DEBUG and time.perf_counter() - t0 > 0.03:
+            print("slow step on the host: fwd %.1f ms, bwd %.1f ms, reduce %.1f ms; longest C-ABI calls (ms): %s" % (
+                (t1 - t0) * 1e3, (t2 - t1) * 1e3, (time.perf_counter() - t2) * 1e3,
+                {k: round(v, 1) for k, v in _cabi.host_profile.items() if v > 1.0}), file=sys.stderr, flush=True)
+        return out
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = [0.0]
+
     def timed(fn, n):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t0 = time.perf_counter()
+        per = []
         for _ in range(n):
+            t1 = time.perf_counter()
             fn()
+            per.append((time.perf_counter() - t1) * 1e3)
+        host_ms[0] = (time.perf_counter() - t0) * 1e3 / n      # host time to ENQUEUE one step (no synchronisation inside)
+        if os.environ.get("GPZ_BENCH_DEBUG") == "1":
+            print("host ms per step:", " ".join(f"{v:.1f}" for v in per), file=sys.stderr, flush=True)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -357,12 +388,19 @@ def run_ours(args):
     for _ in range(warm):
         step(st)
     functional.check_cholesky_info()
+    # A full (generation-2) collection of the CPython garbage collector walks every live object of the interpreter -- about
+    # 100 ms with torch imported -- and fires at allocation-count-dependent moments; one inside a 170 ms timed region doubles
+    # the reading (seen as 19 ms/step with 100 ms host stalls, tools/ + DESIGN.md section 7).  Freezing moves everything
+    # allocated so far out of the collector's reach; the garbage of the steps themselves is still collected.
+    gc.collect()
+    gc.freeze()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     k0 = _cabi.kernel_launches()
     ms = timed(lambda: step(st), args.steps)          # the headline: no per-call instrumentation inside
     launches = (_cabi.kernel_launches() - k0) // args.steps
+    host_enqueue_ms = host_ms[0]
     clocks = sampler.stop() if rank == 0 else None
     # second pass over the same steps with a CUDA-event pair around every C-ABI call: per-call times for the roofline block
     _cabi.profile = {}
@@ -528,7 +566,7 @@ def run_ours(args):
                          l2="inputs larger than L2 (y %.0f MB, Kzx planes %.2f GB per GPU)" % (4e-6 * G * n_loc, 4e-9 * L * M * n_loc),
                          e2e="per step: X, y of the rank's spots uploaded from pinned host memory on a copy stream (double buffered) + "
                              "loss read back to the host with one-step lag"),
-                clocks=clocks, gpu_launches=int(launches),
+                clocks=clocks, gpu_launches=int(launches), host_enqueue_ms_per_step=host_enqueue_ms,
                 e2e=(dict(value=((1e3 / ms_e2e) if main_mode == "strong" else world * 1e3 / ms_e2e), unit="steps/s",
                           h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4) if ms_e2e else None),
                 roofline=roofline, kernels=kernels, per_call_ms=per_call)

@@ -92,6 +92,7 @@ class launch_on:
         _launch_stream = self.prev
 
 
+host_profile = None        # set to {} to record the longest host-side duration of every C-ABI call (debugging)
 profile = None             # set to {} to record CUDA events around every C-ABI call (bench.py roofline numbers)
 
 
@@ -115,6 +116,12 @@ def call(name, dtype, *args):
         rc = fn(*args, st)
         ev1.record(tst)
         profile.setdefault(name, []).append((ev0, ev1))
+    elif host_profile is not None:          # debugging aid: host-side duration of every C-ABI call (longest call per name)
+        import time
+        t0 = time.perf_counter()
+        rc = fn(*args, stream())
+        dt_ms = (time.perf_counter() - t0) * 1e3
+        host_profile[name] = max(host_profile.get(name, 0.0), dt_ms)
     else:
         rc = fn(*args, stream())
     launch_count += 1

@@ -42,6 +42,12 @@ namespace umma {
 #ifndef GPZ_UMMA_EPI_WARPS
 #define GPZ_UMMA_EPI_WARPS 8
 #endif
+// Epilogue modes 3 / 4 read an Aux tile (fp16 planes).  AUX_AHEAD = 1 makes the epilogue warps prefetch the NEXT tile's Aux
+// region into L2 (peeking at the scheduler's other slot) instead of the current tile's; measured SLOWER on the B200
+// (svgp_predict_bwd_h 3.29 -> 3.46 ms: the extra L2 traffic competes with the two output streams), so it is off.
+#ifndef GPZ_UMMA_AUX_AHEAD
+#define GPZ_UMMA_AUX_AHEAD 0
+#endif
 constexpr int BM = 128, BN = 256, BK = 16, BK16 = 32, STAGES = GPZ_UMMA_STAGES;
 constexpr int A_BYTES = BM * BK * 4;          // 8 KB   (128 rows x 64 B, SWIZZLE_64B)
 constexpr int B_BYTES = BN * BK * 4;          // 16 KB  (K-major: 256 rows x 64 B; MN-major tf32: 8 chunks x 16 k-rows x 128 B;
@@ -105,6 +111,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
   }
+}
+// non-blocking probe of an mbarrier phase (acquire): true when the phase with this parity has completed
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
 }
 __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
   asm volatile(
@@ -218,7 +238,12 @@ __device__ __forceinline__ void epilogue_tile_fast(const Params& p, int b, int i
 #pragma unroll
     for (int u = 0; u < 8; ++u) racc[u] = 0.f;
   }
-  uint2 axh[4], axl[4];                              // Aux planes of 4 rows at a time (two batches per chunk)
+#ifndef GPZ_UMMA_AUX_WIN
+#define GPZ_UMMA_AUX_WIN 4                         // rows of the Aux planes held ahead in registers (4 or 8)
+#endif
+  constexpr int AW = GPZ_UMMA_AUX_WIN;
+  static_assert(AW == 4 || AW == 8, "Aux window");
+  uint2 axh[AW], axl[AW];                            // Aux planes of AW rows ahead: a rotating window
   const uint32_t srd = smem_u32(epi) + lr * 128;     // staging read: row (4 itr + lr), 16-byte slot (lane & 7) ^ (row & 7)
   const uint32_t swr = smem_u32(epi) + lane * 128;   // staging write: row lane
 #pragma unroll 1
@@ -229,11 +254,12 @@ __device__ __forceinline__ void epilogue_tile_fast(const Params& p, int b, int i
     if (MODE == 3 || MODE == 4) {
       cv1 = __ldg(reinterpret_cast<const float4*>(p.colv1 + colbase + cc * 32));
       cv2 = __ldg(reinterpret_cast<const float4*>(p.colv2 + colbase + cc * 32));
-      // (the whole Aux region of this warp was prefetched into L2 when the tile was handed out; rows 0..3 of the later chunks
-      // are fetched into the register slots freed by rows 4..7 of the chunk before)
+      // (the Aux region of this warp was prefetched into L2 while the tile before was in the epilogue; every row's slot is
+      // refilled with the same row of the NEXT chunk as soon as it is consumed, so a load has a whole chunk to complete: the
+      // round-2 capture showed 69 % of the epilogue's samples stalled on these loads with a 4-row window)
       if (cc == 0) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < AW; ++u) {
           axh[u] = __ldcs(reinterpret_cast<const uint2*>(p.AuxH + o_chunk + u * ld4));
           axl[u] = __ldcs(reinterpret_cast<const uint2*>(p.AuxL + o_chunk + u * ld4));
         }
@@ -253,13 +279,18 @@ __device__ __forceinline__ void epilogue_tile_fast(const Params& p, int b, int i
       v.x *= alpha_b; v.y *= alpha_b; v.z *= alpha_b; v.w *= alpha_b;
       const int64_t o = o_chunk + itr * ld4;
       if (MODE == 3 || MODE == 4) {
-        const uint2 hh = axh[itr & 3], ll = axl[itr & 3];
-        if (itr < 4) {                                 // this slot is free again: fetch row itr + 4
-          axh[itr] = __ldcs(reinterpret_cast<const uint2*>(p.AuxH + o_chunk + (itr + 4) * ld4));
-          axl[itr] = __ldcs(reinterpret_cast<const uint2*>(p.AuxL + o_chunk + (itr + 4) * ld4));
+        const uint2 hh = axh[itr % AW], ll = axl[itr % AW];
+        if (AW == 8) {
+          if (cc + 1 < EPI_CHUNKS) {                   // the slot is free again: fetch the same row of the next chunk
+            axh[itr] = __ldcs(reinterpret_cast<const uint2*>(p.AuxH + o + 32));
+            axl[itr] = __ldcs(reinterpret_cast<const uint2*>(p.AuxL + o + 32));
+          }
+        } else if (itr < 4) {                          // fetch row itr + 4 of this chunk
+          axh[itr] = __ldcs(reinterpret_cast<const uint2*>(p.AuxH + o + 4 * ld4));
+          axl[itr] = __ldcs(reinterpret_cast<const uint2*>(p.AuxL + o + 4 * ld4));
         } else if (cc + 1 < EPI_CHUNKS) {              // ... and row itr - 4 of the next chunk
-          axh[itr - 4] = __ldcs(reinterpret_cast<const uint2*>(p.AuxH + o_chunk + 32 + (itr - 4) * ld4));
-          axl[itr - 4] = __ldcs(reinterpret_cast<const uint2*>(p.AuxL + o_chunk + 32 + (itr - 4) * ld4));
+          axh[itr - 4] = __ldcs(reinterpret_cast<const uint2*>(p.AuxH + o + 32 - 4 * ld4));
+          axl[itr - 4] = __ldcs(reinterpret_cast<const uint2*>(p.AuxL + o + 32 - 4 * ld4));
         }
         float4 ax;
         ax.x = unpack_sum(hh.x, ll.x, 0) * inv_saux; ax.y = unpack_sum(hh.x, ll.x, 1) * inv_saux;
@@ -562,6 +593,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                         (!p.D2h || ((reinterpret_cast<uintptr_t>(p.D2h) & 7) == 0 && (reinterpret_cast<uintptr_t>(p.D2l) & 7) == 0));
     float* epi = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256) + (warp - 2) * 32 * 32;
     uint32_t acc_iter = 0;
+    bool aux_ahead = false;                  // this tile's Aux region was already prefetched into L2 during the tile before
     for (uint32_t iter = 0;; ++iter) {
       const int slot = iter & 1;
       mbar_wait(sched_full + slot, (iter >> 1) & 1u);
@@ -573,15 +605,32 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const bool has_acc = ti.nkb > 0;
       if (!has_acc && !ti.zero) continue;
       const uint32_t as = acc_iter & 1u;
-      if (F16 && (p.epi_mode == 3 || p.epi_mode == 4) && p.AuxH && has_acc && ti.i0 + BM <= p.m && ti.j0 + BN <= p.n) {
-        // while the MMAs of this tile run: pull this warp's part of the Aux planes (32 rows x 128 columns x 2 planes) into L2
-        const __half* ah = p.AuxH + (int64_t)ti.b * p.sD + (int64_t)(ti.i0 + q * 32 + lane) * p.ldd + ti.j0 + c_begin * 32;
-        const __half* al = p.AuxL + (int64_t)ti.b * p.sD + (int64_t)(ti.i0 + q * 32 + lane) * p.ldd + ti.j0 + c_begin * 32;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(ah));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(al));
-        if (EPI_CHUNKS > 2) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(ah + 64));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(al + 64));
+      if (F16 && (p.epi_mode == 3 || p.epi_mode == 4) && p.AuxH) {
+        // pull this warp's part of the Aux planes (32 rows x 128 columns x 2 planes) into L2: of this tile unless that was done
+        // a tile ago, and of the NEXT tile when the scheduler has already handed it out (the slot cannot be refilled before this
+        // warp arrives on it, so the peek is safe).  With the epilogue as the bottleneck of these modes the hand-out of the
+        // current tile comes too late for the prefetch to land before the loads.
+        auto aux_prefetch = [&](const TileInfo& tj) {
+          const __half* ah = p.AuxH + (int64_t)tj.b * p.sD + (int64_t)(tj.i0 + q * 32 + lane) * p.ldd + tj.j0 + c_begin * 32;
+          const __half* al = p.AuxL + (int64_t)tj.b * p.sD + (int64_t)(tj.i0 + q * 32 + lane) * p.ldd + tj.j0 + c_begin * 32;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(ah));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(al));
+          if (EPI_CHUNKS > 2) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(ah + 64));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(al + 64));
+          }
+        };
+        if (!aux_ahead && has_acc && ti.i0 + BM <= p.m && ti.j0 + BN <= p.n) aux_prefetch(ti);
+        aux_ahead = false;
+        if (GPZ_UMMA_AUX_AHEAD && mbar_test(sched_full + (slot ^ 1), ((iter + 1) >> 1) & 1u)) {
+          const int tn = sched_tile[slot ^ 1];
+          if (tn >= 0) {
+            const TileInfo tj = tile_info(p, tn, mtiles, ntiles);
+            if (tj.nkb > 0 && tj.i0 + BM <= p.m && tj.j0 + BN <= p.n) {
+              aux_prefetch(tj);
+              aux_ahead = true;
+            }
+          }
         }
       }
       if (has_acc) {

@@ -8,6 +8,7 @@ All Functions work on L-batched, contiguous CUDA tensors in float32 or float64.
 from __future__ import annotations
 
 import os
+import sys
 
 import torch
 from torch.autograd import Function
@@ -52,7 +53,7 @@ def side_stream(device):
         # the kernel-build backward runs on this stream by design; autograd orders it against the parameters' accumulation on the
         # main stream (that synchronisation is wanted) and would otherwise print a one-off warning about the stream mismatch
         mute = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
-        if mute is not None:
+        if mute is not None and os.environ.get("GPZ_NO_MUTE") != "1":
             mute(False)
     return st
 
@@ -62,17 +63,17 @@ def set_sync_checks(flag: bool):
     SYNC_CHECKS = bool(flag)
 
 
-_pending_amax = []        # (stats tensor, names) of split-FP16 predict calls whose tracked maxima have not been examined yet
+_pending_amax = {}        # (names, device) -> running max of amax * scale of the split-FP16 predict calls not examined yet
 
 
 def check_cholesky_info():
     """Deferred error checks of the step (one device sync): LAPACK-style `info` of every Cholesky and the overflow guard of
     the split-FP16 planes (a scale bound that did not hold makes an entry inf, which shows up as a non-finite tracked max)."""
     global _pending_info, _pending_amax
-    pend16, _pending_amax = _pending_amax, []
-    pend, _pending_info = _pending_info, []          # both lists are cleared before anything can raise
-    for amax, scale, names in pend16:
-        bad = ~(amax * scale <= 65504.0)               # also true for NaN / inf
+    pend16, _pending_amax = _pending_amax, {}
+    pend, _pending_info = _pending_info, []          # both are cleared before anything can raise
+    for (names, _dev), v in pend16.items():
+        bad = ~(v <= 65504.0)                          # also true for NaN / inf
         if bool(bad.any()):
             which = sorted({names[int(i)] for i in bad.nonzero()[:, 0]})
             raise _cabi.GpzError("split-FP16 predict: " + ", ".join(which) + " left the fp16 range its scale bound allows (or the "
@@ -86,25 +87,72 @@ def check_cholesky_info():
                 f"(leading minor of order {int(info[l])} is not positive-definite)")
 
 
-def _fold_pending_amax():
-    """Long unsynchronised runs: fold the queued overflow guards into ONE entry per name (running max of amax * scale on the
-    device, no sync), so that no guard is ever dropped unexamined."""
-    global _pending_amax
-    acc = {}
-    for amax, scale, names in _pending_amax:
-        v = amax * scale
-        v = torch.where(torch.isnan(v), torch.full_like(v, float("inf")), v)       # fmax would hide a NaN
-        for i, nm in enumerate(names):
-            cur = v[i].max().reshape(1)
-            acc[nm] = cur if nm not in acc else torch.maximum(acc[nm], cur)
-    names = tuple(acc)
-    if names:
-        _pending_amax = [(torch.stack([acc[n] for n in names]), torch.ones((len(names), 1), dtype=acc[names[0]].dtype,
-                                                                          device=acc[names[0]].device), names)]
+def _track_info(info):
+    """Queue a Cholesky `info` vector for the deferred check; long unsynchronised runs fold the queue (largest non-zero minor
+    per factor, one launch per distinct shape) so that it stays bounded and no failure is dropped."""
+    global _pending_info
+    _pending_info.append(info)
+    if len(_pending_info) > 256:
+        groups = {}
+        for t in _pending_info:
+            groups.setdefault((tuple(t.shape), t.device), []).append(t)
+        _pending_info = [torch.stack(g).amax(dim=0) for g in groups.values()]
+
+
+def _track_amax(amax, scale, names):
+    """Queue the overflow guard of one split-FP16 call: a running maximum of amax * scale per name on the device (two small
+    launches, no sync, nothing retained from the call; torch.maximum propagates NaN).  Examined by check_cholesky_info()."""
+    v = amax * scale
+    key = (names, v.device)
+    cur = _pending_amax.get(key)
+    if cur is None or cur.shape != v.shape:
+        if cur is not None:
+            v = torch.maximum(v, cur.amax(dim=-1, keepdim=True).expand_as(v))
+        _pending_amax[key] = v
+    else:
+        torch.maximum(cur, v, out=cur)
 
 
 def _c(t):
     return t if t.is_contiguous() else t.contiguous()
+
+
+# Scratch that lives only inside one backward call (the A diag(2 gv) and dL/dA planes: 2 x 4 L M N bytes, the chain backward's
+# M x M workspaces) is kept resident per (purpose, device, stream) instead of going through the caching allocator every step:
+# requests of 0.67 GB and 1.34 GB interleaved made the allocator split and re-grow its pool for dozens of steps (a cudaMalloc of
+# 1.3 GB inside a backward stalls the host for ~100 ms; bench.py round 2 saw 8.5 -> 19 ms/step from it).  Reuse is safe because a
+# buffer is written and consumed by launches of ONE Function.backward call on ONE stream, and the next use is ordered behind
+# them on that stream.  `release_workspaces()` returns the memory.
+_workspaces = {}
+_workspace_readers = {}     # (purpose, stream) -> event of the last launch on ANOTHER stream that read the workspace
+
+
+def _workspace(tag, shape, dtype, device):
+    device = torch.device(device)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    key = (tag, idx, torch.cuda.current_stream(idx).cuda_stream)
+    n = 1
+    for d in shape:
+        n *= int(d)
+    nbytes = n * torch.empty((), dtype=dtype).element_size()
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        _workspaces.pop(key, None)
+        buf = _workspaces[key] = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+    return buf[:nbytes].view(dtype).view(*shape)
+
+
+def release_workspaces():
+    """Drop the resident backward scratch (it is re-created on the next step)."""
+    _workspaces.clear()
+    _workspace_readers.clear()
+
+
+def _plane_pair(L, m, n, device):
+    """(hi, lo) fp16 planes as ONE allocation of 4 L m n bytes -- the size of every other large tensor of the step (fp32 dL/dKzx,
+    the other plane pairs), so that the caching allocator reuses blocks one-to-one and never splits them."""
+    pair = torch.empty((2, L, m, n), dtype=torch.float16, device=device)
+    return pair[0], pair[1]
 
 
 def gemm(A, B, ta=False, tb=False, alpha=1.0, beta=0.0, out=None, a_tri=0, b_tri=0, d_tri=0, splitk=1):
@@ -308,24 +356,41 @@ class KernelBuild(Function):
         if G is None:
             return (None,) * 12
         x1, x2, sigma, ls, a, r2, g1, g2 = ctx.saved_tensors
-        dt = x1.dtype
-        G = _c(G)
-        n1, D = x1.shape
-        n2 = x2.shape[0]
-        L = sigma.numel()
-        mg = g1 is not None
-        need = ctx.needs_input_grad
-        g_x1 = torch.empty_like(x1) if need[0] else None
-        g_x2 = torch.empty_like(x2) if need[1] else None
-        g_sigma = torch.empty_like(sigma)
-        g_ls = torch.empty_like(ls)
-        g_a = torch.empty_like(a) if mg else None
-        ws = torch.empty(3 * L + n1 * D, dtype=torch.float64, device=x1.device)
-        call("kernel_build_bwd", dt, ptr(x1), ptr(x2), ptr(sigma), ptr(ls), ptr(a), ptr(r2), ptr(g1), ptr(g2),
-             c_i(n1), c_i(n2), c_i(D), c_i(L), c_i(r2.shape[0] if mg else 0), c_i(getattr(ctx, "kind", 0)), scalar(dt, ctx.p_half),
-             ptr(G),
-             ptr(g_x1), ptr(g_x2), ptr(g_sigma), ptr(g_ls), ptr(g_a), ptr(ws))
-        return g_x1, g_x2, g_sigma, g_ls, g_a, None, None, None, None, None, None, None
+        grads = _kernel_build_bwd(x1, x2, sigma, ls, a, r2, g1, g2, ctx.p_half, getattr(ctx, "kind", 0), ctx.needs_input_grad[:2], G)
+        return grads + (None,) * 7
+
+
+def _kernel_build_bwd(x1, x2, sigma, ls, a, r2, g1, g2, p_half, kind, need, G):
+    """(dL/dx1, dL/dx2, dL/dsigma, dL/dlengthscale, dL/da) from dL/dK on the current stream (csrc/kernel_build.cu)."""
+    dt = x1.dtype
+    G = _c(G)
+    n1, D = x1.shape
+    n2 = x2.shape[0]
+    L = sigma.numel()
+    mg = g1 is not None
+    g_x1 = torch.empty_like(x1) if need[0] else None
+    g_x2 = torch.empty_like(x2) if need[1] else None
+    g_sigma = torch.empty_like(sigma)
+    g_ls = torch.empty_like(ls)
+    g_a = torch.empty_like(a) if mg else None
+    ws = torch.empty(3 * L + n1 * D, dtype=torch.float64, device=x1.device)
+    call("kernel_build_bwd", dt, ptr(x1), ptr(x2), ptr(sigma), ptr(ls), ptr(a), ptr(r2), ptr(g1), ptr(g2),
+         c_i(n1), c_i(n2), c_i(D), c_i(L), c_i(r2.shape[0] if mg else 0), c_i(int(kind)), scalar(dt, p_half),
+         ptr(G),
+         ptr(g_x1), ptr(g_x2), ptr(g_sigma), ptr(g_ls), ptr(g_a), ptr(ws))
+    return g_x1, g_x2, g_sigma, g_ls, g_a
+
+
+class KernelBuildBox:
+    """Hand-over between KernelBuildH and the consumer of its planes (SvgpMomentsH).  The consumer's backward launches the
+    kernel-build backward ITSELF on the side stream, as soon as dL/dKzx exists (so it overlaps the M x M x M chain backward that
+    follows on the main stream, and dL/dKzx stays a resident workspace instead of a 4 L M N-byte tensor handed across streams
+    through the autograd engine, whose deferred cross-stream frees made the allocator grow for a dozen steps); the gradients
+    wait here until autograd reaches KernelBuildH.backward, which then only returns them."""
+    __slots__ = ("args", "grads", "event")
+
+    def __init__(self):
+        self.args = self.grads = self.event = None
 
 
 class KernelBuildH(Function):
@@ -334,7 +399,7 @@ class KernelBuildH(Function):
     whose only job is to carry dL/dK back to `gpz_kernel_build_bwd` (which recomputes K and never needed it stored)."""
 
     @staticmethod
-    def forward(ctx, x1, x2, sigma, ls, a, r2, g1, g2, p_half, jitter, kind=0):
+    def forward(ctx, x1, x2, sigma, ls, a, r2, g1, g2, p_half, jitter, kind=0, box=None):
         x1, x2, sigma, ls = _c(x1), _c(x2), _c(sigma), _c(ls)
         dt = x1.dtype
         assert dt == torch.float32
@@ -345,8 +410,7 @@ class KernelBuildH(Function):
         mg = g1 is not None
         if mg:
             a, r2, g1, g2 = _c(a), _c(r2), _c(g1), _c(g2)
-        Kh = torch.empty((L, n1, n2), dtype=torch.float16, device=x1.device)
-        Kl = torch.empty_like(Kh)
+        Kh, Kl = _plane_pair(L, n1, n2, x1.device)
         sK = torch.empty(L, dtype=dt, device=x1.device)
         call("kernel_build_fwd_h", dt, ptr(x1), ptr(x2), ptr(sigma), ptr(ls), ptr(a if mg else None),
              ptr(r2 if mg else None), ptr(g1 if mg else None), ptr(g2 if mg else None), c_i(n1), c_i(n2), c_i(D), c_i(L),
@@ -355,6 +419,10 @@ class KernelBuildH(Function):
                               g2 if mg else None)
         ctx.p_half = p_half
         ctx.kind = int(kind)
+        ctx.box = box
+        if box is not None:
+            box.args = (x1, x2, sigma, ls, a if mg else None, r2 if mg else None, g1 if mg else None, g2 if mg else None,
+                        p_half, int(kind), tuple(ctx.needs_input_grad[:2]))
         handle = torch.empty(1, dtype=dt, device=x1.device).expand(L, n1, n2)
         ctx.set_materialize_grads(False)      # otherwise autograd zero-fills "gradients" for the fp16 planes (2 x 0.67 GB)
         ctx.mark_non_differentiable(Kh, Kl, sK)
@@ -363,7 +431,17 @@ class KernelBuildH(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, G, *unused):
-        return KernelBuild.backward(ctx, G)[:11]
+        box = ctx.box
+        if box is not None and box.grads is not None:
+            grads, box.grads = box.grads, None
+            torch.cuda.current_stream().wait_event(box.event)
+            if G is not None and any(st != 0 for st in G.stride()):
+                # dL/dK also arrived through the graph (the stand-in had a second consumer): the consumer's token is zero, so G
+                # is exactly that remainder
+                extra = KernelBuild.backward(ctx, G)[:5]
+                grads = tuple(g if e is None else (e if g is None else g + e) for g, e in zip(grads, extra))
+            return grads + (None,) * 7
+        return KernelBuild.backward(ctx, G)[:12]
 
 
 def cdist(x1, x2):
@@ -393,7 +471,7 @@ class CholeskyInverse(Function):
             call("chol_inv_tc", dt, ptr(W), ptr(Lc), ptr(Linv), ptr(tmp), ptr(lo_ws), c_i(M), c_i(L), ptr(info))
         else:
             call("chol_inv", dt, ptr(W), ptr(Lc), ptr(Linv), ptr(tmp), c_i(M), c_i(L), ptr(info))
-        _pending_info.append(info)
+        _track_info(info)
         if SYNC_CHECKS:
             check_cholesky_info()
         ctx.save_for_backward(Lc, Linv)
@@ -446,7 +524,7 @@ class SvgpChain(Function):
         info = torch.empty(L, dtype=torch.int32, device=dev)
         call("svgp_chain_fwd", dt, ptr(W), ptr(Lu_raw), ptr(mu), ptr(Lc), ptr(Linv), ptr(Lu), ptr(T), ptr(q), ptr(kl), ptr(aux),
              ptr(ws), c_i(M), c_i(L), c_i(chol_tc), ptr(info))
-        _pending_info.append(info)
+        _track_info(info)
         if SYNC_CHECKS:
             check_cholesky_info()
         ctx.save_for_backward(Lc, Linv, Lu, T, q, mu, aux)
@@ -546,7 +624,7 @@ class SvgpMomentsH(Function):
     of two reductions and 11 products."""
 
     @staticmethod
-    def forward(ctx, Kzz, Lu_raw, mu, Kxx, Kzx, Kh, Kl, sK, consume):
+    def forward(ctx, Kzz, Lu_raw, mu, Kxx, Kzx, Kh, Kl, sK, consume, box=None):
         L, M, _ = Kzz.shape
         dt, dev = Kzz.dtype, Kzz.device
         N = Kh.shape[-1]
@@ -563,8 +641,8 @@ class SvgpMomentsH(Function):
         info = torch.empty(L, dtype=torch.int32, device=dev)
         call("svgp_chain_fwd", dt, ptr(W), ptr(Lu_raw), ptr(mu), ptr(Lc), ptr(Linv), ptr(Lu), ptr(T), ptr(q), ptr(kl), ptr(aux),
              ptr(ws), c_i(M), c_i(L), c_i(chol_tc), ptr(info))
-        _pending_info.append(info)
-        Ah, Al, Ch, Cl = (torch.empty_like(Kh) for _ in range(4))
+        _track_info(info)
+        (Ah, Al), (Ch, Cl) = _plane_pair(L, M, N, dev), _plane_pair(L, M, N, dev)
         mean = torch.empty((L, N), dtype=dt, device=dev)
         var = torch.empty_like(mean)
         ws_h = torch.empty(8 * L * M * M, dtype=torch.float16, device=dev)
@@ -573,13 +651,12 @@ class SvgpMomentsH(Function):
              ptr(Cl), ptr(mean), ptr(var), ptr(ws_h), ptr(ws_f), c_i(M), c_i(N), c_i(L))
         st = ws_f[2 * L * N:].view(-1, L)
         r_sA, r_aA, r_aC, r_sC = (_stat_row(i) for i in (0, 1, 2, 5))
-        _pending_amax.append((torch.stack((st[r_aA], st[r_aC])), torch.stack((st[r_sA], st[r_sC])), ("A", "C")))
-        if len(_pending_amax) > 64:
-            _fold_pending_amax()
+        _track_amax(torch.stack((st[r_aA], st[r_aC])), torch.stack((st[r_sA], st[r_sC])), ("A", "C"))
         if SYNC_CHECKS:
             check_cholesky_info()
         ctx.save_for_backward(Lc, Linv, Lu, T, q, mu, aux, Kh, Kl, sK, Ah, Al, Ch, Cl, ws_h, ws_f)
         ctx.set_materialize_grads(False)
+        ctx.box = box
         return mean, var, kl, Lc, Lu
 
     @staticmethod
@@ -592,22 +669,44 @@ class SvgpMomentsH(Function):
         gm = _c(gm) if gm is not None else torch.zeros((L, N), dtype=dt, device=dev)
         gv = _c(gv) if gv is not None else torch.zeros((L, N), dtype=dt, device=dev)
         gkl, gLc, gLu = cc(gkl), cc(gLc), cc(gLu)
-        AWh, AWl, gAh, gAl = (torch.empty_like(Kh) for _ in range(4))
-        gKzx = torch.empty((L, M, N), dtype=dt, device=dev)
+        AWh, AWl, gAh, gAl = _workspace("predict_bwd_planes", (4, L, M, N), torch.float16, dev)
+        box = ctx.box
+        early = box is not None and box.args is not None and ctx.needs_input_grad[4]
+        main = torch.cuda.current_stream()
+        if early:
+            # dL/dKzx never leaves this call: resident workspace, read by the kernel-build backward launched below on the side stream
+            gKzx = _workspace("moments_gKzx", (L, M, N), dt, dev)
+            wkey = ("moments_gKzx", main.cuda_stream)
+            if wkey in _workspace_readers:
+                main.wait_event(_workspace_readers[wkey])             # the previous step's reader (side stream) is done with it
+        else:
+            gKzx = torch.empty((L, M, N), dtype=dt, device=dev) if ctx.needs_input_grad[4] else _workspace(
+                "moments_gKzx", (L, M, N), dt, dev)
         gqp = torch.empty((L, M), dtype=dt, device=dev)
-        S = torch.empty((2, L, M, M), dtype=dt, device=dev)                 # S1 and its lo plane
+        S = _workspace("moments_bwd_S", (2, L, M, M), dt, dev)              # S1 and its lo plane
         call("svgp_predict_bwd_h", dt, ptr(Kh), ptr(Kl), ptr(sK), ptr(T), ptr(q), ptr(Ah), ptr(Al), ptr(Ch), ptr(Cl), ptr(gm), ptr(gv),
              ptr(AWh), ptr(AWl), ptr(gAh), ptr(gAl), ptr(gKzx), ptr(None), ptr(None), ptr(gqp), ptr(ws_h), ptr(ws_f), ptr(Lc), ptr(S),
              c_i(M), c_i(N), c_i(L))
         stt = ws_f[2 * L * N:].view(-1, L)
-        _pending_amax.append((stt[_stat_row(4)].unsqueeze(0), stt[_stat_row(3)].unsqueeze(0), ("dL/dA",)))
+        _track_amax(stt[_stat_row(4)].unsqueeze(0), stt[_stat_row(3)].unsqueeze(0), ("dL/dA",))
+        if early:
+            side = side_stream(dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                box.grads = _kernel_build_bwd(*box.args, gKzx)
+                box.event = torch.cuda.Event()
+                box.event.record(side)
+            _workspace_readers[wkey] = box.event
+            g_handle = torch.zeros(1, dtype=dt, device=dev).expand(L, M, N)   # zero token: KernelBuildH.backward returns box.grads
+        else:
+            g_handle = gKzx if ctx.needs_input_grad[4] else None
         gKzz = torch.empty((L, M, M), dtype=dt, device=dev)
         gLu_raw = torch.empty_like(gKzz)
         gmu = torch.empty((L, M), dtype=dt, device=dev)
-        ws = torch.empty((13 * L * M * M + 2 * L * M,), dtype=dt, device=dev)
+        ws = _workspace("chain_bwd_s1_ws", (13 * L * M * M + 2 * L * M,), dt, dev)
         call("svgp_chain_bwd_s1", dt, ptr(Lc), ptr(Linv), ptr(Lu), ptr(T), ptr(q), ptr(mu), ptr(aux), ptr(S[0]), ptr(S[1]), ptr(gqp),
              ptr(gkl), ptr(gLc), ptr(gLu), ptr(gKzz), ptr(gLu_raw), ptr(gmu), ptr(ws), c_i(M), c_i(L))
-        return gKzz, gLu_raw, gmu, gv, gKzx, None, None, None, None
+        return gKzz, gLu_raw, gmu, gv, g_handle, None, None, None, None, None
 
 
 class LowerCholesky(Function):
@@ -748,7 +847,7 @@ class PredictH(Function):
         dt = Linv.dtype
         L, M, N = Kh.shape
         dev = Kh.device
-        Ah, Al, Ch, Cl = (torch.empty_like(Kh) for _ in range(4))
+        (Ah, Al), (Ch, Cl) = _plane_pair(L, M, N, dev), _plane_pair(L, M, N, dev)
         mean = torch.empty((L, N), dtype=dt, device=dev)
         var = torch.empty_like(mean)
         ws_h = torch.empty(8 * L * M * M, dtype=torch.float16, device=dev)
@@ -759,9 +858,7 @@ class PredictH(Function):
         # tracked max |A|, max |C| (slots 7, 8 of the stats block, csrc/predict.cu): examined lazily with the Cholesky info
         st = ws_f[2 * L * N:].view(-1, L)
         r_sA, r_aA, r_aC, r_sC = (_stat_row(i) for i in (0, 1, 2, 5))
-        _pending_amax.append((torch.stack((st[r_aA], st[r_aC])), torch.stack((st[r_sA], st[r_sC])), ("A", "C")))
-        if len(_pending_amax) > 64:
-            _fold_pending_amax()
+        _track_amax(torch.stack((st[r_aA], st[r_aC])), torch.stack((st[r_sA], st[r_sC])), ("A", "C"))
         if SYNC_CHECKS:
             check_cholesky_info()
         return mean, var
@@ -775,7 +872,7 @@ class PredictH(Function):
         dev = Kh.device
         gm = _c(gm) if gm is not None else torch.zeros((L, N), dtype=dt, device=dev)
         gv = _c(gv) if gv is not None else torch.zeros((L, N), dtype=dt, device=dev)
-        AWh, AWl, gAh, gAl = (torch.empty_like(Kh) for _ in range(4))
+        AWh, AWl, gAh, gAl = _workspace("predict_bwd_planes", (4, L, M, N), torch.float16, dev)
         gKzx = torch.empty((L, M, N), dtype=dt, device=dev)
         gLinv = torch.zeros_like(Linv)
         gT = torch.zeros_like(T)
@@ -786,7 +883,7 @@ class PredictH(Function):
              ptr(AWh), ptr(AWl), ptr(gAh), ptr(gAl), ptr(gKzx), ptr(gLinv), ptr(gT), ptr(gq), ptr(ws_h), ptr(ws_f), ptr(Lc), ptr(ws_m),
              c_i(M), c_i(N), c_i(L))
         st = ws_f[2 * L * N:].view(-1, L)
-        _pending_amax.append((st[_stat_row(4)].unsqueeze(0), st[_stat_row(3)].unsqueeze(0), ("dL/dA",)))   # max |gA| vs its scale
+        _track_amax(st[_stat_row(4)].unsqueeze(0), st[_stat_row(3)].unsqueeze(0), ("dL/dA",))   # max |gA| vs its scale
         return gv, gKzx, gLinv, gT, gq, None, None, None, None
 
 

@@ -141,7 +141,8 @@ class _SparseGPBase(nn.Module):
         if Kxx.shape[0] != L:
             Kxx = Kxx.expand(L, -1)
         main.wait_stream(side)
-        mean, var, kl, Lc, Lu = F.SvgpMomentsH.apply(Kzz, Lu_raw.to(dt), mu.to(dt), Kxx, handle, Kh, Kl, sK, True)
+        mean, var, kl, Lc, Lu = F.SvgpMomentsH.apply(Kzz, Lu_raw.to(dt), mu.to(dt), Kxx, handle, Kh, Kl, sK, True,
+                                                     getattr(handle, "_gpz_box", None))
         return dict(mean=mean, var=var, kl=kl, Lc=Lc, Lu=Lu, T=None, q=None, _chain=None)
 
     def moments(self, X, groupsX=None, _chain=None):

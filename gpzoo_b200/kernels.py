@@ -49,10 +49,14 @@ class _RBFBase(nn.Module):
         dt = X.dtype
         sigma, ls = sigma.to(dt), ls.to(dt)
         if want_h:      # split-FP16 planes for the tensor-core predict: (stand-in for K, Kh, Kl, scale), leading L kept
+            box = F.KernelBuildBox()       # lets the consumer of the planes launch this build's backward early (functional.py)
             if groupsX is not None:
-                return F.KernelBuildH.apply(X, Z, sigma, ls, self._group_coeff().to(dt), _r2_table(self.embedding, dt).to(X.device),
-                                            groupsX, groupsZ, 0.5 * float(self.input_dim), float(jitter))
-            return F.KernelBuildH.apply(X, Z, sigma, ls, None, None, None, None, 1.0, float(jitter), self._kind)
+                out = F.KernelBuildH.apply(X, Z, sigma, ls, self._group_coeff().to(dt), _r2_table(self.embedding, dt).to(X.device),
+                                           groupsX, groupsZ, 0.5 * float(self.input_dim), float(jitter), 0, box)
+            else:
+                out = F.KernelBuildH.apply(X, Z, sigma, ls, None, None, None, None, 1.0, float(jitter), self._kind, box)
+            out[0]._gpz_box = box
+            return out
         if groupsX is not None:
             a = self._group_coeff().to(dt)
             r2 = _r2_table(self.embedding, dt).to(X.device)
