@@ -680,6 +680,494 @@ template <int FP> int poisson_launch3(const PoissonArgs<float>& a, dim3 grid, cu
   return GPZ_OK;
 }
 
+
+// ---- v4 (fp32, F <= 16): the three F-long contractions on the tensor cores ------------------------------------------------
+// v2 / v3 are bound by instruction issue (3.3 warp instructions per (gene, spot) element, 36 of the 105 thread instructions being
+// the FMAs of the contractions); HBM sits at 12 %.  Here the contractions are warp-level MMAs (mma.sync m16n8k16, bf16 operands,
+// fp32 accumulation) chained in registers the way a fused attention kernel chains QK^T -> P -> PV:
+//   C1[n, g] = EF'^T[n, :] Wm[g, :]^T                      rate tile (16 spots x 8 genes), EF' = softplus(V) exp(F)
+//   t'       = (y / C1 - 1) / E,  ll += y log2 C1          element-wise on the accumulator fragment, y read straight into that layout
+//   D2[n, l] += t'^T[n, g] Wm[g, l]                        the packed C1 fragments of two gene tiles ARE the A fragment (d ll / d EF')
+//   D3[l, g] += EF'[l, n] t'^T[n, g]                       B fragment = movmatrix-transposed packed t' (d ll / d Wm, over the spots)
+// Every operand is split x = hi + lo into two bf16 (|x - hi - lo| <= 2^-18 |x|) and a product is hi*hi + hi*lo + lo*hi, so a
+// contraction carries ~1e-5 relative error at worst (1e-6 measured on the gradients) - bf16 rather than fp16 because exp(F) and y / r
+// have fp32 range.  Three launches:
+//   prep  per gene: softplus(W) as bf16 hi / lo planes [G][16] + fp32 column sums per gene range; per spot and sample: EF' as bf16
+//         planes [E][B][16]; zeroes the D2 accumulator.  Everything that is per gene or per spot is done ONCE here, not once per CTA.
+//   main  grid (256-spot blocks) x (gene ranges).  A warp owns 32 spots (two 16-spot sub-tiles, D2 resident in registers over the
+//         CTA's gene range) and walks the range in 16-gene blocks; D3 is summed over the sub-tiles in registers, over the warps through
+//         shared memory once per 64-gene chunk, and leaves as per-CTA partials (same workspace layout as v2).  D2 leaves by vector
+//         atomics into [E][B][16].  ~0.6 warp instructions per element instead of 3.3.
+//   post  gW = softplus'(W) * sum of the partials; per spot: gF = EF' D2 -> d/dmean, d/dspread, d/dV, and the terms that never needed
+//         the G x B elements: sum_g r = sum_l EF'_l (sum_g Wm_gl), d ll / d V = softplus'(V) / softplus(V) sum_l EF'_l D2_l; the last
+//         block to finish adds up the log-likelihood partials.
+constexpr int P4_WARPS = 8, P4_THREADS = 32 * P4_WARPS, P4_SUB = 2, P4_SPOTS = P4_WARPS * P4_SUB * 16;
+constexpr int P4_GCH = 64;            // genes per staged chunk of loadings (four 16-gene blocks)
+constexpr int P4_WLD = 24;            // bf16 per shared-memory row of loadings: 48-byte rows keep ldmatrix conflict-free
+constexpr int P4_ALD = 72;            // floats per row of the D3 exchange buffer: float2 stores of a half-warp hit 32 distinct banks
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float e0, float e1) {      // e0 -> bits 0..15, e1 -> bits 16..31
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(e1), "f"(e0));
+  return d;
+}
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16x2(x0, x1);
+  lo = pack_bf16x2(x0 - __uint_as_float(hi << 16), x1 - __uint_as_float(hi & 0xffff0000u));
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t movmatrix_t(uint32_t a) {              // 8x8 b16 transpose across the warp
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&d)[4], const void* p) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_t(uint32_t (&d)[4], const void* p) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]) : "r"(addr));
+}
+
+// workspace of the v4 path behind the ll / gW partials
+struct Poisson4Ws {
+  uint16_t* wh; uint16_t* wl;          // [G][16]   softplus(W), bf16 hi / lo (factors >= F are zero)
+  float* wsum;                         // [nby][16] column sums of softplus(W) over the gene range of grid row y
+  uint16_t* efh; uint16_t* efl;        // [E][B][16] EF' = softplus(V) exp(mean + eps sd), bf16 hi / lo
+  float* d2;                           // [E][B][16] sum_g t'[g, n] Wm[g, l]
+  double* rs_part;                     // [post spot blocks] sum over the block's spots of sum_l EF'_l Wsum_l
+  unsigned int* ticket;                // last-block-done counter of the post kernel
+};
+
+// EF'[l, n] of sample e for the four factors lq .. lq + 3 of spot n (exact fp32; used by prep and by post).  All twelve loads are issued
+// before anything is computed (factor indices clamped instead of predicated): one memory latency, not twelve.
+__device__ __forceinline__ void poisson_ef4(const PoissonArgs<float>& a, int e, int n, int lq, float spV, float (&ev)[4], float (&epsv)[4],
+                                            float (&sdv)[4]) {
+  float sp[4], mn[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int f = min(lq + j, a.F - 1);
+    const int64_t o = (int64_t)f * a.B + n;
+    sp[j] = a.spread[o];
+    mn[j] = a.mean[o];
+    epsv[j] = a.eps[((int64_t)e * a.F + f) * a.B + n];
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int f = lq + j;
+    sdv[j] = f < a.n_var ? sqrtf(sp[j] > a.clamp_min ? sp[j] : a.clamp_min) : sp[j];
+    ev[j] = f < a.F ? spV * expf(fmaf(epsv[j], sdv[j], mn[j])) : 0.f;
+  }
+}
+
+// blocks [0, nby): loadings of one gene range; blocks [nby, ...): 64 spots of one sample each (thread <-> spot tid / 4, factors 4 (tid & 3)..+3)
+__global__ void __launch_bounds__(256) poisson_prep4_kernel(const PoissonArgs<float> a, const Poisson4Ws w, int nby, int spot_blocks) {
+  __shared__ float part[8][16];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int lq = (tid & 3) * 4;
+  if ((int)blockIdx.x < nby) {
+    if (blockIdx.x == 0 && tid == 0) *w.ticket = 0u;
+    const int g_begin = blockIdx.x * a.genes_per_cta, g_end = min(a.G, g_begin + a.genes_per_cta);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int g = g_begin + (tid >> 2); g < g_end; g += 64) {
+      float wv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        wv[j] = 0.f;
+        if (lq + j < a.F) {
+          wv[j] = a.W[(int64_t)g * a.F + lq + j];
+          if (a.w_softplus) wv[j] = softplus(wv[j]);
+        }
+        acc[j] += wv[j];
+      }
+      uint32_t h0, l0, h1, l1;
+      split_bf16x2(wv[0], wv[1], h0, l0);
+      split_bf16x2(wv[2], wv[3], h1, l1);
+      *reinterpret_cast<uint2*>(w.wh + (int64_t)g * 16 + lq) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(w.wl + (int64_t)g * 16 + lq) = make_uint2(l0, l1);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v = acc[j];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (lane < 4) part[warp][lq + j] = v;
+    }
+    __syncthreads();
+    if (tid < 16) {
+      float v = 0.f;
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) v += part[w8][tid];
+      w.wsum[blockIdx.x * 16 + tid] = v;
+    }
+    return;
+  }
+  const int sb = blockIdx.x - nby, e = sb / spot_blocks, n = (sb - e * spot_blocks) * 64 + (tid >> 2);
+  if (n >= a.B) return;
+  const float spV = softplus(a.V[a.idx ? a.idx[n] : (int64_t)n]);
+  float ev[4], epsv[4], sdv[4];
+  poisson_ef4(a, e, n, lq, spV, ev, epsv, sdv);
+  uint32_t h0, l0, h1, l1;
+  split_bf16x2(ev[0], ev[1], h0, l0);
+  split_bf16x2(ev[2], ev[3], h1, l1);
+  const int64_t o = ((int64_t)e * a.B + n) * 16 + lq;
+  *reinterpret_cast<uint2*>(w.efh + o) = make_uint2(h0, h1);
+  *reinterpret_cast<uint2*>(w.efl + o) = make_uint2(l0, l1);
+  *reinterpret_cast<float4*>(w.d2 + o) = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+__device__ __noinline__ float lfact_slow(float y) { return lgammaf(y + 1.f); }     // counts >= 64 or non-integer y: rare, kept out of line
+
+template <bool HAS_IDX>
+__global__ void __launch_bounds__(P4_THREADS, 2) poisson_kernel4(const PoissonArgs<float> a, const Poisson4Ws w) {
+  __shared__ __align__(16) uint16_t sWh[P4_GCH][P4_WLD];      // softplus(W) chunk, bf16 hi / lo, [gene][factor]
+  __shared__ __align__(16) uint16_t sWl[P4_GCH][P4_WLD];
+  __shared__ __align__(16) float sAcc[P4_WARPS][16][P4_ALD];  // per-warp D3[l][gene of the chunk]
+  __shared__ double red[32];
+  __shared__ float lfact[64];                                 // log(y!) for integer counts y < 64
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r = lane >> 2, c = lane & 3;                      // fragment coordinates (groupID, threadID_in_group)
+  if (a.with_lgamma && tid < 64) lfact[tid] = lgammaf((float)(tid + 1));
+  const int nw = blockIdx.x * P4_SPOTS + warp * (16 * P4_SUB);          // first spot of the warp
+  const bool block_full = (blockIdx.x + 1) * P4_SPOTS <= a.B;
+  const bool fast_cols = !HAS_IDX && block_full;                        // the thread's four columns are nw + r + {0, 8, 16, 24}
+  const float invE = 1.f / (float)a.E;
+  const int g_begin = blockIdx.y * a.genes_per_cta;
+  const int g_end = min(a.G, g_begin + a.genes_per_cta);
+  constexpr float LN2 = 0.69314718055994530942f;
+
+  // the thread's spots: sub-tile s, half h -> n = nw + 16 s + r + 8 h ; invalid spots read a valid column of y and have EF' = 0
+  int col[P4_SUB][2];                                         // columns of y: 32-bit (Ntot < 2^31)
+  if (!fast_cols) {
+#pragma unroll
+    for (int s = 0; s < P4_SUB; ++s)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int nc = min(nw + 16 * s + r + 8 * h, a.B - 1);
+        col[s][h] = HAS_IDX ? (int)a.idx[nc] : nc;
+      }
+  }
+
+  // y in accumulator-fragment layout: register q = 4 tt + i of sub-tile s <-> gene gblk + 8 tt + 2c + (i & 1), spot half i >> 1.
+  // Rows past the gene range re-read the range's last row (masked when consumed: only the last block of a range is ragged), so the
+  // loads carry no predicate and no select and really are in flight for a whole block.
+  float yreg[P4_SUB][8];
+  const float* ybase = a.y;
+  const int ld = (int)a.y_ld;                          // a row of y is shorter than 2^31 entries
+  const int ld8 = 8 * ld;
+  auto load_y = [&](int s, int gblk) {
+    if (fast_cols && gblk + 16 <= g_end) {
+      // interior block: the four rows 2c, 2c + 1, 2c + 8, 2c + 9 from one base pointer (one 32 x 32 -> 64-bit multiply-add, three adds)
+      const float* p0 = ybase + (int64_t)(gblk + 2 * c) * ld + (nw + r + 16 * s);
+      const float* p1 = p0 + ld;
+      const float* p2 = p0 + ld8;
+      const float* p3 = p2 + ld;
+      yreg[s][0] = __ldcs(p0); yreg[s][1] = __ldcs(p1); yreg[s][2] = __ldcs(p0 + 8); yreg[s][3] = __ldcs(p1 + 8);
+      yreg[s][4] = __ldcs(p2); yreg[s][5] = __ldcs(p3); yreg[s][6] = __ldcs(p2 + 8); yreg[s][7] = __ldcs(p3 + 8);
+      return;
+    }
+    // ragged block / gathered columns: four clamped row pointers
+    const float* rowp[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int g = min(gblk + 8 * (j >> 1) + 2 * c + (j & 1), g_end - 1);
+      rowp[j] = ybase + (int64_t)g * ld;
+    }
+    if (fast_cols) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) yreg[s][q] = __ldcs(rowp[2 * (q >> 2) + (q & 1)] + (nw + r + 16 * s) + 8 * ((q >> 1) & 1));
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) yreg[s][q] = __ldcs(rowp[2 * (q >> 2) + (q & 1)] + col[s][(q >> 1) & 1]);
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < P4_SUB; ++s) load_y(s, g_begin);
+
+  double ll = 0.0;
+  for (int e = 0; e < a.E; ++e) {
+    // operand fragments of the sample: A1 = EF'^T [16 spots x 16 factors] (rate), A3 = EF' [16 factors x 16 spots] (d/dW);
+    // register k of A1 <-> spot half k & 1, factors 2c + 8 (k >> 1) + {0, 1}
+    uint32_t a1h[P4_SUB][4], a1l[P4_SUB][4], a3h[P4_SUB][4], a3l[P4_SUB][4];
+    float d2[P4_SUB][2][4];
+#pragma unroll
+    for (int s = 0; s < P4_SUB; ++s) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int n = nw + 16 * s + r + 8 * (k & 1);
+        a1h[s][k] = 0u; a1l[s][k] = 0u;
+        if (n < a.B) {
+          const int64_t o = (((int64_t)e * a.B + n) * 16 + 2 * c + 8 * (k >> 1)) >> 1;
+          a1h[s][k] = reinterpret_cast<const uint32_t*>(w.efh)[o];
+          a1l[s][k] = reinterpret_cast<const uint32_t*>(w.efl)[o];
+        }
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < P4_SUB; ++s) {
+      a3h[s][0] = movmatrix_t(a1h[s][0]); a3h[s][1] = movmatrix_t(a1h[s][2]);
+      a3h[s][2] = movmatrix_t(a1h[s][1]); a3h[s][3] = movmatrix_t(a1h[s][3]);
+      a3l[s][0] = movmatrix_t(a1l[s][0]); a3l[s][1] = movmatrix_t(a1l[s][2]);
+      a3l[s][2] = movmatrix_t(a1l[s][1]); a3l[s][3] = movmatrix_t(a1l[s][3]);
+#pragma unroll
+      for (int lt = 0; lt < 2; ++lt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d2[s][lt][i] = 0.f;
+    }
+
+    for (int g0 = g_begin; g0 < g_end; g0 += P4_GCH) {
+      __syncthreads();                              // the previous chunk's reduction is done with sAcc; every warp is done with sW
+      {                                             // stage the chunk's loadings: thread <-> (gene tid / 4, factors 4 (tid & 3) ..+3)
+        const int gi = tid >> 2, lq = (tid & 3) * 4;
+        uint2 vh = make_uint2(0u, 0u), vl = make_uint2(0u, 0u);
+        if (g0 + gi < g_end) {
+          vh = *reinterpret_cast<const uint2*>(w.wh + (int64_t)(g0 + gi) * 16 + lq);
+          vl = *reinterpret_cast<const uint2*>(w.wl + (int64_t)(g0 + gi) * 16 + lq);
+        }
+        *reinterpret_cast<uint2*>(&sWh[gi][lq]) = vh;
+        *reinterpret_cast<uint2*>(&sWl[gi][lq]) = vl;
+      }
+      __syncthreads();
+      const int nblk = min(P4_GCH / 16, (g_end - g0 + 15) >> 4);
+      float llc = 0.f, llg = 0.f;
+#pragma unroll 1
+      for (int jb = 0; jb < nblk; ++jb) {
+        const int gblk = g0 + 16 * jb;
+        // next block in (sample, gene) order, for the y prefetch
+        int gnext = gblk + 16;
+        if (gnext >= g_end) gnext = (e + 1 < a.E) ? g_begin : -1;
+        const bool ragged = gblk + 16 > g_end || !block_full;          // uniform: some of the 16 x 32 elements are not there
+        // ldmatrix row addresses.  rate: B[k = factor][n = gene], matrices (genes 0-7, l 0-7), (genes 0-7, l 8-15), (genes 8-15, l 0-7),
+        // (genes 8-15, l 8-15); d/dEF': B[k = gene][n = factor], transposed on load: (genes 0-7, l 0-7), (genes 8-15, l 0-7), (genes 0-7,
+        // l 8-15), (genes 8-15, l 8-15).  The fragments are (re)loaded per sub-tile right before their MMAs to keep them short-lived.
+        const int mi = lane >> 3, row = lane & 7;
+        const int o1 = (16 * jb + (mi >> 1) * 8 + row) * P4_WLD + (mi & 1) * 8;
+        const int o2 = (16 * jb + (mi & 1) * 8 + row) * P4_WLD + (mi >> 1) * 8;
+        float d3[2][4];
+#pragma unroll
+        for (int tt = 0; tt < 2; ++tt)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) d3[tt][i] = 0.f;
+#pragma unroll
+        for (int s = 0; s < P4_SUB; ++s) {
+          float c1[2][4];
+          {
+            uint32_t b1h[4], b1l[4];
+            ldmatrix_x4(b1h, &sWh[0][0] + o1);
+            ldmatrix_x4(b1l, &sWl[0][0] + o1);
+#pragma unroll
+            for (int tt = 0; tt < 2; ++tt) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) c1[tt][i] = 0.f;
+              mma_bf16(c1[tt], a1l[s], b1h[2 * tt], b1h[2 * tt + 1]);
+              mma_bf16(c1[tt], a1h[s], b1l[2 * tt], b1l[2 * tt + 1]);
+              mma_bf16(c1[tt], a1h[s], b1h[2 * tt], b1h[2 * tt + 1]);
+            }
+          }
+          if (ragged) {                             // genes past the range / spots past the minibatch carry no count
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (gblk + 8 * (q >> 2) + 2 * c + (q & 1) >= g_end || nw + 16 * s + r + 8 * ((q >> 1) & 1) >= a.B) yreg[s][q] = 0.f;
+          }
+          // element-wise on the rate fragment
+          float t[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float y = yreg[s][q];
+            const float rate = fmaxf(c1[q >> 2][q & 3], 1e-30f);
+            float rinv;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(rate));
+            llc = fmaf(y, __log2f(rate), llc);
+            t[q] = fmaf(y * invE, rinv, -invE);
+          }
+          if (a.with_lgamma) {
+            // log(y!) from the table, branch-free: the entry of min(trunc(y), 63), exact whenever y is an integer count below 64
+            // (lfact[0] = lfact[1] = 0); anything else (y >= 64, non-integer y) is detected by comparing back and redone exactly.
+            bool exact = true;
+            float lg8 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float y = yreg[s][q];
+              const int yi = (int)min((unsigned)__float2int_rz(y), 63u);       // negative or huge -> 63, which fails the comparison
+              exact = exact && ((float)yi == y);
+              lg8 += lfact[yi];
+            }
+            if (!exact) {
+              lg8 = 0.f;
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float y = yreg[s][q];
+                const int yi = (int)min((unsigned)__float2int_rz(y), 63u);
+                lg8 += ((float)yi == y) ? lfact[yi] : lfact_slow(y);
+              }
+            }
+            llg += lg8;
+          }
+          if (gnext >= 0) load_y(s, gnext);         // the sub-tile's y registers are free: fetch the next block's values into them
+          // t' as the A fragment [16 spots x 16 genes]: a0 = tile 0 rows r, a1 = tile 0 rows r + 8, a2 / a3 = tile 1
+          uint32_t th[4], tl[4];
+          split_bf16x2(t[0], t[1], th[0], tl[0]);
+          split_bf16x2(t[2], t[3], th[1], tl[1]);
+          split_bf16x2(t[4], t[5], th[2], tl[2]);
+          split_bf16x2(t[6], t[7], th[3], tl[3]);
+          {
+            uint32_t b2h[4], b2l[4];
+            ldmatrix_x4_t(b2h, &sWh[0][0] + o2);
+            ldmatrix_x4_t(b2l, &sWl[0][0] + o2);
+#pragma unroll
+            for (int lt = 0; lt < 2; ++lt) {
+              mma_bf16(d2[s][lt], tl, b2h[2 * lt], b2h[2 * lt + 1]);
+              mma_bf16(d2[s][lt], th, b2l[2 * lt], b2l[2 * lt + 1]);
+              mma_bf16(d2[s][lt], th, b2h[2 * lt], b2h[2 * lt + 1]);
+            }
+          }
+          // t'^T as B fragments [16 spots x 8 genes] of the two gene tiles
+#pragma unroll
+          for (int tt = 0; tt < 2; ++tt) {
+            const uint32_t bh0 = movmatrix_t(th[2 * tt]), bh1 = movmatrix_t(th[2 * tt + 1]);
+            const uint32_t bl0 = movmatrix_t(tl[2 * tt]), bl1 = movmatrix_t(tl[2 * tt + 1]);
+            mma_bf16(d3[tt], a3l[s], bh0, bh1);
+            mma_bf16(d3[tt], a3h[s], bl0, bl1);
+            mma_bf16(d3[tt], a3h[s], bh0, bh1);
+          }
+        }
+        // D3[l = r (+8)][gene = 16 jb + 8 tt + 2c (+1)] of this warp's 32 spots
+#pragma unroll
+        for (int tt = 0; tt < 2; ++tt) {
+          *reinterpret_cast<float2*>(&sAcc[warp][r][16 * jb + 8 * tt + 2 * c]) = make_float2(d3[tt][0], d3[tt][1]);
+          *reinterpret_cast<float2*>(&sAcc[warp][r + 8][16 * jb + 8 * tt + 2 * c]) = make_float2(d3[tt][2], d3[tt][3]);
+        }
+      }
+      ll += (double)((llc * LN2 - llg) * invE);
+      __syncthreads();
+      const int nvalid = min(P4_GCH, g_end - g0) * a.F;
+      for (int i = tid; i < nvalid; i += P4_THREADS) {
+        const int gi = i / a.F, f = i - gi * a.F;
+        float v = 0.f;
+#pragma unroll
+        for (int w8 = 0; w8 < P4_WARPS; ++w8) v += sAcc[w8][f][gi];
+        float* dst = a.gW_part + ((int64_t)blockIdx.x * a.G + g0 + gi) * a.F + f;
+        *dst = e == 0 ? v : *dst + v;
+      }
+    }
+    // D2[n][l] of the sample leaves the registers: (n = r + 8 (i >> 1), l = 8 lt + 2c + (i & 1)) pairs as float2
+#pragma unroll
+    for (int s = 0; s < P4_SUB; ++s)
+#pragma unroll
+      for (int lt = 0; lt < 2; ++lt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int n = nw + 16 * s + r + 8 * h;
+          if (n < a.B) {
+            float2* dst = reinterpret_cast<float2*>(w.d2 + ((int64_t)e * a.B + n) * 16 + 8 * lt + 2 * c);
+            const float2 v = make_float2(d2[s][lt][2 * h], d2[s][lt][2 * h + 1]);
+            if (a.atomic_out) atomicAdd(dst, v); else *dst = v;
+          }
+        }
+  }
+  const double tot = block_sum<double>(ll, red);
+  if (tid == 0) a.ll_part[blockIdx.y * gridDim.x + blockIdx.x] = tot;
+}
+
+// blocks [0, gw_blocks): gW[g, f] = (softplus'(W[g, f]) or 1) * sum_b gW_part[b, g, f]; blocks [gw_blocks, ...): 64 spots each, all samples:
+// gF = EF' D2 -> d/dmean, d/dspread, d/dV and sum_g r.  The last block to finish sums the log-likelihood partials (fixed order).
+__global__ void __launch_bounds__(256) poisson_post4_kernel(const PoissonArgs<float> a, const Poisson4Ws w, float* __restrict__ gW, int nbx,
+                                                            int nby, int gw_blocks, int spot_blocks, double* __restrict__ ll_out) {
+  __shared__ double red[32];
+  __shared__ float wsum[16];
+  __shared__ bool last;
+  const int tid = threadIdx.x;
+  if ((int)blockIdx.x < gw_blocks) {
+    // 64 outputs per block; thread (o, p) adds the partials of the CTAs b = p, p + 4, ... (independent loads, 256-byte rows)
+    __shared__ float part[4][64];
+    const int64_t GF = (int64_t)a.G * a.F, i = (int64_t)blockIdx.x * 64 + (tid & 63);
+    const int p = tid >> 6;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (i < GF) {
+      int b = p;
+      for (; b + 12 < nbx; b += 16) {
+        s0 += a.gW_part[(int64_t)b * GF + i];
+        s1 += a.gW_part[(int64_t)(b + 4) * GF + i];
+        s2 += a.gW_part[(int64_t)(b + 8) * GF + i];
+        s3 += a.gW_part[(int64_t)(b + 12) * GF + i];
+      }
+      for (; b < nbx; b += 4) s0 += a.gW_part[(int64_t)b * GF + i];
+    }
+    part[p][tid & 63] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (tid < 64 && i < GF) {
+      const float s = (part[0][tid] + part[1][tid]) + (part[2][tid] + part[3][tid]);
+      gW[i] = a.w_softplus ? s * softplus_grad(a.W[i]) : s;
+    }
+  } else {
+    if (tid < 16) {
+      float v = 0.f;
+      for (int by = 0; by < nby; ++by) v += w.wsum[by * 16 + tid];
+      wsum[tid] = v;
+    }
+    __syncthreads();
+    const int sb = blockIdx.x - gw_blocks, n = sb * 64 + (tid >> 2), lq = (tid & 3) * 4;
+    float rs = 0.f, gsum = 0.f, vraw = 0.f, spV = 1.f;
+    if (n < a.B) {
+      vraw = a.V[a.idx ? a.idx[n] : (int64_t)n];
+      spV = softplus(vraw);
+      float gm[4] = {0.f, 0.f, 0.f, 0.f}, gs[4] = {0.f, 0.f, 0.f, 0.f}, sdv[4];
+      for (int e = 0; e < a.E; ++e) {
+        float ev[4], epsv[4];
+        poisson_ef4(a, e, n, lq, spV, ev, epsv, sdv);
+        const float4 d = *reinterpret_cast<const float4*>(w.d2 + ((int64_t)e * a.B + n) * 16 + lq);
+        const float dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float gF = ev[j] * dv[j];
+          gm[j] += gF;
+          gs[j] = fmaf(gF, epsv[j], gs[j]);
+          gsum += gF;
+          rs = fmaf(ev[j], wsum[lq + j], rs);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int f = lq + j;
+        if (f < a.F) {
+          const int64_t o = (int64_t)f * a.B + n;
+          float gsp = gs[j];
+          if (f < a.n_var) gsp = a.spread[o] >= a.clamp_min ? gsp / (2.f * sdv[j]) : 0.f;   // d sd / d var = 1 / (2 sd) where not clamped
+          a.gmean[o] = gm[j];
+          a.gspread[o] = gsp;
+        }
+      }
+    }
+    // d ll / d V[n] = softplus'(V) / softplus(V) * sum_e sum_l gF_e[l, n]   (sum_g (y - r) = E sum_l EF'_l D2_l; 1/E is inside t')
+    gsum += __shfl_xor_sync(0xffffffffu, gsum, 1);
+    gsum += __shfl_xor_sync(0xffffffffu, gsum, 2);
+    if (n < a.B && (tid & 3) == 0) a.gV[n] = softplus_grad(vraw) * gsum / spV;
+    const double tot = block_sum<double>((double)rs, red);
+    if (tid == 0) w.rs_part[sb] = tot;
+  }
+  // last block done: ll = sum(main partials) - sum(rate sums) / E
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) last = atomicAdd(w.ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  double s = 0.0;
+  for (int i = tid; i < nbx * nby; i += 256) s += __ldcg(a.ll_part + i);
+  double rsum = 0.0;
+  for (int i = tid; i < spot_blocks; i += 256) rsum += __ldcg(w.rs_part + i);
+  s -= rsum / (double)a.E;
+  s = block_sum<double>(s, red);
+  if (tid == 0) ll_out[0] = s;
+}
+
 // gW[g,f] = (softplus'(W[g,f]) or 1) * sum_b gW_part[b,g,f]
 template <typename T>
 __global__ void poisson_gw_reduce_kernel(const T* __restrict__ part, const T* __restrict__ W, T* __restrict__ gW, int64_t GF, int nb,
@@ -705,11 +1193,12 @@ template <typename T, int FMAX> constexpr size_t poisson_smem() {
 template <typename T, int FMAX> constexpr size_t poisson_smem2() {
   return ((sizeof(T) * PZ_GCH * (P2_SPOTS + 1) + 15) / 16) * 16 + sizeof(T) * (FMAX * P2_SPOTS + PZ_GCH * FMAX + 4 * PZ_GCH * FMAX);
 }
-static int poisson_version() {          // GPZ_POISSON_V: 1 = thread-per-spot kernel, 2 = two spots per thread, 3 = 2 on packed fp32x2 FMAs (fp32 only; measured equal to 2: the kernel is bound by bookkeeping instructions, not by the FMAs)
+static int poisson_version() {          // GPZ_POISSON_V: 1 = thread-per-spot kernel, 2 = two spots per thread, 3 = 2 on packed fp32x2 FMAs (fp32 only; measured equal to 2: both are bound by bookkeeping instructions), 4 (default) = tensor-core contractions (fp32, F <= 16; anything else runs 2)
   static int v = -1;
-  if (v < 0) { const char* e = getenv("GPZ_POISSON_V"); v = e ? atoi(e) : 2; }
+  if (v < 0) { const char* e = getenv("GPZ_POISSON_V"); v = e ? atoi(e) : 4; }
   return v;
 }
+static bool poisson_use_v4(int F, bool is_f32) { return is_f32 && F <= 16 && poisson_version() >= 4; }
 static bool poisson_v2_forced() { return poisson_version() == 2; }
 template <typename T, int FMAX> int poisson_launch(const PoissonArgs<T>& a, dim3 grid, cudaStream_t st) {
   if (poisson_version() >= 2) {
@@ -725,7 +1214,17 @@ template <typename T, int FMAX> int poisson_launch(const PoissonArgs<T>& a, dim3
   return GPZ_OK;
 }
 
-static void poisson_grid(int G, int B, int* nbx, int* nby, int* gpc) {
+static void poisson_grid(int G, int F, int B, bool is_f32, int* nbx, int* nby, int* gpc) {
+  if (poisson_use_v4(F, is_f32)) {        // 256 spots per CTA, gene ranges in whole 16-gene blocks, about four waves of 2 CTAs per SM
+    *nbx = (int)cdiv(B, P4_SPOTS);
+    const int blocks = (int)cdiv(G, 16);
+    int by = 1;
+    if (*nbx < 1184) by = (int)min((int64_t)blocks, (int64_t)max(1, 1184 / (*nbx > 0 ? *nbx : 1)));
+    const int bpc = (int)cdiv(blocks, by);
+    *gpc = bpc * 16;
+    *nby = (int)cdiv(G, *gpc);
+    return;
+  }
   *nbx = (int)cdiv(B, poisson_version() >= 2 ? P2_SPOTS : PZ_SPOTS);
   const int chunks = (int)cdiv(G, PZ_GCH);
   int by = 1;
@@ -733,6 +1232,18 @@ static void poisson_grid(int G, int B, int* nbx, int* nby, int* gpc) {
   const int cpc = (int)cdiv(chunks, by);
   *gpc = cpc * PZ_GCH;
   *nby = (int)cdiv(G, *gpc);
+}
+
+// workspace: ll partials (double) | gW partials [nbx][G][F] | (v4) the Poisson4Ws arrays
+static size_t poisson_ll_slots(int nbx, int nby) { return ((size_t)nbx * nby + 2 + 1) & ~(size_t)1; }   // keeps what follows 16-byte aligned
+static size_t poisson_ws_bytes(int G, int F, int B, int E, bool is_f32, size_t elt, int nbx, int nby) {
+  size_t b = sizeof(double) * poisson_ll_slots(nbx, nby) + (elt * (size_t)nbx * G * F + 15) / 16 * 16;
+  if (poisson_use_v4(F, is_f32)) {
+    const size_t EB16 = 16 * (size_t)(E > 0 ? E : 1) * B;
+    b += 2 * sizeof(uint16_t) * 16 * (size_t)G + 2 * sizeof(uint16_t) * EB16 + sizeof(float) * EB16 + sizeof(float) * 16 * (size_t)nby +
+         sizeof(double) * (size_t)cdiv(B, 64) + 16;
+  }
+  return b;
 }
 
 template <typename T>
@@ -744,14 +1255,14 @@ int poisson_fwdbwd(PoissonArgs<T> a, T* gW, double* ll_out, void* ws, size_t ws_
     return GPZ_OK;
   }
   int nbx, nby, gpc;
-  poisson_grid(a.G, a.B, &nbx, &nby, &gpc);
-  const size_t need = sizeof(double) * ((size_t)nbx * nby + 2) + sizeof(T) * (size_t)nbx * a.G * a.F;
+  poisson_grid(a.G, a.F, a.B, std::is_same<T, float>::value, &nbx, &nby, &gpc);
+  const size_t need = poisson_ws_bytes(a.G, a.F, a.B, a.E, std::is_same<T, float>::value, sizeof(T), nbx, nby);
   if (ws_bytes < need) return GPZ_ERR_BADARG;
   a.ll_part = reinterpret_cast<double*>(ws);
-  a.gW_part = reinterpret_cast<T*>(a.ll_part + (size_t)nbx * nby + 2);
+  a.gW_part = reinterpret_cast<T*>(a.ll_part + poisson_ll_slots(nbx, nby));
   a.genes_per_cta = gpc;
   a.atomic_out = nby > 1;
-  if (a.atomic_out) {
+  if (a.atomic_out && !poisson_use_v4(a.F, std::is_same<T, float>::value)) {
     GPZ_CUDA(cudaMemsetAsync(a.gV, 0, sizeof(T) * a.B, st));
     GPZ_CUDA(cudaMemsetAsync(a.gmean, 0, sizeof(T) * a.B * a.F, st));
     GPZ_CUDA(cudaMemsetAsync(a.gspread, 0, sizeof(T) * a.B * a.F, st));
@@ -759,7 +1270,29 @@ int poisson_fwdbwd(PoissonArgs<T> a, T* gW, double* ll_out, void* ws, size_t ws_
   dim3 grid(nbx, nby);
   int rc;
   if constexpr (std::is_same<T, float>::value) {
-    if (poisson_version() >= 3) {          // fp32: the packed-FMA kernel
+    if (poisson_use_v4(a.F, true)) {       // fp32, F <= 16: contractions on the tensor cores
+      unsigned char* p4 = reinterpret_cast<unsigned char*>(a.gW_part) + (sizeof(T) * (size_t)nbx * a.G * a.F + 15) / 16 * 16;
+      const size_t EB16 = 16 * (size_t)a.E * a.B;
+      const int spot_blocks = (int)cdiv(a.B, 64), gw_blocks = (int)cdiv((int64_t)a.G * a.F, 64);
+      Poisson4Ws w;
+      w.d2 = reinterpret_cast<float*>(p4); p4 += sizeof(float) * EB16;
+      w.wsum = reinterpret_cast<float*>(p4); p4 += sizeof(float) * 16 * (size_t)nby;
+      w.rs_part = reinterpret_cast<double*>(p4); p4 += sizeof(double) * (size_t)spot_blocks;       // 8-byte aligned: every block above is a multiple of 64 B
+      w.efh = reinterpret_cast<uint16_t*>(p4); p4 += sizeof(uint16_t) * EB16;
+      w.efl = reinterpret_cast<uint16_t*>(p4); p4 += sizeof(uint16_t) * EB16;
+      w.wh = reinterpret_cast<uint16_t*>(p4); p4 += sizeof(uint16_t) * 16 * (size_t)a.G;
+      w.wl = reinterpret_cast<uint16_t*>(p4); p4 += sizeof(uint16_t) * 16 * (size_t)a.G;
+      w.ticket = reinterpret_cast<unsigned int*>(p4);
+      poisson_prep4_kernel<<<nby + a.E * spot_blocks, 256, 0, st>>>(a, w, nby, spot_blocks);
+      GPZ_CHECK_LAUNCH();
+      if (a.idx) poisson_kernel4<true><<<grid, P4_THREADS, 0, st>>>(a, w);
+      else poisson_kernel4<false><<<grid, P4_THREADS, 0, st>>>(a, w);
+      GPZ_CHECK_LAUNCH();
+      poisson_post4_kernel<<<gw_blocks + spot_blocks, 256, 0, st>>>(a, w, gW, nbx, nby, gw_blocks, spot_blocks, ll_out);
+      GPZ_CHECK_LAUNCH();
+      return GPZ_OK;
+    }
+    if (poisson_version() == 3) {          // fp32: the packed-FMA kernel
       if (a.F <= 4) rc = poisson_launch3<2>(a, grid, st);
       else if (a.F <= 10) rc = poisson_launch3<5>(a, grid, st);
       else if (a.F <= 12) rc = poisson_launch3<6>(a, grid, st);
@@ -813,10 +1346,10 @@ __global__ void poisson_rate_kernel(const T* __restrict__ W, int w_softplus, con
 using namespace gpz;
 
 #define GPZ_POISSON_IMPL(SUF, T)                                                                                       \
-  extern "C" int64_t gpz_poisson_workspace_bytes_##SUF(int G, int F, int B) {                                          \
+  extern "C" int64_t gpz_poisson_workspace_bytes_##SUF(int G, int F, int B, int E) {                                   \
     int nbx, nby, gpc;                                                                                                 \
-    poisson_grid(G, B, &nbx, &nby, &gpc);                                                                              \
-    return (int64_t)(sizeof(double) * ((size_t)nbx * nby + 2) + sizeof(T) * (size_t)nbx * G * F);                      \
+    poisson_grid(G, F, B, sizeof(T) == 4, &nbx, &nby, &gpc);                                                           \
+    return (int64_t)poisson_ws_bytes(G, F, B, E, sizeof(T) == 4, sizeof(T), nbx, nby);                                 \
   }                                                                                                                    \
   extern "C" int gpz_poisson_fwdbwd_##SUF(const T* y, int64_t y_ld, const int64_t* idx, const T* W, int w_softplus,    \
                                           const T* V, const T* mean, const T* spread, const T* eps, int G, int F,      \

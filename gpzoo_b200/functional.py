@@ -1087,7 +1087,7 @@ class PoissonLL(Function):
             assert y.shape[1] == B
         lib = _cabi.lib()
         suf = "f32" if dt == torch.float32 else "f64"
-        ws_bytes = int(getattr(lib, f"gpz_poisson_workspace_bytes_{suf}")(c_i(G), c_i(F), c_i(B)))
+        ws_bytes = int(getattr(lib, f"gpz_poisson_workspace_bytes_{suf}")(c_i(G), c_i(F), c_i(B), c_i(E)))
         ws = torch.empty(ws_bytes // 8 + 1, dtype=torch.float64, device=W.device)
         ll = torch.empty(1, dtype=torch.float64, device=W.device)
         gW = torch.empty_like(W)

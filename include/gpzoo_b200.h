@@ -180,8 +180,8 @@ int gpz_vnngp_bwd_f64(const double* X, const double* Z, const double* sigma, con
  *      utilities.py:479,507,611-614 (ELBO reduction); torch poisson.py log_prob.
  *      spread[f,:] is a variance (clamped at clamp_min, gp.py:228/378/118) for f < n_var and a std-dev otherwise.
  *      ll: one double on the device.  ws sized by gpz_poisson_workspace_bytes_*. */
-int64_t gpz_poisson_workspace_bytes_f32(int G, int F, int B);
-int64_t gpz_poisson_workspace_bytes_f64(int G, int F, int B);
+int64_t gpz_poisson_workspace_bytes_f32(int G, int F, int B, int E);
+int64_t gpz_poisson_workspace_bytes_f64(int G, int F, int B, int E);
 int gpz_poisson_fwdbwd_f32(const float* y, int64_t y_ld, const int64_t* idx, const float* W, int w_softplus, const float* V,
                            const float* mean, const float* spread, const float* eps, int G, int F, int B, int E, int n_var,
                            float clamp_min, int with_lgamma, double* ll, float* gW, float* gV, float* gmean, float* gspread,
