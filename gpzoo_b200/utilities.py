@@ -1,8 +1,8 @@
 """Hot-path helpers and training loops with GPzoo's `gpzoo.utilities` names.
 
-Only the functions on or next to the ELBO path are provided: the data
-preparation / plotting helpers of the reference (utilities.py:14-23, 38-375, 421-448) are CPU
-pre-processing and out of scope.  The training loops call the fused `model.elbo(...)`.
+The functions on or next to the ELBO path plus the initialisation pipeline
+(`gpzoo_b200.initialisation`); the anndata / squidpy / plotting helpers of the
+reference (utilities.py:50-69, 86-156, 421-448) are host-side data handling and out of scope.  The training loops call the fused `model.elbo(...)`.
 """
 from __future__ import annotations
 
@@ -10,6 +10,9 @@ import torch
 
 from . import functional as F
 from .kernels import embed_distance_matrix as _embed_distance_matrix  # noqa: F401  (utilities.py:459-469)
+# the initialisation pipeline of the notebooks (utilities.py:14-24, 38-44, 71-84, 237-313), on the device
+from .initialisation import (build_group_distances, init_softplus, lnormal_approx_dirichlet, regularized_nmf,  # noqa: F401
+                             rescale_spatial_coords, shrink_factors, shrink_loadings)
 
 
 def whitened_KL(mz, Lz):

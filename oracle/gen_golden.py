@@ -124,8 +124,68 @@ def gen_round2():
     print("state_dict_shapes.json written")
 
 
+def gen_init():
+    """Initialisation pipeline: outputs of the reference's own utilities.py functions (which call
+    sklearn.decomposition.NMF) on a small seeded count matrix, plus the notebook formula for the variational mean."""
+    ref = load_reference()
+    U = ref.utilities
+    rng = np.random.RandomState(3)
+    N, G, L = 90, 40, 4
+    Ftrue = np.abs(rng.standard_normal((N, L))) * np.array([2.0, 1.0, 0.5, 0.25])
+    Wtrue = np.abs(rng.standard_normal((G, L)))
+    Y = rng.poisson(Ftrue @ Wtrue.T + 0.05).astype(np.float64)
+    sz = Y.sum(1, keepdims=True) / Y.sum(1).mean()
+    blob = dict(Y=Y, sz=sz)
+    # the two ways the notebooks call it (NSF_Hybrid_benchmark.ipynb cell 7) and the defaults (sklearn's coordinate descent)
+    calls = {
+        "mu_kl": dict(shrinkage=0.2, max_iter=200, solver="mu", init="nndsvdar", beta_loss="kullback-leibler", random_state=0),
+        "mu_fro": dict(shrinkage=0.3, max_iter=150, solver="mu", init="random", beta_loss="frobenius", random_state=5),
+        "cd": dict(shrinkage=0.2, max_iter=200, init="random", random_state=1),
+    }
+    from sklearn.decomposition import NMF
+    for name, kw in calls.items():
+        Fl, Wl = U.regularized_nmf(Y.copy(), L, sz=sz, **kw)
+        blob[f"{name}_F"], blob[f"{name}_W"] = Fl, Wl
+        nkw = {k: v for k, v in kw.items() if k != "shrinkage"}
+        m = NMF(L, **nkw)
+        blob[f"{name}_eF"] = m.fit_transform(Y.copy())
+        blob[f"{name}_H"] = m.components_
+        blob[f"{name}_n_iter"] = m.n_iter_
+    # post-processing alone (factors / loadings given)
+    Fp, Wp = U.regularized_nmf(Y.copy(), L, sz=1, pseudocount=1e-2, factors=blob["cd_eF"].copy(), loadings=blob["cd_H"].T.copy(),
+                               shrinkage=0.25)
+    blob["post_F"], blob["post_W"] = Fp, Wp
+    blob["lnormal"] = np.array([U.lnormal_approx_dirichlet(l) for l in (1.1, 4, 10)])
+    mat = rng.standard_normal((6, 5)) * 8 + 5
+    mat[0, 0] = 25.0
+    mat = np.abs(mat) + 0.1
+    blob["softplus_in"], blob["softplus_out"] = mat, U.init_softplus(mat)
+    X = rng.uniform(0, 1, (50, 2)) * np.array([300.0, 120.0]) + np.array([1000.0, -40.0])
+    blob["coords_in"], blob["coords_out"] = X.copy(), U.rescale_spatial_coords(X.copy())
+    groups = torch.from_numpy(rng.randint(0, 4, 50))
+    blob["groups"] = groups.numpy()
+    blob["group_distances"] = U.build_group_distances(torch.from_numpy(blob["coords_out"]).float(), groups).numpy()
+    # projection of log-scale factors onto the inducing points (Slideseqv2_estimate_lengthscales.ipynb cell 16), fp64
+    Xs = torch.from_numpy(blob["coords_out"])
+    Z = Xs[:12].clone()
+    kern = ref.kernels.NSF_RBF(L=3, sigma=1.0, lengthscale=1.0)
+    kern.double()
+    fac = torch.from_numpy(rng.standard_normal((3, 50)))
+    with torch.no_grad():
+        Kzx = kern.forward(Z, Xs)
+        Kzz = kern.forward(Z, Z)
+        L1 = torch.linalg.cholesky(U.add_jitter(Kzx @ Kzx.transpose(-2, -1), 1e-5))
+        mu = Kzz @ torch.cholesky_solve(Kzx @ fac[:, :, None], L1)
+    blob["proj_Z"], blob["proj_factors"], blob["proj_mu"] = Z.numpy(), fac.numpy(), mu[:, :, 0].numpy()
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, "init_pipeline.npz"), **blob)
+    print("init_pipeline.npz written", {k: int(blob[f"{k}_n_iter"]) for k in calls})
+
+
 def main():
     torch.manual_seed(0)
+    if "--init" in sys.argv:
+        return gen_init()
     if "--round2" in sys.argv:
         return gen_round2()
     ref = load_reference()

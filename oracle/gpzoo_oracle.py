@@ -352,3 +352,41 @@ def value_and_grads(fn: Callable[[], dict], leaves: dict):
     for t in leaves.values():
         t.grad = None
     return {k: (v.detach() if torch.is_tensor(v) else v) for k, v in out.items()}, grads
+
+
+# ------------------------------------------------------------------------------------------------
+# initialisation pipeline: the deterministic part of utilities.py:237-313, restated on numpy-like arrays
+# ------------------------------------------------------------------------------------------------
+def lnormal_approx_dirichlet(L):
+    """utilities.py:237-250."""
+    import math
+    s2 = math.log(2 * L) - math.log(L + 1)
+    return -math.log(L) - s2 / 2.0, math.sqrt(s2)
+
+
+def regularized_nmf_post(eF, W, L, sz=1.0, pseudocount=1e-2, shrinkage=0.2):
+    """What regularized_nmf does to the NMF's (factors N x L, loadings G x L): utilities.py:284-299 with the shrinkage of
+    :301-313.  torch tensors (fp64) in and out."""
+    a = shrinkage
+    if 0 < a < 1:
+        W = W * (1 - a) + a * W.sum(0) / float(W.shape[0])
+    wsum = W.sum(0)
+    eF = eF * wsum
+    if 0 < a < 1:
+        eF = eF * (1 - a) + a * eF.sum(1, keepdim=True) / float(eF.shape[1])
+    Fl = torch.log(pseudocount + eF) - torch.log(torch.as_tensor(sz, dtype=eF.dtype))
+    mu, _ = lnormal_approx_dirichlet(max(L, 1.1))
+    wt = Fl.mean(0) - mu
+    return Fl - wt, W * torch.exp(wt - torch.log(wsum))
+
+
+def init_softplus(mat, minval=1e-5):
+    """utilities.py:38-44."""
+    return torch.where(mat < 20, torch.log(torch.exp(mat.clamp(max=20.0)) - 1 + minval), mat)
+
+
+def rescale_spatial_coords(X, box_side=4):
+    """utilities.py:71-84."""
+    X = X - X.min(0).values
+    X = X * (box_side / torch.exp(torch.log(X.max(0).values).mean()))
+    return X - X.mean(0)

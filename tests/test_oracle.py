@@ -111,3 +111,18 @@ def test_oracle_matches_live_reference_fp32_and_fp64():
             assert relerr(out[k], rout[k]) < tol, (k, dtype)
         for k, v in rgrad.items():
             assert relerr(grads[k], v) < 10 * tol, (k, dtype)
+
+
+def test_init_pipeline_golden():
+    """The deterministic part of the initialisation pipeline (utilities.py:237-313, 38-44, 71-84) against the reference's outputs."""
+    z = np.load(GOLDEN + "/init_pipeline.npz")
+    t = lambda k: torch.from_numpy(z[k])
+    for name, shrink in (("mu_kl", 0.2), ("mu_fro", 0.3), ("cd", 0.2)):
+        Fl, W = O.regularized_nmf_post(t(name + "_eF"), t(name + "_H").t(), 4, sz=t("sz"), shrinkage=shrink)
+        assert relerr(Fl, t(name + "_F")) < TOL and relerr(W, t(name + "_W")) < TOL, name
+    Fl, W = O.regularized_nmf_post(t("cd_eF"), t("cd_H").t(), 4, shrinkage=0.25)
+    assert relerr(Fl, t("post_F")) < TOL and relerr(W, t("post_W")) < TOL
+    assert relerr(O.init_softplus(t("softplus_in")), t("softplus_out")) < TOL
+    assert relerr(O.rescale_spatial_coords(t("coords_in")), t("coords_out")) < TOL
+    for l, ref in zip((1.1, 4, 10), z["lnormal"]):
+        assert np.allclose(O.lnormal_approx_dirichlet(l), ref, rtol=1e-14, atol=1e-14)
