@@ -837,20 +837,22 @@ __global__ void __launch_bounds__(P4_THREADS, 2) poisson_kernel4(const PoissonAr
   if (a.with_lgamma && tid < 64) lfact[tid] = lgammaf((float)(tid + 1));
   const int nw = blockIdx.x * P4_SPOTS + warp * (16 * P4_SUB);          // first spot of the warp
   const bool block_full = (blockIdx.x + 1) * P4_SPOTS <= a.B;
-  const bool fast_cols = !HAS_IDX && block_full;                        // the thread's four columns are nw + r + {0, 8, 16, 24}
+  // fragment row r (+8) of sub-tile s <-> spot nw + 16 s + 2 r (+1): a thread's two spots of a sub-tile are neighbours, so one 8-byte load
+  // per gene row fetches both (the row <-> spot assignment inside a 16-spot tile is free as long as EF' and D2 use the same one)
+  const bool fast_cols = !HAS_IDX && block_full && (a.y_ld & 1) == 0 && (reinterpret_cast<uintptr_t>(a.y) & 7) == 0;
   const float invE = 1.f / (float)a.E;
   const int g_begin = blockIdx.y * a.genes_per_cta;
   const int g_end = min(a.G, g_begin + a.genes_per_cta);
   constexpr float LN2 = 0.69314718055994530942f;
 
-  // the thread's spots: sub-tile s, half h -> n = nw + 16 s + r + 8 h ; invalid spots read a valid column of y and have EF' = 0
+  // the thread's spots: sub-tile s, half h -> n = nw + 16 s + 2 r + h ; invalid spots read a valid column of y and have EF' = 0
   int col[P4_SUB][2];                                         // columns of y: 32-bit (Ntot < 2^31)
   if (!fast_cols) {
 #pragma unroll
     for (int s = 0; s < P4_SUB; ++s)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const int nc = min(nw + 16 * s + r + 8 * h, a.B - 1);
+        const int nc = min(nw + 16 * s + 2 * r + h, a.B - 1);
         col[s][h] = HAS_IDX ? (int)a.idx[nc] : nc;
       }
   }
@@ -865,12 +867,14 @@ __global__ void __launch_bounds__(P4_THREADS, 2) poisson_kernel4(const PoissonAr
   auto load_y = [&](int s, int gblk) {
     if (fast_cols && gblk + 16 <= g_end) {
       // interior block: the four rows 2c, 2c + 1, 2c + 8, 2c + 9 from one base pointer (one 32 x 32 -> 64-bit multiply-add, three adds)
-      const float* p0 = ybase + (int64_t)(gblk + 2 * c) * ld + (nw + r + 16 * s);
+      const float* p0 = ybase + (int64_t)(gblk + 2 * c) * ld + (nw + 16 * s + 2 * r);
       const float* p1 = p0 + ld;
       const float* p2 = p0 + ld8;
       const float* p3 = p2 + ld;
-      yreg[s][0] = __ldcs(p0); yreg[s][1] = __ldcs(p1); yreg[s][2] = __ldcs(p0 + 8); yreg[s][3] = __ldcs(p1 + 8);
-      yreg[s][4] = __ldcs(p2); yreg[s][5] = __ldcs(p3); yreg[s][6] = __ldcs(p2 + 8); yreg[s][7] = __ldcs(p3 + 8);
+      const float2 v0 = __ldcs(reinterpret_cast<const float2*>(p0)), v1 = __ldcs(reinterpret_cast<const float2*>(p1));
+      const float2 v2 = __ldcs(reinterpret_cast<const float2*>(p2)), v3 = __ldcs(reinterpret_cast<const float2*>(p3));
+      yreg[s][0] = v0.x; yreg[s][1] = v1.x; yreg[s][2] = v0.y; yreg[s][3] = v1.y;
+      yreg[s][4] = v2.x; yreg[s][5] = v3.x; yreg[s][6] = v2.y; yreg[s][7] = v3.y;
       return;
     }
     // ragged block / gathered columns: four clamped row pointers
@@ -880,9 +884,9 @@ __global__ void __launch_bounds__(P4_THREADS, 2) poisson_kernel4(const PoissonAr
       const int g = min(gblk + 8 * (j >> 1) + 2 * c + (j & 1), g_end - 1);
       rowp[j] = ybase + (int64_t)g * ld;
     }
-    if (fast_cols) {
+    if (!HAS_IDX && block_full) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) yreg[s][q] = __ldcs(rowp[2 * (q >> 2) + (q & 1)] + (nw + r + 16 * s) + 8 * ((q >> 1) & 1));
+      for (int q = 0; q < 8; ++q) yreg[s][q] = __ldcs(rowp[2 * (q >> 2) + (q & 1)] + (nw + 16 * s + 2 * r) + ((q >> 1) & 1));
     } else {
 #pragma unroll
       for (int q = 0; q < 8; ++q) yreg[s][q] = __ldcs(rowp[2 * (q >> 2) + (q & 1)] + col[s][(q >> 1) & 1]);
@@ -901,7 +905,7 @@ __global__ void __launch_bounds__(P4_THREADS, 2) poisson_kernel4(const PoissonAr
     for (int s = 0; s < P4_SUB; ++s) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int n = nw + 16 * s + r + 8 * (k & 1);
+        const int n = nw + 16 * s + 2 * r + (k & 1);
         a1h[s][k] = 0u; a1l[s][k] = 0u;
         if (n < a.B) {
           const int64_t o = (((int64_t)e * a.B + n) * 16 + 2 * c + 8 * (k >> 1)) >> 1;
@@ -974,7 +978,7 @@ __global__ void __launch_bounds__(P4_THREADS, 2) poisson_kernel4(const PoissonAr
           if (ragged) {                             // genes past the range / spots past the minibatch carry no count
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-              if (gblk + 8 * (q >> 2) + 2 * c + (q & 1) >= g_end || nw + 16 * s + r + 8 * ((q >> 1) & 1) >= a.B) yreg[s][q] = 0.f;
+              if (gblk + 8 * (q >> 2) + 2 * c + (q & 1) >= g_end || nw + 16 * s + 2 * r + ((q >> 1) & 1) >= a.B) yreg[s][q] = 0.f;
           }
           // element-wise on the rate fragment
           float t[8];
@@ -1064,7 +1068,7 @@ __global__ void __launch_bounds__(P4_THREADS, 2) poisson_kernel4(const PoissonAr
       for (int lt = 0; lt < 2; ++lt)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const int n = nw + 16 * s + r + 8 * h;
+          const int n = nw + 16 * s + 2 * r + h;
           if (n < a.B) {
             float2* dst = reinterpret_cast<float2*>(w.d2 + ((int64_t)e * a.B + n) * 16 + 8 * lt + 2 * c);
             const float2 v = make_float2(d2[s][lt][2 * h], d2[s][lt][2 * h + 1]);
