@@ -822,9 +822,33 @@ __global__ void __launch_bounds__(256) poisson_prep4_kernel(const PoissonArgs<fl
   *reinterpret_cast<float4*>(w.d2 + o) = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+// Counts as stored by the caller: fp32 (the reference's format), or uint8 / int16 / int32 (lossless for counts, 4x / 2x less HBM
+// traffic and upload).  y_load2 fetches the two neighbouring spots of a fragment row pair with one load.
+// Small unsigned integers become floats on the ALU / FMA pipes (2^23 + k has k in its low mantissa bits), not through I2F, which
+// shares the quarter-rate XU pipe with the kernel's log2 / reciprocal.
+__device__ __forceinline__ float u16_to_float(unsigned k) { return __uint_as_float(0x4B000000u | k) - 8388608.f; }
+template <typename YT> __device__ __forceinline__ float y_load1(const YT* p) { return (float)__ldcs(p); }
+template <> __device__ __forceinline__ float y_load1<uint8_t>(const uint8_t* p) { return u16_to_float(__ldcs(p)); }
+template <> __device__ __forceinline__ float y_load1<int16_t>(const int16_t* p) {
+  return u16_to_float(__ldcs(reinterpret_cast<const unsigned short*>(p)));              // counts: non-negative by contract
+}
+template <typename YT> __device__ __forceinline__ void y_load2(const YT* p, float& a, float& b);
+template <> __device__ __forceinline__ void y_load2<float>(const float* p, float& a, float& b) {
+  const float2 v = __ldcs(reinterpret_cast<const float2*>(p)); a = v.x; b = v.y;
+}
+template <> __device__ __forceinline__ void y_load2<uint8_t>(const uint8_t* p, float& a, float& b) {
+  const unsigned v = __ldcs(reinterpret_cast<const unsigned short*>(p)); a = u16_to_float(v & 0xffu); b = u16_to_float(v >> 8);
+}
+template <> __device__ __forceinline__ void y_load2<int16_t>(const int16_t* p, float& a, float& b) {
+  const unsigned v = __ldcs(reinterpret_cast<const unsigned*>(p)); a = u16_to_float(v & 0xffffu); b = u16_to_float(v >> 16);
+}
+template <> __device__ __forceinline__ void y_load2<int32_t>(const int32_t* p, float& a, float& b) {
+  const int2 v = __ldcs(reinterpret_cast<const int2*>(p)); a = (float)v.x; b = (float)v.y;
+}
+
 __device__ __noinline__ float lfact_slow(float y) { return lgammaf(y + 1.f); }     // counts >= 64 or non-integer y: rare, kept out of line
 
-template <bool HAS_IDX>
+template <bool HAS_IDX, typename YT>
 __global__ void __launch_bounds__(P4_THREADS, 2) poisson_kernel4(const PoissonArgs<float> a, const Poisson4Ws w) {
   __shared__ __align__(16) uint16_t sWh[P4_GCH][P4_WLD];      // softplus(W) chunk, bf16 hi / lo, [gene][factor]
   __shared__ __align__(16) uint16_t sWl[P4_GCH][P4_WLD];
@@ -839,7 +863,7 @@ __global__ void __launch_bounds__(P4_THREADS, 2) poisson_kernel4(const PoissonAr
   const bool block_full = (blockIdx.x + 1) * P4_SPOTS <= a.B;
   // fragment row r (+8) of sub-tile s <-> spot nw + 16 s + 2 r (+1): a thread's two spots of a sub-tile are neighbours, so one 8-byte load
   // per gene row fetches both (the row <-> spot assignment inside a 16-spot tile is free as long as EF' and D2 use the same one)
-  const bool fast_cols = !HAS_IDX && block_full && (a.y_ld & 1) == 0 && (reinterpret_cast<uintptr_t>(a.y) & 7) == 0;
+  const bool fast_cols = !HAS_IDX && block_full && (a.y_ld & 1) == 0 && (reinterpret_cast<uintptr_t>(a.y) & (2 * sizeof(YT) - 1)) == 0;
   const float invE = 1.f / (float)a.E;
   const int g_begin = blockIdx.y * a.genes_per_cta;
   const int g_end = min(a.G, g_begin + a.genes_per_cta);
@@ -861,24 +885,22 @@ __global__ void __launch_bounds__(P4_THREADS, 2) poisson_kernel4(const PoissonAr
   // Rows past the gene range re-read the range's last row (masked when consumed: only the last block of a range is ragged), so the
   // loads carry no predicate and no select and really are in flight for a whole block.
   float yreg[P4_SUB][8];
-  const float* ybase = a.y;
+  const YT* ybase = reinterpret_cast<const YT*>(a.y);      // a.y carries the caller's pointer whatever its element type
   const int ld = (int)a.y_ld;                          // a row of y is shorter than 2^31 entries
   const int ld8 = 8 * ld;
   auto load_y = [&](int s, int gblk) {
     if (fast_cols && gblk + 16 <= g_end) {
       // interior block: the four rows 2c, 2c + 1, 2c + 8, 2c + 9 from one base pointer (one 32 x 32 -> 64-bit multiply-add, three adds)
-      const float* p0 = ybase + (int64_t)(gblk + 2 * c) * ld + (nw + 16 * s + 2 * r);
-      const float* p1 = p0 + ld;
-      const float* p2 = p0 + ld8;
-      const float* p3 = p2 + ld;
-      const float2 v0 = __ldcs(reinterpret_cast<const float2*>(p0)), v1 = __ldcs(reinterpret_cast<const float2*>(p1));
-      const float2 v2 = __ldcs(reinterpret_cast<const float2*>(p2)), v3 = __ldcs(reinterpret_cast<const float2*>(p3));
-      yreg[s][0] = v0.x; yreg[s][1] = v1.x; yreg[s][2] = v0.y; yreg[s][3] = v1.y;
-      yreg[s][4] = v2.x; yreg[s][5] = v3.x; yreg[s][6] = v2.y; yreg[s][7] = v3.y;
+      const YT* p0 = ybase + (int64_t)(gblk + 2 * c) * ld + (nw + 16 * s + 2 * r);
+      const YT* p1 = p0 + ld;
+      const YT* p2 = p0 + ld8;
+      const YT* p3 = p2 + ld;
+      y_load2<YT>(p0, yreg[s][0], yreg[s][2]); y_load2<YT>(p1, yreg[s][1], yreg[s][3]);
+      y_load2<YT>(p2, yreg[s][4], yreg[s][6]); y_load2<YT>(p3, yreg[s][5], yreg[s][7]);
       return;
     }
     // ragged block / gathered columns: four clamped row pointers
-    const float* rowp[4];
+    const YT* rowp[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int g = min(gblk + 8 * (j >> 1) + 2 * c + (j & 1), g_end - 1);
@@ -886,10 +908,10 @@ __global__ void __launch_bounds__(P4_THREADS, 2) poisson_kernel4(const PoissonAr
     }
     if (!HAS_IDX && block_full) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) yreg[s][q] = __ldcs(rowp[2 * (q >> 2) + (q & 1)] + (nw + 16 * s + 2 * r) + ((q >> 1) & 1));
+      for (int q = 0; q < 8; ++q) yreg[s][q] = y_load1<YT>(rowp[2 * (q >> 2) + (q & 1)] + (nw + 16 * s + 2 * r) + ((q >> 1) & 1));
     } else {
 #pragma unroll
-      for (int q = 0; q < 8; ++q) yreg[s][q] = __ldcs(rowp[2 * (q >> 2) + (q & 1)] + col[s][(q >> 1) & 1]);
+      for (int q = 0; q < 8; ++q) yreg[s][q] = y_load1<YT>(rowp[2 * (q >> 2) + (q & 1)] + col[s][(q >> 1) & 1]);
     }
   };
 #pragma unroll
@@ -1250,9 +1272,11 @@ static size_t poisson_ws_bytes(int G, int F, int B, int E, bool is_f32, size_t e
   return b;
 }
 
+// y_kind: element type of y — 0 = T (the reference's format), 1 = uint8, 2 = int16, 3 = int32 (fp32 tensor-core kernel only)
 template <typename T>
-int poisson_fwdbwd(PoissonArgs<T> a, T* gW, double* ll_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+int poisson_fwdbwd(PoissonArgs<T> a, T* gW, double* ll_out, void* ws, size_t ws_bytes, cudaStream_t st, int y_kind = 0) {
   if (a.F < 1 || a.F > 32 || a.E < 1 || a.G < 1) return GPZ_ERR_UNSUPPORTED;
+  if (y_kind < 0 || y_kind > 3 || (y_kind != 0 && !poisson_use_v4(a.F, std::is_same<T, float>::value))) return GPZ_ERR_UNSUPPORTED;
   if (a.B == 0) {                       // empty minibatch: ll = 0, no gradient
     GPZ_CUDA(cudaMemsetAsync(ll_out, 0, sizeof(double), st));
     GPZ_CUDA(cudaMemsetAsync(gW, 0, sizeof(T) * (size_t)a.G * a.F, st));
@@ -1289,8 +1313,16 @@ int poisson_fwdbwd(PoissonArgs<T> a, T* gW, double* ll_out, void* ws, size_t ws_
       w.ticket = reinterpret_cast<unsigned int*>(p4);
       poisson_prep4_kernel<<<nby + a.E * spot_blocks, 256, 0, st>>>(a, w, nby, spot_blocks);
       GPZ_CHECK_LAUNCH();
-      if (a.idx) poisson_kernel4<true><<<grid, P4_THREADS, 0, st>>>(a, w);
-      else poisson_kernel4<false><<<grid, P4_THREADS, 0, st>>>(a, w);
+#define GPZ_P4_LAUNCH(YT)                                                              \
+  do {                                                                                 \
+    if (a.idx) poisson_kernel4<true, YT><<<grid, P4_THREADS, 0, st>>>(a, w);           \
+    else poisson_kernel4<false, YT><<<grid, P4_THREADS, 0, st>>>(a, w);                \
+  } while (0)
+      if (y_kind == 1) GPZ_P4_LAUNCH(uint8_t);
+      else if (y_kind == 2) GPZ_P4_LAUNCH(int16_t);
+      else if (y_kind == 3) GPZ_P4_LAUNCH(int32_t);
+      else GPZ_P4_LAUNCH(float);
+#undef GPZ_P4_LAUNCH
       GPZ_CHECK_LAUNCH();
       poisson_post4_kernel<<<gw_blocks + spot_blocks, 256, 0, st>>>(a, w, gW, nbx, nby, gw_blocks, spot_blocks, ll_out);
       GPZ_CHECK_LAUNCH();
@@ -1376,3 +1408,15 @@ using namespace gpz;
 
 GPZ_POISSON_IMPL(f32, float)
 GPZ_POISSON_IMPL(f64, double)
+
+// counts stored as uint8 / int16 / int32 (y_kind 1 / 2 / 3; 0 = float): same outputs and workspace as gpz_poisson_fwdbwd_f32
+extern "C" int gpz_poisson_fwdbwd_yt_f32(const void* y, int y_kind, int64_t y_ld, const int64_t* idx, const float* W, int w_softplus,
+                                         const float* V, const float* mean, const float* spread, const float* eps, int G, int F, int B,
+                                         int E, int n_var, float clamp_min, int with_lgamma, double* ll, float* gW, float* gV,
+                                         float* gmean, float* gspread, void* ws, int64_t ws_bytes, void* stream) {
+  PoissonArgs<float> a;
+  a.y = reinterpret_cast<const float*>(y); a.y_ld = y_ld; a.idx = idx; a.W = W; a.w_softplus = w_softplus; a.V = V; a.mean = mean;
+  a.spread = spread; a.eps = eps; a.G = G; a.F = F; a.B = B; a.E = E; a.n_var = n_var; a.clamp_min = clamp_min;
+  a.with_lgamma = with_lgamma; a.gV = gV; a.gmean = gmean; a.gspread = gspread;
+  return poisson_fwdbwd<float>(a, gW, ll, ws, (size_t)ws_bytes, (cudaStream_t)stream, y_kind);
+}

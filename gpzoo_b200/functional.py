@@ -194,6 +194,7 @@ def gemm(A, B, ta=False, tb=False, alpha=1.0, beta=0.0, out=None, a_tri=0, b_tri
     return out
 
 
+POISSON_NARROW_Y = os.environ.get("GPZ_POISSON_V", "4") == "4"     # integer-typed counts are read as stored (K7 tensor-core kernel only)
 GEMM16_MIN_DIM = 2048        # M x M x M products at least this large go to the split-FP16 kernel
 
 
@@ -1073,11 +1074,19 @@ class PoissonLL(Function):
     """mean_E sum_{g,n} Poisson log-lik of y under rate = softplus(V) (w(W) @ exp(mean + eps*sd)),
     with all gradients produced by the same pass (csrc/poisson.cu)."""
 
+    Y_KINDS = {torch.uint8: 1, torch.int16: 2, torch.int32: 3}     # counts stored as integers (gpz_poisson_fwdbwd_yt_f32)
+
     @staticmethod
     def forward(ctx, y, idx, W, V, mean, spread, eps, n_var, clamp_min, w_softplus, with_lgamma):
-        y, W, V, mean, spread, eps = _c(y), _c(W), _c(V), _c(mean), _c(spread), _c(eps)
+        W, V, mean, spread, eps = _c(W), _c(V), _c(mean), _c(spread), _c(eps)
         dt = W.dtype
         G, F = W.shape
+        # y: the reference passes floats; integer counts (uint8 / int16 / int32) are read as stored by the fp32 tensor-core kernel
+        # (F <= 16), any other combination is converted on the device
+        y_kind = PoissonLL.Y_KINDS.get(y.dtype, 0) if (dt == torch.float32 and F <= 16 and POISSON_NARROW_Y) else 0
+        if y_kind == 0 and y.dtype != dt:
+            y = y.to(dt)
+        y = _c(y)
         B = mean.shape[1]
         E = eps.shape[0]
         assert y.shape[0] == G and mean.shape[0] == F and eps.shape[1] == F and eps.shape[2] == B
@@ -1094,9 +1103,13 @@ class PoissonLL(Function):
         gV = torch.empty(B, dtype=dt, device=W.device)
         gmean = torch.empty_like(mean)
         gspread = torch.empty_like(spread)
-        call("poisson_fwdbwd", dt, ptr(y), c_i64(y.shape[1]), ptr(idx), ptr(W), c_i(int(w_softplus)), ptr(V), ptr(mean),
-             ptr(spread), ptr(eps), c_i(G), c_i(F), c_i(B), c_i(E), c_i(int(n_var)), scalar(dt, clamp_min),
-             c_i(int(with_lgamma)), ptr(ll), ptr(gW), ptr(gV), ptr(gmean), ptr(gspread), ptr(ws), c_i64(ws_bytes))
+        tail = (c_i64(y.shape[1]), ptr(idx), ptr(W), c_i(int(w_softplus)), ptr(V), ptr(mean), ptr(spread), ptr(eps), c_i(G), c_i(F),
+                c_i(B), c_i(E), c_i(int(n_var)), scalar(dt, clamp_min), c_i(int(with_lgamma)), ptr(ll), ptr(gW), ptr(gV), ptr(gmean),
+                ptr(gspread), ptr(ws), c_i64(ws_bytes))
+        if y_kind:
+            call("poisson_fwdbwd_yt", dt, ptr(y), c_i(y_kind), *tail)
+        else:
+            call("poisson_fwdbwd", dt, ptr(y), *tail)
         ctx.save_for_backward(gW, gV, gmean, gspread, idx)
         ctx.nV = V.shape[0]
         return ll.to(dt).reshape(())

@@ -191,6 +191,12 @@ int gpz_poisson_fwdbwd_f64(const double* y, int64_t y_ld, const int64_t* idx, co
                            int E, int n_var, double clamp_min, int with_lgamma, double* ll, double* gW, double* gV,
                            double* gmean, double* gspread, void* ws, int64_t ws_bytes, void* stream);
 /* compatibility path: materialise pY.rate (E x G x B) for callers of model.forward() (likelihoods.py:83-85) */
+/* the same with the counts stored as integers: y_kind 1 = uint8, 2 = int16, 3 = int32 (0 = float).  Lossless for count data, a
+ * quarter / half of the HBM traffic and of the host upload.  fp32, F <= 16 (the tensor-core kernel); GPZ_ERR_UNSUPPORTED otherwise. */
+int gpz_poisson_fwdbwd_yt_f32(const void* y, int y_kind, int64_t y_ld, const int64_t* idx, const float* W, int w_softplus, const float* V,
+                              const float* mean, const float* spread, const float* eps, int G, int F, int B, int E, int n_var,
+                              float clamp_min, int with_lgamma, double* ll, float* gW, float* gV, float* gmean, float* gspread,
+                              void* ws, int64_t ws_bytes, void* stream);
 int gpz_poisson_rate_f32(const float* W, int w_softplus, const float* V, const int64_t* idx, const float* F, float* rate,
                          int G, int nF, int B, int E, void* stream);
 int gpz_poisson_rate_f64(const double* W, int w_softplus, const double* V, const int64_t* idx, const double* F, double* rate,

@@ -31,6 +31,21 @@ def test_no_cpu_fallback(lib):
         k(torch.randn(5, 2), torch.randn(3, 2))
 
 
+def test_initialisation_has_no_host_path():
+    """The initialisation pipeline refuses to run without a CUDA device; its pure formulas need none."""
+    import numpy as np
+    from gpzoo_b200 import initialisation as I, utilities as U
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            I.nmf(np.ones((6, 4)), 2)
+        with pytest.raises(RuntimeError):
+            U.regularized_nmf(np.ones((6, 4)), 2)
+    mu, sd = U.lnormal_approx_dirichlet(4)
+    assert abs(mu - (-np.log(4) - (np.log(8) - np.log(5)) / 2)) < 1e-15 and abs(sd - np.sqrt(np.log(8) - np.log(5))) < 1e-15
+    assert set(("regularized_nmf", "shrink_factors", "shrink_loadings", "init_softplus", "rescale_spatial_coords",
+                "build_group_distances", "lnormal_approx_dirichlet")) <= set(dir(U))
+
+
 def test_product_never_imports_oracle():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for dirpath, _, files in os.walk(os.path.join(root, "gpzoo_b200")):

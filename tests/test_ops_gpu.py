@@ -241,6 +241,41 @@ def test_poisson_fused_vs_oracle(dt, case):
     assert relerr(r2, rate) < tol
 
 
+@pytest.mark.parametrize("ydt", [torch.uint8, torch.int16, torch.int32])
+@pytest.mark.parametrize("case", ["full", "idx", "ragged"])
+def test_poisson_integer_counts(ydt, case):
+    """Counts stored as uint8 / int16 / int32 are read as stored (gpz_poisson_fwdbwd_yt_f32): the same numbers as the float-y call."""
+    from gpzoo_b200 import _cabi, functional as F
+    g = torch.Generator().manual_seed(21)
+    G, Fn, E = 77, 6, 2
+    Ntot = {"full": 512, "idx": 400, "ragged": 333}[case]            # 333: odd row length -> the scalar-load path
+    y = torch.poisson(torch.rand(G, Ntot, generator=g) * 3, generator=g)
+    y[3, 5] = 200.0
+    idx = torch.randperm(Ntot, generator=g)[:257].to(DEV) if case == "idx" else None
+    B = Ntot if idx is None else 257
+    W, V = torch.rand(G, Fn, generator=g), 1 + 0.2 * torch.randn(Ntot, generator=g)
+    mean, spread = 0.3 * torch.randn(Fn, B, generator=g), 0.05 + 0.3 * torch.rand(Fn, B, generator=g)
+    eps = torch.randn(E, Fn, B, generator=g)
+
+    def run(yy):
+        lv = [t.clone().to(DEV).requires_grad_(True) for t in (W, V, mean, spread)]
+        _cabi.profile = {}
+        out = F.PoissonLL.apply(yy.to(DEV), idx, lv[0], lv[1], lv[2], lv[3], eps.to(DEV), 3, 5e-2, True, True)
+        calls, _cabi.profile = set(_cabi.profile), None
+        out.backward()
+        return out, [t.grad for t in lv], calls
+    o_f, g_f, c_f = run(y)
+    o_i, g_i, c_i = run(y.to(ydt))
+    assert "poisson_fwdbwd" in c_f and "poisson_fwdbwd_yt" in c_i
+    assert relerr(o_i, o_f) < 1e-7                        # same arithmetic; the D2 atomics over the gene ranges are not ordered
+    for a, b in zip(g_i, g_f):
+        assert relerr(a, b) < 1e-6
+    # and fp64 parameters with integer counts: converted on the device
+    lv = [t.double().to(DEV).requires_grad_(True) for t in (W, V, mean, spread)]
+    o64 = F.PoissonLL.apply(y.to(ydt).to(DEV), idx, lv[0], lv[1], lv[2], lv[3], eps.double().to(DEV), 3, 5e-2, True, True)
+    assert relerr(o_i, o64) < 1e-6
+
+
 @pytest.mark.parametrize("bk", [0, 1])
 def test_umma_gemm_split_tf32(bk):
     """tcgen05/TMA split-TF32 GEMM vs fp64: ragged sizes, batch, triangular skipping, Cin, lo output, split-K."""
