@@ -487,7 +487,7 @@ def run_ours(args):
             assert len(losses) == n and all(v == v for v in losses)
 
         e2e_steps(2)
-        n_e2e = max(2, args.steps // 2)
+        n_e2e = max(2, args.steps)                   # K steps like the device-resident leg (the first upload is exposed: pipeline fill)
         ms_e2e = timed(lambda: e2e_steps(n_e2e), 1) / n_e2e
         del dbuf
 
