@@ -388,6 +388,13 @@ def run_ours(args):
     for _ in range(warm):
         step(st)
     functional.check_cholesky_info()
+    # first pass over the K steps with a CUDA-event pair around every C-ABI call: per-call times for the roofline block.  It runs
+    # BEFORE the headline pass so that one-off host stalls of a young process (allocator growth, NCCL connection set-up: a 60 ms
+    # gap was seen once in the first 20 steps of a 2-rank run with W = 3) land here and not in the headline's 0.1-0.2 s.
+    _cabi.profile = {}
+    timed(lambda: step(st), args.steps)
+    prof, _cabi.profile = _cabi.profile, None
+    functional.check_cholesky_info()
     # A full (generation-2) collection of the CPython garbage collector walks every live object of the interpreter -- about
     # 100 ms with torch imported -- and fires at allocation-count-dependent moments; one inside a 170 ms timed region doubles
     # the reading (seen as 19 ms/step with 100 ms host stalls, tools/ + DESIGN.md section 7).  Freezing moves everything
@@ -402,10 +409,6 @@ def run_ours(args):
     launches = (_cabi.kernel_launches() - k0) // args.steps
     host_enqueue_ms = host_ms[0]
     clocks = sampler.stop() if rank == 0 else None
-    # second pass over the same steps with a CUDA-event pair around every C-ABI call: per-call times for the roofline block
-    _cabi.profile = {}
-    timed(lambda: step(st), args.steps)
-    prof, _cabi.profile = _cabi.profile, None
     functional.check_cholesky_info()
     n_loc = int(st["idx"].numel()) if minibatched else int(st["X"].shape[0])
 
@@ -565,7 +568,9 @@ def run_ours(args):
                              "; backward of the replicated O(M^3) chain sharded by factor (1 all-to-all)" if shard_chain else ""),
                          l2="inputs larger than L2 (y %.0f MB, Kzx planes %.2f GB per GPU)" % (4e-6 * G * n_loc, 4e-9 * L * M * n_loc),
                          e2e="per step: X, y of the rank's spots uploaded from pinned host memory on a copy stream (double buffered) + "
-                             "loss read back to the host with one-step lag"),
+                             "loss read back to the host with one-step lag",
+                         order="W warm-up steps, K steps with per-call CUDA events (per_call_ms / kernels), then the K timed steps of "
+                               "the headline, then the K e2e steps"),
                 clocks=clocks, gpu_launches=int(launches), host_enqueue_ms_per_step=host_enqueue_ms,
                 e2e=(dict(value=((1e3 / ms_e2e) if main_mode == "strong" else world * 1e3 / ms_e2e), unit="steps/s",
                           h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=4) if ms_e2e else None),
