@@ -126,3 +126,25 @@ def test_init_pipeline_golden():
     assert relerr(O.rescale_spatial_coords(t("coords_in")), t("coords_out")) < TOL
     for l, ref in zip((1.1, 4, 10), z["lnormal"]):
         assert np.allclose(O.lnormal_approx_dirichlet(l), ref, rtol=1e-14, atol=1e-14)
+
+
+@pytest.mark.parametrize("solver,beta_loss", [("mu", "kullback-leibler"), ("mu", "frobenius"), ("cd", "frobenius")])
+def test_nmf_oracle_vs_sklearn(solver, beta_loss):
+    """The numpy restatement of sklearn's NMF solvers (the third-party algorithm behind utilities.py:253-299) against sklearn itself,
+    from the same start, including the iteration at which the stopping rule fires."""
+    import warnings
+    from sklearn.decomposition import NMF
+    from oracle import nmf_oracle as NO
+    Y = np.load(GOLDEN + "/init_pipeline.npz")["Y"]
+    rng = np.random.RandomState(7)
+    W0, H0 = np.abs(rng.standard_normal((Y.shape[0], 4))) + 0.1, np.abs(rng.standard_normal((4, Y.shape[1]))) + 0.1
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = NMF(4, init="custom", solver=solver, beta_loss=beta_loss, max_iter=300, tol=1e-4)
+        Wr = m.fit_transform(Y.copy(), W=W0.copy(), H=H0.copy())
+    if solver == "mu":
+        W, H, n = NO.nmf_mu(Y, W0, H0, 1 if beta_loss == "kullback-leibler" else 2, max_iter=300, tol=1e-4)
+    else:
+        W, H, n = NO.nmf_cd(Y, W0, H0, max_iter=300, tol=1e-4)
+    assert n == m.n_iter_
+    assert relerr(W, Wr) < 1e-9 and relerr(H, m.components_) < 1e-9
