@@ -357,6 +357,9 @@ def project_to_inducing(kernel, Z, X, factors, jitter=1e-5):
     (Slideseqv2_estimate_lengthscales.ipynb cell 16: cholesky + cholesky_solve; NSF_Hybrid_benchmark.ipynb cell 11 uses a
     pseudo-inverse for the same product).  kernel: an L-factor gpzoo_b200 kernel; factors: L x N.  -> mu L x M."""
     Zd, was_np = _as_device(Z)
+    par = next(iter(kernel.parameters()), None)
+    if par is not None and par.is_cuda:              # compute in the kernel module's precision, on its device
+        Zd = Zd.to(par.device, par.dtype)
     Xd, _ = _as_device(X, Zd.device, Zd.dtype)
     Fd, _ = _as_device(factors, Zd.device, Zd.dtype)
     with torch.no_grad():
